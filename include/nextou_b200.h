@@ -1,0 +1,144 @@
+/*
+ * nextou_b200 — C-ABI of the B200-native NexToU hot path (libnextou_b200.so).
+ *
+ * The reference (PengchengShi1220/NexToU) has no native code and no FFI: every GPU
+ * instruction is issued by stock PyTorch ATen ops.  This header is therefore the NEW seam
+ * under the reference's Python classes; each entry point names the reference call site
+ * (file:line under /root/reference) whose arithmetic it replaces.
+ *
+ * Conventions
+ *   - extern "C", plain pointers and sizes, no torch types.
+ *   - every function returns 0 on success or a negative nextou_status code; the message
+ *     of the last failure on the calling thread is returned by nextou_last_error().
+ *   - all pointers are DEVICE pointers unless the name ends in _host; the caller allocates
+ *     every input, output and workspace (a *_workspace_bytes query exists where needed).
+ *   - `stream` is a cudaStream_t passed as void*; work is enqueued, never synchronised.
+ *   - dtype codes: NEXTOU_F32 = 0, NEXTOU_BF16 = 1.
+ *   - "token-major" = row per token / voxel, channels contiguous (NDHWC); `ld*` are row
+ *     strides in ELEMENTS.
+ */
+#ifndef NEXTOU_B200_H
+#define NEXTOU_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define NEXTOU_ABI_VERSION 1
+
+enum nextou_status {
+  NEXTOU_OK = 0,
+  NEXTOU_ERR_INVALID = -1,     /* bad argument (shape, alignment, unsupported k, ...) */
+  NEXTOU_ERR_CUDA = -2,        /* a CUDA runtime / driver call failed                */
+  NEXTOU_ERR_UNSUPPORTED = -3, /* valid request this build cannot serve              */
+  NEXTOU_ERR_WORKSPACE = -4    /* workspace too small                                */
+};
+
+enum nextou_dtype { NEXTOU_F32 = 0, NEXTOU_BF16 = 1 };
+
+int nextou_abi_version(void);
+const char* nextou_last_error(void);
+/* number of kernels launched by this library on this process so far (bench.py's gpu_launches) */
+long long nextou_launch_count(void);
+
+/* ------------------------------------------------------------------------------------------
+ * kNN graph build.  Replaces DenseDilatedKnnGraph.forward (network_architecture/torch_edge.py:151-163):
+ * F.normalize (TE:154-160) -> pairwise distance (TE:12-55) -> += relative_pos (TE:79,86,107)
+ * -> topk(-dist, k*dilation) (TE:80,87,108) -> [..., ::dilation] (TE:133).
+ * ------------------------------------------------------------------------------------------ */
+
+/* Step 1: L2-normalise token rows (F.normalize p=2 dim=channels eps=1e-12, TE:154-160) and
+ * transpose to channel-major fp32:  xn[b][c][n] = x[b][n][c] / max(||x[b][n]||, 1e-12),
+ * sq[b][n] = sum_c xn^2.   x: token-major, dtype f32|bf16, row stride ldx, batch stride
+ * x_batch_stride (elements).  If row_map != NULL (int32[B*N]) the source row of (b,n) is
+ * row_map[b*N+n] (absolute row index into x; used to fold torch.roll + window_partition,
+ * NexToU_Encoder_Decoder.py:634-660,784 into the load).  xn: [B][C][ldn], ldn >= N, ldn % 4 == 0.
+ * normalize = 0 skips the division (xn = x, sq = sum_c x^2): dense_knn_matrix called on raw features (TE:58-90). */
+int nextou_knn_normalize(const void* x, int x_dtype, long long ldx, long long x_batch_stride,
+                         const int32_t* row_map, int B, int N, int C, int normalize, float* xn, int ldn,
+                         float* sq, void* stream);
+
+/* Step 2: fused distance tile + running top-k; the N x M distance matrix is never written.
+ *   dist[b][i][j] = (sqx[b][i] + (-2 * dot(xn[b][:,i], yn[b][:,j]))) + sqy[b][j]  (+ relpos[i][j])
+ * out_idx[b][i][0..k) = indices j of the (k*dilation) smallest dist in ascending (dist, j)
+ * order, keeping every dilation-th (TE:133).  relpos is (N, M) fp32 row-major shared by all b,
+ * or NULL.  For the self-graph (TE:58-90) pass yn = xn, sqy = sqx, M = N.
+ * out_idx is int64 [B][N][k] (the dtype torch.topk returns); if out_idx32 != NULL an int32 copy
+ * is written as well (consumed by nextou_mrconv_*).  Requires 1 <= k*dilation <= 32, <= M. */
+int nextou_knn_topk(const float* xn, const float* sqx, int ldn, const float* yn, const float* sqy,
+                    int ldm, const float* relpos, int B, int N, int M, int C, int k, int dilation,
+                    int64_t* out_idx, int32_t* out_idx32, void* stream);
+
+/* ------------------------------------------------------------------------------------------
+ * Max-relative message passing.  Replaces MRConv.forward lines 401-409
+ * (network_architecture/NexToU_Encoder_Decoder.py) and batched_index_select (torch_nn.py:94-115):
+ *   out[row][2c] = x[row][c];  out[row][2c+1] = max_j ( y[nbr(row,j)][c] - x[row][c] )
+ * x, y, out token-major (dtype f32|bf16, same for all three).  idx: int32 [R][k], candidate index LOCAL
+ * to its graph (graph g = r / N owns candidates g*M .. g*M+M-1).  q_row_map / y_row_map (int32 or NULL)
+ * translate "graph-major" query / candidate numbers to physical rows (shifted windows, ED:634-660,784).
+ * arg: uint8 [rows][C] neighbour slot attaining the max (first on ties), consumed by the backward.
+ * ------------------------------------------------------------------------------------------ */
+int nextou_mrconv_gather_fwd(const void* x, long long ldx, const void* y, long long ldy, int dtype, int C,
+                             const int32_t* idx, int k, const int32_t* q_row_map, const int32_t* y_row_map,
+                             long long R, int N, int M, void* out, long long ldo, uint8_t* arg, void* stream);
+/* dx[row][c] += dout[row][2c] - dout[row][2c+1];  dy[nbr(row,arg)][c] += dout[row][2c+1].
+ * dx / dy are fp32 accumulation buffers the caller zero-fills (dy may alias dx for the self graph). */
+int nextou_mrconv_gather_bwd(const void* dout, long long ldo, int dtype, int C, const int32_t* idx, int k,
+                             const uint8_t* arg, const int32_t* q_row_map, const int32_t* y_row_map, long long R,
+                             int N, int M, float* dx, long long lddx, float* dy, long long lddy, void* stream);
+
+/* ------------------------------------------------------------------------------------------
+ * Pool-GNN down / up-sampling on token-major volumes [B*D*H*W][C] (2-D: D = 1, pd = 1).  Replaces
+ * nn.MaxPool3d(return_indices) / nn.MaxUnpool3d / F.avg_pool3d in PoolDyGraphConv.forward
+ * (NexToU_Encoder_Decoder.py:511-512, 524-528, 536-549).  Pools are non-overlapping; `arg` holds the
+ * uint8 child index (dz*ph*pw + dy*pw + dx) of the maximum instead of torch's int64 flat index.
+ * Unpool: output channel j takes the arg of channel j % Carg (indices_cat = cat(indices, indices), ED:536).
+ * ------------------------------------------------------------------------------------------ */
+int nextou_maxpool3d_fwd(const void* x, int dtype, long long ldx, int C, int B, int D, int H, int W, int pd, int ph,
+                         int pw, void* out, long long ldo, uint8_t* arg, void* stream);
+int nextou_maxpool3d_bwd(const void* dout, int dtype, long long ldo, const uint8_t* arg, int C, int B, int D, int H,
+                         int W, int pd, int ph, int pw, void* dx, long long ldx, void* stream);
+int nextou_avgpool3d_fwd(const void* x, int dtype, long long ldx, int C, int B, int D, int H, int W, int pd, int ph,
+                         int pw, void* out, long long ldo, void* stream);
+int nextou_avgpool3d_bwd(const void* dout, int dtype, long long ldo, int C, int B, int D, int H, int W, int pd, int ph,
+                         int pw, void* dx, long long ldx, void* stream);
+int nextou_maxunpool3d_fwd(const void* g, int dtype, long long ldg, const uint8_t* arg, int Carg, int C2, int B, int D,
+                           int H, int W, int pd, int ph, int pw, void* out, long long ldo, void* stream);
+int nextou_maxunpool3d_bwd(const void* dout, int dtype, long long ldo, const uint8_t* arg, int Carg, int C2, int B,
+                           int D, int H, int W, int pd, int ph, int pw, void* dg, long long ldg, void* stream);
+
+/* ------------------------------------------------------------------------------------------
+ * (Binary) topological interaction loss.  Replaces BTI_Loss.forward (loss/bti_loss.py:120-145),
+ * binary_topological_interaction_module (bti_loss.py:76-117) and the TI twins (loss/ti_loss.py).
+ * Logits are addressed as logits[b*stride_b + c*stride_c + v*stride_v] (NCDHW-contiguous and
+ * channels-last both fit); target dtype codes: 0 f32, 1 bf16, 2 i64, 3 u8, 4 i32; <= 32 classes.
+ * ------------------------------------------------------------------------------------------ */
+/* labels[b][v] = argmax_c logits (first maximum; bti_loss.py:132-134); if ce != NULL also the per-voxel
+ * fp64 cross entropy  logsumexp(logits) - logits[target]  (bti_loss.py:141; 0 for out-of-range targets). */
+int nextou_bti_argmax_ce(const void* logits, int dtype, long long stride_b, long long stride_c, long long stride_v,
+                         int B, int NC, long long V, const void* target, int target_code, uint8_t* labels, double* ce,
+                         void* stream);
+/* crit[b][z][y][x] = 1 iff any interaction t is violated:  (dilate(C_t) & A_t) | (dilate(A_t) & C_t), with
+ * A_t / C_t the voxels whose label bit is in mask_a[t] / mask_c[t] (inclusion: C := ~(C|A), bti_loss.py:91-95),
+ * dilation by the 3^d box of radius min_thick (connectivity 26 / 8) or the 6- / 4-cross, zero padded.
+ * The three interaction arrays are HOST pointers (n_inter <= 32 entries). */
+int nextou_bti_critical_map(const uint8_t* labels, int B, int D, int H, int W, int dim, const uint32_t* mask_a_host,
+                            const uint32_t* mask_c_host, const uint8_t* inclusion_host, int n_inter, int connectivity,
+                            int min_thick, uint8_t* crit, void* stream);
+size_t nextou_bti_masked_sum_workspace_bytes(int B);
+/* out[0] = mean_b sum_v ce[b][v] * crit[b][v]  (bti_loss.py:142-143), fp64, fixed summation order. */
+int nextou_bti_masked_sum(const double* ce, const uint8_t* crit, int B, long long V, double* workspace, double* out,
+                          void* stream);
+/* dlogits = crit * grad_out[0] / B * (softmax(logits) - onehot(target)); grad_out is a DEVICE fp64 scalar. */
+int nextou_bti_ce_bwd(const void* logits, int dtype, long long stride_b, long long stride_c, long long stride_v, int B,
+                      int NC, long long V, const void* target, int target_code, const uint8_t* crit,
+                      const double* grad_out, void* dlogits, long long dstride_b, long long dstride_c,
+                      long long dstride_v, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* NEXTOU_B200_H */

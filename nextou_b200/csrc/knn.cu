@@ -1,0 +1,316 @@
+// kNN graph build for the Pool-/Swin-GNN blocks: row normalisation + fused distance-tile / running top-k.
+// Replaces DenseDilatedKnnGraph.forward and the dense_knn_matrix helpers
+// (reference network_architecture/torch_edge.py:12-163).  The N x M distance matrix never
+// leaves the SM: a CTA owns BM query rows, walks the candidates in BN-wide chunks, keeps the
+// fp32 distance tile in shared memory and folds it into a per-row sorted top-32 list with a
+// warp-shuffle bitonic sort + merge.
+//
+// Arithmetic contract (shared with oracle/c/nextou_oracle.c, which it must match BIT FOR BIT):
+//   * sums over channels in the normalise step: lane l accumulates c = l, l+32, ... with fmaf,
+//     then a 16/8/4/2/1 xor-butterfly of plain adds;
+//   * dot(x_i, y_j): one accumulator, acc = fmaf(x[c], y[c], acc) for c = 0..C-1 in order;
+//   * dist = ((sqx_i + (-2*acc)) + sqy_j) + relpos[i][j], each op rounded to fp32 (TE:21-23,86);
+//   * order: ascending (dist, j) — ties go to the lowest candidate index.
+#include "common.cuh"
+#include <limits.h>
+
+namespace nextou {
+
+// ------------------------------------------------------------------------------------------
+// Step 1: normalise rows, transpose to channel-major
+// ------------------------------------------------------------------------------------------
+__device__ __forceinline__ float butterfly_sum(float v) {
+#pragma unroll
+  for (int off = 16; off > 0; off >>= 1) v = __fadd_rn(v, __shfl_xor_sync(0xffffffffu, v, off));
+  return v;
+}
+
+__global__ void __launch_bounds__(256) knn_normalize_kernel(const void* __restrict__ x, int dtype, long long ldx,
+                                                            long long bstride, const int32_t* __restrict__ row_map,
+                                                            int N, int C, int normalize, float* __restrict__ xn,
+                                                            int ldn, float* __restrict__ sq) {
+  extern __shared__ float tile[];  // [32][CS]
+  const int CS = C | 1;            // odd row stride -> conflict-free transposed reads
+  const int b = blockIdx.y;
+  const int n0 = blockIdx.x * 32;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const int r = warp * 4 + i;
+    const int n = n0 + r;
+    float* trow = tile + r * CS;
+    if (n < N) {
+      const long long src = row_map ? (long long)row_map[(long long)b * N + n] * ldx : (long long)b * bstride + (long long)n * ldx;
+      float ss = 0.f;
+      for (int c = lane; c < C; c += 32) {
+        const float v = ld_as_f32(x, dtype, src + c);
+        trow[c] = v;
+        ss = fmaf(v, v, ss);
+      }
+      ss = butterfly_sum(ss);
+      const float denom = fmaxf(sqrtf(ss), 1e-12f);
+      float t = 0.f;
+      for (int c = lane; c < C; c += 32) {
+        const float v = normalize ? __fdiv_rn(trow[c], denom) : trow[c];
+        trow[c] = v;
+        t = fmaf(v, v, t);
+      }
+      t = butterfly_sum(t);
+      if (lane == 0) sq[(long long)b * N + n] = t;
+    } else {
+      for (int c = lane; c < C; c += 32) trow[c] = 0.f;
+    }
+  }
+  __syncthreads();
+  const int n = n0 + lane;
+  if (n < ldn) {
+    for (int c = warp; c < C; c += 8) xn[((long long)b * C + c) * ldn + n] = tile[lane * CS + c];
+  }
+}
+
+// ------------------------------------------------------------------------------------------
+// Step 2: distance tile + running top-k
+// ------------------------------------------------------------------------------------------
+struct Cand {
+  float d;
+  int i;
+};
+__device__ __forceinline__ bool cand_less(float ad, int ai, float bd, int bi) {
+  return (ad < bd) || (ad == bd && ai < bi);
+}
+// one compare-exchange stage of a 32-lane bitonic network
+__device__ __forceinline__ void cmpex(float& d, int& i, int stride, bool keep_min) {
+  const float od = __shfl_xor_sync(0xffffffffu, d, stride);
+  const int oi = __shfl_xor_sync(0xffffffffu, i, stride);
+  const bool other_less = cand_less(od, oi, d, i);
+  const bool take = keep_min ? other_less : !other_less;
+  if (take) {
+    d = od;
+    i = oi;
+  }
+}
+__device__ __forceinline__ void bitonic_sort32(float& d, int& i, int lane) {
+#pragma unroll
+  for (int k2 = 2; k2 <= 32; k2 <<= 1) {
+#pragma unroll
+    for (int s = k2 >> 1; s > 0; s >>= 1) {
+      const bool up = ((lane & k2) == 0);
+      const bool lower = ((lane & s) == 0);
+      cmpex(d, i, s, lower == up);
+    }
+  }
+}
+__device__ __forceinline__ void bitonic_merge32(float& d, int& i, int lane) {
+#pragma unroll
+  for (int s = 16; s > 0; s >>= 1) cmpex(d, i, s, (lane & s) == 0);
+}
+
+constexpr int KNN_KC = 16;
+
+template <int BM, int BN, int TM, int TN>
+struct KnnCfg {
+  static constexpr int TX = BN / TN, TY = BM / TM, NT = TX * TY;
+  static constexpr int DS = BN + 4;  // distance tile row stride (floats)
+  static constexpr size_t smem_bytes =
+      sizeof(float) * (2 * KNN_KC * BM + 2 * KNN_KC * BN + (size_t)BM * DS + (size_t)BM * 32) + sizeof(int) * BM * 32;
+};
+
+template <int BM, int BN, int TM, int TN>
+__global__ void __launch_bounds__(KnnCfg<BM, BN, TM, TN>::NT)
+    knn_topk_kernel(const float* __restrict__ xn, const float* __restrict__ sqx, int ldn,
+                    const float* __restrict__ yn, const float* __restrict__ sqy, int ldm,
+                    const float* __restrict__ relpos, int N, int M, int C, int k, int dilation,
+                    int64_t* __restrict__ out, int32_t* __restrict__ out32) {
+  using Cfg = KnnCfg<BM, BN, TM, TN>;
+  constexpr int KC = KNN_KC, TX = Cfg::TX, TY = Cfg::TY, NT = Cfg::NT, DS = Cfg::DS;
+  extern __shared__ __align__(16) float smem[];
+  float* Xs = smem;                    // [2][KC][BM]
+  float* Ys = Xs + 2 * KC * BM;        // [2][KC][BN]
+  float* Ds = Ys + 2 * KC * BN;        // [BM][DS]
+  float* Ld = Ds + BM * DS;            // [BM][32]
+  int* Li = reinterpret_cast<int*>(Ld + BM * 32);
+
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int tx = tid % TX, ty = tid / TX;
+  const int b = blockIdx.y;
+  const int i0 = blockIdx.x * BM;
+  const int K = k * dilation;
+  const float* xb = xn + (long long)b * C * ldn;
+  const float* yb = yn + (long long)b * C * ldm;
+  const int nslab = (C + KC - 1) / KC;
+
+  for (int t = tid; t < BM * 32; t += NT) {
+    Ld[t] = __int_as_float(0x7f800000);
+    Li[t] = INT_MAX;
+  }
+
+  for (int j0 = 0; j0 < M; j0 += BN) {
+    float acc[TM][TN];
+#pragma unroll
+    for (int i = 0; i < TM; ++i)
+#pragma unroll
+      for (int j = 0; j < TN; ++j) acc[i][j] = 0.f;
+
+    auto load_slab = [&](int s, int buf) {
+      const int c0 = s * KC;
+      for (int g = tid; g < KC * BM / 4; g += NT) {
+        const int kc = g / (BM / 4), q = g % (BM / 4);
+        const int c = c0 + kc, col = i0 + q * 4;
+        const bool ok = (c < C) && (col < ldn);
+        cp_async16(Xs + (buf * KC + kc) * BM + q * 4, ok ? (const void*)(xb + (long long)c * ldn + col) : (const void*)xb, ok);
+      }
+      for (int g = tid; g < KC * BN / 4; g += NT) {
+        const int kc = g / (BN / 4), q = g % (BN / 4);
+        const int c = c0 + kc, col = j0 + q * 4;
+        const bool ok = (c < C) && (col < ldm);
+        cp_async16(Ys + (buf * KC + kc) * BN + q * 4, ok ? (const void*)(yb + (long long)c * ldm + col) : (const void*)yb, ok);
+      }
+      cp_async_commit();
+    };
+
+    load_slab(0, 0);
+    for (int s = 0; s < nslab; ++s) {
+      if (s + 1 < nslab) {
+        load_slab(s + 1, (s + 1) & 1);
+        cp_async_wait<1>();
+      } else {
+        cp_async_wait<0>();
+      }
+      __syncthreads();
+      const float* xs = Xs + (s & 1) * KC * BM;
+      const float* ys = Ys + (s & 1) * KC * BN;
+#pragma unroll
+      for (int kc = 0; kc < KC; ++kc) {
+        float a[TM], bb[TN];
+#pragma unroll
+        for (int g = 0; g < TM / 4; ++g) {
+          const float4 v = *reinterpret_cast<const float4*>(xs + kc * BM + g * 4 * TY + ty * 4);
+          a[g * 4 + 0] = v.x; a[g * 4 + 1] = v.y; a[g * 4 + 2] = v.z; a[g * 4 + 3] = v.w;
+        }
+#pragma unroll
+        for (int g = 0; g < TN / 4; ++g) {
+          const float4 v = *reinterpret_cast<const float4*>(ys + kc * BN + g * 4 * TX + tx * 4);
+          bb[g * 4 + 0] = v.x; bb[g * 4 + 1] = v.y; bb[g * 4 + 2] = v.z; bb[g * 4 + 3] = v.w;
+        }
+#pragma unroll
+        for (int i = 0; i < TM; ++i)
+#pragma unroll
+          for (int j = 0; j < TN; ++j) acc[i][j] = fmaf(a[i], bb[j], acc[i][j]);
+      }
+      __syncthreads();
+    }
+
+    // epilogue: distances -> shared tile
+#pragma unroll
+    for (int i = 0; i < TM; ++i) {
+      const int row = (i / 4) * 4 * TY + ty * 4 + (i % 4);
+      const int gi = i0 + row;
+      const float sx = (gi < N) ? sqx[(long long)b * N + gi] : 0.f;
+#pragma unroll
+      for (int g = 0; g < TN / 4; ++g) {
+        const int col = g * 4 * TX + tx * 4;
+        float dv[4];
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+          const int gj = j0 + col + e;
+          float d = __int_as_float(0x7f800000);
+          if (gi < N && gj < M) {
+            d = __fadd_rn(__fadd_rn(sx, __fmul_rn(-2.f, acc[i][g * 4 + e])), sqy[(long long)b * M + gj]);
+            if (relpos) d = __fadd_rn(d, relpos[(long long)gi * M + gj]);
+          }
+          dv[e] = d;
+        }
+        *reinterpret_cast<float4*>(Ds + row * DS + col) = make_float4(dv[0], dv[1], dv[2], dv[3]);
+      }
+    }
+    __syncthreads();
+
+    // per-row running top-32 (one warp per row, rows strided over the warps)
+    for (int row = warp; row < BM; row += NT / 32) {
+      const int gi = i0 + row;
+      if (gi >= N) continue;
+      float td = Ld[row * 32 + lane];
+      int ti = Li[row * 32 + lane];
+#pragma unroll 1
+      for (int s = 0; s < BN / 32; ++s) {
+        const int gj = j0 + s * 32 + lane;
+        float d = Ds[row * DS + s * 32 + lane];
+        int ci = gj;
+        if (gj >= M) {
+          d = __int_as_float(0x7f800000);
+          ci = INT_MAX;
+        }
+        const float thr = __shfl_sync(0xffffffffu, td, K - 1);
+        if (!__any_sync(0xffffffffu, d < thr)) continue;
+        bitonic_sort32(d, ci, lane);
+        const float rd = __shfl_sync(0xffffffffu, d, 31 - lane);
+        const int ri = __shfl_sync(0xffffffffu, ci, 31 - lane);
+        if (cand_less(rd, ri, td, ti)) {
+          td = rd;
+          ti = ri;
+        }
+        bitonic_merge32(td, ti, lane);
+      }
+      Ld[row * 32 + lane] = td;
+      Li[row * 32 + lane] = ti;
+      if (j0 + BN >= M && lane < K && (lane % dilation) == 0) {
+        const long long o = ((long long)b * N + gi) * k + lane / dilation;
+        out[o] = ti;
+        if (out32) out32[o] = ti;
+      }
+    }
+    __syncthreads();
+  }
+}
+
+template <int BM, int BN, int TM, int TN>
+static int launch_topk(const float* xn, const float* sqx, int ldn, const float* yn, const float* sqy, int ldm,
+                       const float* relpos, int B, int N, int M, int C, int k, int dilation, int64_t* out,
+                       int32_t* out32, cudaStream_t st) {
+  using Cfg = KnnCfg<BM, BN, TM, TN>;
+  auto kern = knn_topk_kernel<BM, BN, TM, TN>;
+  int rc = ensure_smem(kern, Cfg::smem_bytes);
+  if (rc) return rc;
+  dim3 grid((N + BM - 1) / BM, B);
+  kern<<<grid, Cfg::NT, Cfg::smem_bytes, st>>>(xn, sqx, ldn, yn, sqy, ldm, relpos, N, M, C, k, dilation, out, out32);
+  return check_launch("knn_topk_kernel");
+}
+
+}  // namespace nextou
+
+using namespace nextou;
+
+extern "C" int nextou_knn_normalize(const void* x, int x_dtype, long long ldx, long long x_batch_stride,
+                                    const int32_t* row_map, int B, int N, int C, int normalize, float* xn, int ldn,
+                                    float* sq, void* stream) {
+  NEXTOU_REQUIRE(x && xn && sq, "knn_normalize: null pointer");
+  NEXTOU_REQUIRE(B > 0 && N > 0 && C > 0, "knn_normalize: bad shape B=%d N=%d C=%d", B, N, C);
+  NEXTOU_REQUIRE(B <= 65535, "knn_normalize: B=%d > 65535", B);
+  NEXTOU_REQUIRE(ldn >= N && ldn % 4 == 0, "knn_normalize: ldn=%d must be >= N=%d and a multiple of 4", ldn, N);
+  NEXTOU_REQUIRE(x_dtype == NEXTOU_F32 || x_dtype == NEXTOU_BF16, "knn_normalize: bad dtype %d", x_dtype);
+  const size_t smem = sizeof(float) * 32 * (size_t)(C | 1);
+  NEXTOU_REQUIRE(smem <= 200 * 1024, "knn_normalize: C=%d too large", C);
+  int rc = ensure_smem(knn_normalize_kernel, smem);
+  if (rc) return rc;
+  dim3 grid((ldn + 31) / 32, B);
+  knn_normalize_kernel<<<grid, 256, smem, (cudaStream_t)stream>>>(x, x_dtype, ldx, x_batch_stride, row_map, N, C, normalize,
+                                                                 xn, ldn, sq);
+  return check_launch("knn_normalize_kernel");
+}
+
+extern "C" int nextou_knn_topk(const float* xn, const float* sqx, int ldn, const float* yn, const float* sqy, int ldm,
+                               const float* relpos, int B, int N, int M, int C, int k, int dilation, int64_t* out_idx,
+                               int32_t* out_idx32, void* stream) {
+  NEXTOU_REQUIRE(xn && sqx && yn && sqy && out_idx, "knn_topk: null pointer");
+  NEXTOU_REQUIRE(B > 0 && N > 0 && M > 0 && C > 0, "knn_topk: bad shape B=%d N=%d M=%d C=%d", B, N, M, C);
+  NEXTOU_REQUIRE(B <= 65535, "knn_topk: B=%d > 65535", B);
+  NEXTOU_REQUIRE(k >= 1 && dilation >= 1 && k * dilation <= 32, "knn_topk: k*dilation=%d outside [1,32]", k * dilation);
+  NEXTOU_REQUIRE(k * dilation <= M, "knn_topk: k*dilation=%d > M=%d (topk would fail, TE:87)", k * dilation, M);
+  NEXTOU_REQUIRE(ldn >= N && ldn % 4 == 0 && ldm >= M && ldm % 4 == 0, "knn_topk: ldn/ldm must be padded to 4");
+  cudaStream_t st = (cudaStream_t)stream;
+  const long long tiles128 = (long long)((N + 127) / 128) * B;
+  if (tiles128 >= 2LL * num_sms())
+    return launch_topk<128, 128, 8, 8>(xn, sqx, ldn, yn, sqy, ldm, relpos, B, N, M, C, k, dilation, out_idx, out_idx32, st);
+  return launch_topk<64, 128, 4, 8>(xn, sqx, ldn, yn, sqy, ldm, relpos, B, N, M, C, k, dilation, out_idx, out_idx32, st);
+}

@@ -1,0 +1,217 @@
+// Pool-GNN down/up-sampling on token-major (NDHWC) activations.
+// Replaces nn.MaxPool3d(return_indices) / nn.MaxUnpool3d / F.avg_pool3d in PoolDyGraphConv.forward
+// (reference network_architecture/NexToU_Encoder_Decoder.py:511-512, 524-528, 536-549) and their backward.
+// All pools are non-overlapping (kernel == stride).  The arg-max is stored as the uint8 CHILD index
+// (dz*ph*pw + dy*pw + dx) instead of torch's int64 flat voxel index; ties keep the first child in
+// (dz, dy, dx) scan order like ATen's max_pool3d_with_indices.
+// HBM-bound elementwise kernels: one thread per (voxel, channel), channels fastest (coalesced).
+#include "common.cuh"
+
+namespace nextou {
+
+struct PoolGeom {
+  int B, D, H, W, pd, ph, pw, Dp, Hp, Wp;
+};
+
+// pooled voxel p (flat over B,Dp,Hp,Wp) + child index -> flat input voxel
+__device__ __forceinline__ long long child_voxel(const PoolGeom& g, long long p, int child) {
+  const int xw = (int)(p % g.Wp);
+  long long t = p / g.Wp;
+  const int yh = (int)(t % g.Hp);
+  t /= g.Hp;
+  const int zd = (int)(t % g.Dp);
+  const int b = (int)(t / g.Dp);
+  const int dx = child % g.pw, dy = (child / g.pw) % g.ph, dz = child / (g.pw * g.ph);
+  return (((long long)b * g.D + zd * g.pd + dz) * g.H + yh * g.ph + dy) * g.W + xw * g.pw + dx;
+}
+// input voxel v -> pooled voxel + child
+__device__ __forceinline__ void parent_of(const PoolGeom& g, long long v, long long& p, int& child) {
+  const int x = (int)(v % g.W);
+  long long t = v / g.W;
+  const int y = (int)(t % g.H);
+  t /= g.H;
+  const int z = (int)(t % g.D);
+  const int b = (int)(t / g.D);
+  p = (((long long)b * g.Dp + z / g.pd) * g.Hp + y / g.ph) * g.Wp + x / g.pw;
+  child = ((z % g.pd) * g.ph + (y % g.ph)) * g.pw + (x % g.pw);
+}
+
+template <typename T>
+__global__ void maxpool_fwd_kernel(const T* __restrict__ x, long long ldx, int C, PoolGeom g, T* __restrict__ out,
+                                   long long ldo, uint8_t* __restrict__ arg, long long total) {
+  const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= total) return;
+  const int c = (int)(t % C);
+  const long long p = t / C;
+  const int nchild = g.pd * g.ph * g.pw;
+  float best = to_f(x[child_voxel(g, p, 0) * ldx + c]);
+  int bi = 0;
+  for (int ch = 1; ch < nchild; ++ch) {
+    const float v = to_f(x[child_voxel(g, p, ch) * ldx + c]);
+    if (v > best || (v != v && best == best)) {  // NaN propagates like ATen
+      best = v;
+      bi = ch;
+    }
+  }
+  out[p * ldo + c] = from_f<T>(best);
+  arg[p * C + c] = (uint8_t)bi;
+}
+
+template <typename T>
+__global__ void maxpool_bwd_kernel(const T* __restrict__ dout, long long ldo, const uint8_t* __restrict__ arg, int C,
+                                   PoolGeom g, T* __restrict__ dx, long long ldx, long long total) {
+  const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= total) return;
+  const int c = (int)(t % C);
+  const long long v = t / C;
+  long long p;
+  int child;
+  parent_of(g, v, p, child);
+  dx[v * ldx + c] = (arg[p * C + c] == child) ? dout[p * ldo + c] : from_f<T>(0.f);
+}
+
+template <typename T>
+__global__ void avgpool_fwd_kernel(const T* __restrict__ x, long long ldx, int C, PoolGeom g, T* __restrict__ out,
+                                   long long ldo, long long total) {
+  const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= total) return;
+  const int c = (int)(t % C);
+  const long long p = t / C;
+  const int nchild = g.pd * g.ph * g.pw;
+  float s = 0.f;
+  for (int ch = 0; ch < nchild; ++ch) s = __fadd_rn(s, to_f(x[child_voxel(g, p, ch) * ldx + c]));
+  out[p * ldo + c] = from_f<T>(__fdiv_rn(s, (float)nchild));
+}
+
+template <typename T>
+__global__ void avgpool_bwd_kernel(const T* __restrict__ dout, long long ldo, int C, PoolGeom g, T* __restrict__ dx,
+                                   long long ldx, long long total) {
+  const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= total) return;
+  const int c = (int)(t % C);
+  const long long v = t / C;
+  long long p;
+  int child;
+  parent_of(g, v, p, child);
+  dx[v * ldx + c] = from_f<T>(__fdiv_rn(to_f(dout[p * ldo + c]), (float)(g.pd * g.ph * g.pw)));
+}
+
+// unpool: out[v][j] = (arg[parent(v)][j % Carg] == child(v)) ? gsrc[parent(v)][j] : 0      (ED:536-549)
+template <typename T>
+__global__ void maxunpool_fwd_kernel(const T* __restrict__ gsrc, long long ldg, const uint8_t* __restrict__ arg,
+                                     int Carg, int C2, PoolGeom g, T* __restrict__ out, long long ldo,
+                                     long long total) {
+  const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= total) return;
+  const int j = (int)(t % C2);
+  const long long v = t / C2;
+  long long p;
+  int child;
+  parent_of(g, v, p, child);
+  out[v * ldo + j] = (arg[p * Carg + (j % Carg)] == child) ? gsrc[p * ldg + j] : from_f<T>(0.f);
+}
+
+template <typename T>
+__global__ void maxunpool_bwd_kernel(const T* __restrict__ dout, long long ldo, const uint8_t* __restrict__ arg,
+                                     int Carg, int C2, PoolGeom g, T* __restrict__ dg, long long ldg,
+                                     long long total) {
+  const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= total) return;
+  const int j = (int)(t % C2);
+  const long long p = t / C2;
+  const long long v = child_voxel(g, p, arg[p * Carg + (j % Carg)]);
+  dg[p * ldg + j] = dout[v * ldo + j];
+}
+
+static int make_geom(PoolGeom& g, int B, int D, int H, int W, int pd, int ph, int pw) {
+  if (B <= 0 || D <= 0 || H <= 0 || W <= 0 || pd <= 0 || ph <= 0 || pw <= 0) {
+    set_error("pool: bad geometry B=%d D=%d H=%d W=%d p=(%d,%d,%d)", B, D, H, W, pd, ph, pw);
+    return NEXTOU_ERR_INVALID;
+  }
+  if (D % pd || H % ph || W % pw || pd * ph * pw > 255) {
+    set_error("pool: volume (%d,%d,%d) not divisible by pool (%d,%d,%d)", D, H, W, pd, ph, pw);
+    return NEXTOU_ERR_INVALID;
+  }
+  g = PoolGeom{B, D, H, W, pd, ph, pw, D / pd, H / ph, W / pw};
+  return 0;
+}
+
+static inline unsigned blocks_for(long long total) { return (unsigned)((total + 255) / 256); }
+
+}  // namespace nextou
+
+using namespace nextou;
+
+extern "C" int nextou_maxpool3d_fwd(const void* x, int dtype, long long ldx, int C, int B, int D, int H, int W, int pd,
+                                    int ph, int pw, void* out, long long ldo, uint8_t* arg, void* stream) {
+  PoolGeom g;
+  int rc = make_geom(g, B, D, H, W, pd, ph, pw);
+  if (rc) return rc;
+  NEXTOU_REQUIRE(x && out && arg && C > 0, "maxpool3d_fwd: bad args");
+  const long long total = (long long)B * g.Dp * g.Hp * g.Wp * C;
+  DISPATCH_T(dtype, maxpool_fwd_kernel<T><<<blocks_for(total), 256, 0, (cudaStream_t)stream>>>(
+                        (const T*)x, ldx, C, g, (T*)out, ldo, arg, total);)
+  return check_launch("maxpool_fwd_kernel");
+}
+
+extern "C" int nextou_maxpool3d_bwd(const void* dout, int dtype, long long ldo, const uint8_t* arg, int C, int B, int D,
+                                    int H, int W, int pd, int ph, int pw, void* dx, long long ldx, void* stream) {
+  PoolGeom g;
+  int rc = make_geom(g, B, D, H, W, pd, ph, pw);
+  if (rc) return rc;
+  NEXTOU_REQUIRE(dout && dx && arg && C > 0, "maxpool3d_bwd: bad args");
+  const long long total = (long long)B * D * H * W * C;
+  DISPATCH_T(dtype, maxpool_bwd_kernel<T><<<blocks_for(total), 256, 0, (cudaStream_t)stream>>>(
+                        (const T*)dout, ldo, arg, C, g, (T*)dx, ldx, total);)
+  return check_launch("maxpool_bwd_kernel");
+}
+
+extern "C" int nextou_avgpool3d_fwd(const void* x, int dtype, long long ldx, int C, int B, int D, int H, int W, int pd,
+                                    int ph, int pw, void* out, long long ldo, void* stream) {
+  PoolGeom g;
+  int rc = make_geom(g, B, D, H, W, pd, ph, pw);
+  if (rc) return rc;
+  NEXTOU_REQUIRE(x && out && C > 0, "avgpool3d_fwd: bad args");
+  const long long total = (long long)B * g.Dp * g.Hp * g.Wp * C;
+  DISPATCH_T(dtype, avgpool_fwd_kernel<T><<<blocks_for(total), 256, 0, (cudaStream_t)stream>>>(
+                        (const T*)x, ldx, C, g, (T*)out, ldo, total);)
+  return check_launch("avgpool_fwd_kernel");
+}
+
+extern "C" int nextou_avgpool3d_bwd(const void* dout, int dtype, long long ldo, int C, int B, int D, int H, int W,
+                                    int pd, int ph, int pw, void* dx, long long ldx, void* stream) {
+  PoolGeom g;
+  int rc = make_geom(g, B, D, H, W, pd, ph, pw);
+  if (rc) return rc;
+  NEXTOU_REQUIRE(dout && dx && C > 0, "avgpool3d_bwd: bad args");
+  const long long total = (long long)B * D * H * W * C;
+  DISPATCH_T(dtype, avgpool_bwd_kernel<T><<<blocks_for(total), 256, 0, (cudaStream_t)stream>>>(
+                        (const T*)dout, ldo, C, g, (T*)dx, ldx, total);)
+  return check_launch("avgpool_bwd_kernel");
+}
+
+extern "C" int nextou_maxunpool3d_fwd(const void* gsrc, int dtype, long long ldg, const uint8_t* arg, int Carg, int C2,
+                                      int B, int D, int H, int W, int pd, int ph, int pw, void* out, long long ldo,
+                                      void* stream) {
+  PoolGeom g;
+  int rc = make_geom(g, B, D, H, W, pd, ph, pw);
+  if (rc) return rc;
+  NEXTOU_REQUIRE(gsrc && out && arg && Carg > 0 && C2 > 0, "maxunpool3d_fwd: bad args");
+  const long long total = (long long)B * D * H * W * C2;
+  DISPATCH_T(dtype, maxunpool_fwd_kernel<T><<<blocks_for(total), 256, 0, (cudaStream_t)stream>>>(
+                        (const T*)gsrc, ldg, arg, Carg, C2, g, (T*)out, ldo, total);)
+  return check_launch("maxunpool_fwd_kernel");
+}
+
+extern "C" int nextou_maxunpool3d_bwd(const void* dout, int dtype, long long ldo, const uint8_t* arg, int Carg, int C2,
+                                      int B, int D, int H, int W, int pd, int ph, int pw, void* dg, long long ldg,
+                                      void* stream) {
+  PoolGeom g;
+  int rc = make_geom(g, B, D, H, W, pd, ph, pw);
+  if (rc) return rc;
+  NEXTOU_REQUIRE(dout && dg && arg && Carg > 0 && C2 > 0, "maxunpool3d_bwd: bad args");
+  const long long total = (long long)B * g.Dp * g.Hp * g.Wp * C2;
+  DISPATCH_T(dtype, maxunpool_bwd_kernel<T><<<blocks_for(total), 256, 0, (cudaStream_t)stream>>>(
+                        (const T*)dout, ldo, arg, Carg, C2, g, (T*)dg, ldg, total);)
+  return check_launch("maxunpool_bwd_kernel");
+}

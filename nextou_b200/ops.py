@@ -1,0 +1,359 @@
+"""Tensor-level entry points of the CUDA hot path (thin wrappers over the C-ABI, include/nextou_b200.h).
+
+Everything here works on *token-major* 2-D views ``[rows, C]`` (row = voxel / token, channels contiguous,
+``stride(0)`` = row pitch) of channels-last activations; `as_tokens` gives that view without a copy when the
+tensor already is channels-last.  There is no CPU or PyTorch fallback: a non-CUDA tensor or a missing
+``libnextou_b200.so`` raises.
+"""
+from __future__ import annotations
+
+import ctypes
+from typing import Optional, Sequence, Tuple
+
+import torch
+
+from . import _lib
+from ._lib import NextouError, cf, check, cstream, dtype_code, ll, ptr
+
+
+# ----------------------------------------------------------------------------------------------
+# layout helpers
+# ----------------------------------------------------------------------------------------------
+def _need_cuda(*ts):
+    for t in ts:
+        if t is not None and not t.is_cuda:
+            raise NextouError("nextou_b200 ops need CUDA tensors (there is no CPU fallback path)")
+
+
+def channels_last(x: torch.Tensor) -> torch.Tensor:
+    """Return x (N, C, *spatial) in channels-last physical layout (no copy if it already is)."""
+    fmt = torch.channels_last_3d if x.dim() == 5 else torch.channels_last
+    return x.contiguous(memory_format=fmt)
+
+
+def as_tokens(x: torch.Tensor) -> torch.Tensor:
+    """(N, C, *spatial) -> [N*prod(spatial), C] token-major view (copies only if x is not channels-last)."""
+    x = channels_last(x)
+    perm = (0, *range(2, x.dim()), 1)
+    return x.permute(*perm).reshape(-1, x.shape[1])
+
+
+def from_tokens(tok: torch.Tensor, batch: int, spatial: Sequence[int]) -> torch.Tensor:
+    """[rows, C] token-major -> logical (N, C, *spatial) tensor that is physically channels-last (a view)."""
+    C = tok.shape[1]
+    x = tok.reshape(batch, *spatial, C)
+    nd = len(spatial)
+    return x.permute(0, nd + 1, *range(1, nd + 1))
+
+
+def _tok2d(t: torch.Tensor) -> torch.Tensor:
+    if t.dim() != 2 or t.stride(1) != 1:
+        t = t.reshape(-1, t.shape[-1]).contiguous()
+    return t
+
+
+def _work_dtype(t: torch.Tensor) -> torch.Tensor:
+    """fp32 and bf16 are native; fp16 (nnU-Net's default autocast dtype) is widened to bf16-range-safe fp32."""
+    if t.dtype in (torch.float32, torch.bfloat16):
+        return t
+    return t.float()
+
+
+# ----------------------------------------------------------------------------------------------
+# kNN graph  (torch_edge.py:139-163)
+# ----------------------------------------------------------------------------------------------
+def knn_normalize(tok: torch.Tensor, graphs: int, n_per_graph: int, row_map: Optional[torch.Tensor] = None,
+                  normalize: bool = True) -> Tuple[torch.Tensor, torch.Tensor]:
+    """L2-normalise token rows and transpose: returns (xn [graphs, C, ldn] fp32, sq [graphs, n] fp32)."""
+    tok = _tok2d(_work_dtype(tok))
+    _need_cuda(tok, row_map)
+    C = tok.shape[1]
+    ldn = (n_per_graph + 3) // 4 * 4
+    xn = torch.empty((graphs, C, ldn), device=tok.device, dtype=torch.float32)
+    sq = torch.empty((graphs, n_per_graph), device=tok.device, dtype=torch.float32)
+    if row_map is not None:
+        assert row_map.dtype == torch.int32 and row_map.numel() == graphs * n_per_graph
+    else:
+        assert tok.shape[0] == graphs * n_per_graph, (tok.shape, graphs, n_per_graph)
+    check(_lib.lib().nextou_knn_normalize(ptr(tok), dtype_code(tok), ll(tok.stride(0)), ll(n_per_graph * tok.stride(0)),
+                                          ptr(row_map), graphs, n_per_graph, C, int(normalize), ptr(xn), ldn, ptr(sq),
+                                          cstream()),
+          "nextou_knn_normalize")
+    return xn, sq
+
+
+def knn_topk(xn, sqx, yn=None, sqy=None, relpos: Optional[torch.Tensor] = None, k: int = 9, dilation: int = 1,
+             want_i32: bool = True):
+    """Fused distance + top-k.  Returns (idx int64 [graphs, N, k], idx32 int32 or None)."""
+    if yn is None:
+        yn, sqy = xn, sqx
+    _need_cuda(xn, yn, relpos)
+    B, C, ldn = xn.shape
+    N = sqx.shape[1]
+    M = sqy.shape[1]
+    ldm = yn.shape[2]
+    if relpos is not None:
+        relpos = relpos.reshape(-1, relpos.shape[-1])
+        if relpos.shape != (N, M):
+            raise NextouError(f"relative_pos shape {tuple(relpos.shape)} != ({N}, {M})")
+        relpos = relpos.contiguous().float()
+    out = torch.empty((B, N, k), device=xn.device, dtype=torch.int64)
+    out32 = torch.empty((B, N, k), device=xn.device, dtype=torch.int32) if want_i32 else None
+    check(_lib.lib().nextou_knn_topk(ptr(xn), ptr(sqx), ldn, ptr(yn), ptr(sqy), ldm, ptr(relpos), B, N, M, C, k, dilation,
+                                     ptr(out), ptr(out32), cstream()), "nextou_knn_topk")
+    return out, out32
+
+
+def knn_graph(x_tok, graphs: int, n: int, y_tok=None, m: Optional[int] = None, relpos=None, k: int = 9, dilation: int = 1,
+              x_row_map=None, y_row_map=None, normalize: bool = True):
+    """DenseDilatedKnnGraph on token-major inputs (deterministic `[::dilation]` branch, TE:133)."""
+    with torch.no_grad():
+        xn, sqx = knn_normalize(x_tok, graphs, n, x_row_map, normalize)
+        if y_tok is None:
+            return knn_topk(xn, sqx, None, None, relpos, k, dilation)
+        yn, sqy = knn_normalize(y_tok, graphs, m, y_row_map, normalize)
+        return knn_topk(xn, sqx, yn, sqy, relpos, k, dilation)
+
+
+# ----------------------------------------------------------------------------------------------
+# MRConv message passing (NexToU_Encoder_Decoder.py:401-409)
+# ----------------------------------------------------------------------------------------------
+class _MRConvGather(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x_tok, y_tok, idx32, qmap, ymap, n, m):
+        self_graph = y_tok is None
+        x_tok = _tok2d(_work_dtype(x_tok))
+        y2 = x_tok if self_graph else _tok2d(_work_dtype(y_tok)).to(x_tok.dtype)
+        _need_cuda(x_tok, y2, idx32)
+        R = idx32.shape[0] * idx32.shape[1]
+        k = idx32.shape[2]
+        C = x_tok.shape[1]
+        out = torch.empty((x_tok.shape[0], 2 * C), device=x_tok.device, dtype=x_tok.dtype)
+        arg = torch.empty((x_tok.shape[0], C), device=x_tok.device, dtype=torch.uint8)
+        if qmap is None and x_tok.shape[0] != R:
+            raise NextouError(f"mrconv: {x_tok.shape[0]} query rows but {R} index rows")
+        check(_lib.lib().nextou_mrconv_gather_fwd(ptr(x_tok), ll(x_tok.stride(0)), ptr(y2), ll(y2.stride(0)),
+                                                  dtype_code(x_tok), C, ptr(idx32), k, ptr(qmap), ptr(ymap), ll(R), n, m,
+                                                  ptr(out), ll(out.stride(0)), ptr(arg), cstream()),
+              "nextou_mrconv_gather_fwd")
+        ctx.save_for_backward(idx32, arg, qmap, ymap)
+        ctx.meta = (n, m, x_tok.shape, None if self_graph else y2.shape, x_tok.dtype)
+        return out
+
+    @staticmethod
+    def backward(ctx, dout):
+        idx32, arg, qmap, ymap = ctx.saved_tensors
+        n, m, xshape, yshape, dt = ctx.meta
+        dout = _tok2d(dout.to(dt))
+        C = xshape[1]
+        dx = torch.zeros(xshape, device=dout.device, dtype=torch.float32)
+        dy = dx if yshape is None else torch.zeros(yshape, device=dout.device, dtype=torch.float32)
+        R = idx32.shape[0] * idx32.shape[1]
+        check(_lib.lib().nextou_mrconv_gather_bwd(ptr(dout), ll(dout.stride(0)), dtype_code(dout), C, ptr(idx32),
+                                                  idx32.shape[2], ptr(arg), ptr(qmap), ptr(ymap), ll(R), n, m, ptr(dx),
+                                                  ll(dx.stride(0)), ptr(dy), ll(dy.stride(0)), cstream()),
+              "nextou_mrconv_gather_bwd")
+        return dx.to(dt), (None if yshape is None else dy.to(dt)), None, None, None, None, None
+
+
+def mrconv_gather(x_tok, idx32, n: int, m: int, y_tok=None, q_row_map=None, y_row_map=None) -> torch.Tensor:
+    """[rows, C] -> [rows, 2C] = interleave(x, max_j(y[nbr_j] - x)).  idx32: int32 [graphs, n, k]."""
+    return _MRConvGather.apply(x_tok, y_tok, idx32.contiguous(), q_row_map, y_row_map, n, m)
+
+
+# ----------------------------------------------------------------------------------------------
+# pooling on token-major volumes (NexToU_Encoder_Decoder.py:511-512, 524-528, 536-549)
+# ----------------------------------------------------------------------------------------------
+def _geom(batch, spatial, pool):
+    sp = list(spatial)
+    pl = list(pool)
+    if len(sp) == 2:
+        sp, pl = [1] + sp, [1] + pl
+    return (batch, *sp, *pl)
+
+
+class _MaxPool(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, tok, batch, spatial, pool):
+        tok = _tok2d(_work_dtype(tok))
+        _need_cuda(tok)
+        B, D, H, W, pd, ph, pw = _geom(batch, spatial, pool)
+        C = tok.shape[1]
+        P = B * (D // pd) * (H // ph) * (W // pw)
+        out = torch.empty((P, C), device=tok.device, dtype=tok.dtype)
+        arg = torch.empty((P, C), device=tok.device, dtype=torch.uint8)
+        check(_lib.lib().nextou_maxpool3d_fwd(ptr(tok), dtype_code(tok), ll(tok.stride(0)), C, B, D, H, W, pd, ph, pw,
+                                              ptr(out), ll(out.stride(0)), ptr(arg), cstream()), "nextou_maxpool3d_fwd")
+        ctx.save_for_backward(arg)
+        ctx.meta = (B, D, H, W, pd, ph, pw, C, tok.dtype)
+        ctx.mark_non_differentiable(arg)
+        return out, arg
+
+    @staticmethod
+    def backward(ctx, dout, _darg):
+        (arg,) = ctx.saved_tensors
+        B, D, H, W, pd, ph, pw, C, dt = ctx.meta
+        dout = _tok2d(dout.to(dt))
+        dx = torch.empty((B * D * H * W, C), device=dout.device, dtype=dt)
+        check(_lib.lib().nextou_maxpool3d_bwd(ptr(dout), dtype_code(dout), ll(dout.stride(0)), ptr(arg), C, B, D, H, W, pd,
+                                              ph, pw, ptr(dx), ll(dx.stride(0)), cstream()), "nextou_maxpool3d_bwd")
+        return dx, None, None, None
+
+
+class _AvgPool(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, tok, batch, spatial, pool):
+        tok = _tok2d(_work_dtype(tok))
+        _need_cuda(tok)
+        B, D, H, W, pd, ph, pw = _geom(batch, spatial, pool)
+        C = tok.shape[1]
+        P = B * (D // pd) * (H // ph) * (W // pw)
+        out = torch.empty((P, C), device=tok.device, dtype=tok.dtype)
+        check(_lib.lib().nextou_avgpool3d_fwd(ptr(tok), dtype_code(tok), ll(tok.stride(0)), C, B, D, H, W, pd, ph, pw,
+                                              ptr(out), ll(out.stride(0)), cstream()), "nextou_avgpool3d_fwd")
+        ctx.meta = (B, D, H, W, pd, ph, pw, C, tok.dtype)
+        return out
+
+    @staticmethod
+    def backward(ctx, dout):
+        B, D, H, W, pd, ph, pw, C, dt = ctx.meta
+        dout = _tok2d(dout.to(dt))
+        dx = torch.empty((B * D * H * W, C), device=dout.device, dtype=dt)
+        check(_lib.lib().nextou_avgpool3d_bwd(ptr(dout), dtype_code(dout), ll(dout.stride(0)), C, B, D, H, W, pd, ph, pw,
+                                              ptr(dx), ll(dx.stride(0)), cstream()), "nextou_avgpool3d_bwd")
+        return dx, None, None, None
+
+
+class _MaxUnpool(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, g, arg, batch, spatial, pool):
+        g = _tok2d(_work_dtype(g))
+        _need_cuda(g, arg)
+        B, D, H, W, pd, ph, pw = _geom(batch, spatial, pool)
+        C2, Carg = g.shape[1], arg.shape[1]
+        out = torch.empty((B * D * H * W, C2), device=g.device, dtype=g.dtype)
+        check(_lib.lib().nextou_maxunpool3d_fwd(ptr(g), dtype_code(g), ll(g.stride(0)), ptr(arg), Carg, C2, B, D, H, W, pd,
+                                                ph, pw, ptr(out), ll(out.stride(0)), cstream()), "nextou_maxunpool3d_fwd")
+        ctx.save_for_backward(arg)
+        ctx.meta = (B, D, H, W, pd, ph, pw, C2, Carg, g.dtype, g.shape[0])
+        return out
+
+    @staticmethod
+    def backward(ctx, dout):
+        (arg,) = ctx.saved_tensors
+        B, D, H, W, pd, ph, pw, C2, Carg, dt, P = ctx.meta
+        dout = _tok2d(dout.to(dt))
+        dg = torch.empty((P, C2), device=dout.device, dtype=dt)
+        check(_lib.lib().nextou_maxunpool3d_bwd(ptr(dout), dtype_code(dout), ll(dout.stride(0)), ptr(arg), Carg, C2, B, D,
+                                                H, W, pd, ph, pw, ptr(dg), ll(dg.stride(0)), cstream()),
+              "nextou_maxunpool3d_bwd")
+        return dg, None, None, None, None
+
+
+def maxpool_tokens(tok, batch, spatial, pool):
+    """Non-overlapping max pool; spatial = full-resolution (D,H,W) or (H,W).  Returns (pooled, uint8 child arg)."""
+    return _MaxPool.apply(tok, batch, tuple(spatial), tuple(pool))
+
+
+def avgpool_tokens(tok, batch, spatial, pool):
+    return _AvgPool.apply(tok, batch, tuple(spatial), tuple(pool))
+
+
+def maxunpool_tokens(g, arg, batch, spatial, pool):
+    """Scatter pooled rows back to full resolution: channel j uses arg[:, j % arg.shape[1]] (ED:536)."""
+    return _MaxUnpool.apply(g, arg, batch, tuple(spatial), tuple(pool))
+
+
+# ----------------------------------------------------------------------------------------------
+# BTI / TI loss (loss/bti_loss.py:76-145)
+# ----------------------------------------------------------------------------------------------
+_TGT_CODE = {torch.float32: 0, torch.bfloat16: 1, torch.int64: 2, torch.uint8: 3, torch.int32: 4}
+
+
+def _prep_logits(x):
+    """logits (b, c, *spatial) -> (tensor, (batch, class, voxel) element strides); copies only if the spatial
+    dims do not flatten to one stride (NCDHW-contiguous and channels-last both flatten)."""
+    x = _work_dtype(x)
+    try:
+        xv = x.view(x.shape[0], x.shape[1], -1)
+    except RuntimeError:
+        x = x.contiguous()
+        xv = x.view(x.shape[0], x.shape[1], -1)
+    return x, tuple(xv.stride())
+
+
+def _prep_target(y):
+    y = y.reshape(y.shape[0], -1)
+    if y.dtype not in _TGT_CODE:
+        y = y.float()
+    return y.contiguous()
+
+
+def bti_labels(logits: torch.Tensor) -> torch.Tensor:
+    """argmax over classes as uint8 (b, *spatial) (bti_loss.py:132-134)."""
+    _need_cuda(logits)
+    x, (sb, sc, sv) = _prep_logits(logits)
+    B, NC = x.shape[:2]
+    V = x[0, 0].numel()
+    labels = torch.empty((B, *x.shape[2:]), device=x.device, dtype=torch.uint8)
+    check(_lib.lib().nextou_bti_argmax_ce(ptr(x), dtype_code(x), ll(sb), ll(sc), ll(sv), B, NC, ll(V), ptr(None), 0,
+                                          ptr(labels), ptr(None), cstream()), "nextou_bti_argmax_ce")
+    return labels
+
+
+def bti_critical_map(labels: torch.Tensor, mask_a, mask_c, inclusion, connectivity: int, min_thick: int = 1) -> torch.Tensor:
+    """uint8 critical-voxel map from uint8 labels (b, *spatial) and the interaction table (host int lists)."""
+    _need_cuda(labels)
+    labels = labels.contiguous()
+    dim = labels.dim() - 1
+    B = labels.shape[0]
+    D, H, W = (1, *labels.shape[1:]) if dim == 2 else labels.shape[1:]
+    n = len(mask_a)
+    A = (ctypes.c_uint32 * max(n, 1))(*[int(v) & 0xFFFFFFFF for v in mask_a])
+    Cm = (ctypes.c_uint32 * max(n, 1))(*[int(v) & 0xFFFFFFFF for v in mask_c])
+    inc = (ctypes.c_uint8 * max(n, 1))(*[1 if v else 0 for v in inclusion])
+    crit = torch.empty_like(labels)
+    check(_lib.lib().nextou_bti_critical_map(ptr(labels), B, D, H, W, dim, A, Cm, inc, n, connectivity, min_thick,
+                                             ptr(crit), cstream()), "nextou_bti_critical_map")
+    return crit
+
+
+class _BTILoss(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, logits, target, table, connectivity, min_thick):
+        _need_cuda(logits, target)
+        x, (sb, sc, sv) = _prep_logits(logits)
+        y = _prep_target(target)
+        B, NC = x.shape[:2]
+        V = x[0, 0].numel()
+        L = _lib.lib()
+        labels = torch.empty((B, *x.shape[2:]), device=x.device, dtype=torch.uint8)
+        ce = torch.empty((B, V), device=x.device, dtype=torch.float64)
+        check(L.nextou_bti_argmax_ce(ptr(x), dtype_code(x), ll(sb), ll(sc), ll(sv), B, NC, ll(V), ptr(y), _TGT_CODE[y.dtype],
+                                     ptr(labels), ptr(ce), cstream()), "nextou_bti_argmax_ce")
+        crit = bti_critical_map(labels, *table, connectivity, min_thick)
+        L.nextou_bti_masked_sum_workspace_bytes.restype = ctypes.c_size_t
+        ws = torch.empty(L.nextou_bti_masked_sum_workspace_bytes(B) // 8, device=x.device, dtype=torch.float64)
+        out = torch.empty((), device=x.device, dtype=torch.float64)
+        check(L.nextou_bti_masked_sum(ptr(ce), ptr(crit), B, ll(V), ptr(ws), ptr(out), cstream()), "nextou_bti_masked_sum")
+        ctx.save_for_backward(x, y, crit)
+        ctx.meta = (sb, sc, sv, B, NC, V, logits.dtype)
+        return out
+
+    @staticmethod
+    def backward(ctx, gout):
+        x, y, crit = ctx.saved_tensors
+        sb, sc, sv, B, NC, V, in_dtype = ctx.meta
+        g = gout.to(torch.float64).contiguous()
+        dx = torch.empty_like(x)  # preserves strides
+        if dx.stride() != x.stride():
+            dx = torch.empty_strided(x.shape, x.stride(), device=x.device, dtype=x.dtype)
+        check(_lib.lib().nextou_bti_ce_bwd(ptr(x), dtype_code(x), ll(sb), ll(sc), ll(sv), B, NC, ll(V), ptr(y),
+                                           _TGT_CODE[y.dtype], ptr(crit), ptr(g), ptr(dx), ll(sb), ll(sc), ll(sv), cstream()),
+              "nextou_bti_ce_bwd")
+        return dx.to(in_dtype), None, None, None, None
+
+
+def bti_loss(logits, target, mask_a, mask_c, inclusion, connectivity: int, min_thick: int = 1) -> torch.Tensor:
+    """fp64 scalar: mean_b sum_v CE(logits, target)[b, v] * critical[b, v]  (bti_loss.py:141-143)."""
+    return _BTILoss.apply(logits, target, (list(mask_a), list(mask_c), list(inclusion)), connectivity, min_thick)

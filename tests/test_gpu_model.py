@@ -1,0 +1,163 @@
+"""GPU parity of the whole network (product modules on CUDA) against the CPU oracle and the reference goldens.
+
+A randomly initialised NexToU is chaotic in its neighbour lists, so whole-network comparisons are teacher-forced:
+the product's own kNN results are recorded per site, VERIFIED against the oracle's fp64 distances (every chosen
+neighbour within 1e-4 of the true k-th distance) and replayed into the oracle forward.
+"""
+import numpy as np
+import pytest
+import torch
+
+from oracle import torch_oracle as TO
+from tests import helpers as H
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda"
+
+
+def _record_graphs(model):
+    from nextou_b200.blocks import PoolGrapher, SwinGrapher
+    rec = []
+
+    def hook(mod, inp, out):
+        rec.append(mod.graph_conv.last_nn_idx.detach().long().cpu())
+
+    hs = [m.register_forward_hook(hook) for m in model.modules() if isinstance(m, (PoolGrapher, SwinGrapher))]
+    return rec, hs
+
+
+@pytest.fixture(autouse=True)
+def _strict_fp32():
+    old = (torch.backends.cudnn.allow_tf32, torch.backends.cuda.matmul.allow_tf32)
+    torch.backends.cudnn.allow_tf32 = False
+    torch.backends.cuda.matmul.allow_tf32 = False
+    yield
+    torch.backends.cudnn.allow_tf32, torch.backends.cuda.matmul.allow_tf32 = old
+
+
+@pytest.mark.parametrize("fname,cfg", [("model_mini3d_reference.npz", H.MINI3D), ("model_mini2d_reference.npz", H.MINI2D)],
+                         ids=["mini3d", "mini2d"])
+def test_model_fp32_forward_backward_vs_oracle(fname, cfg):
+    npz = H.golden_model(fname)
+    model = H.build_product(cfg)
+    H.load_golden_into(model, npz)
+    sd = H.full_state_dict_for_oracle(model)
+    model = model.to(DEV).train()
+    rec, hooks = _record_graphs(model)
+    g = torch.Generator().manual_seed(42)
+    x = torch.randn(1, 1, *cfg["patch"], generator=g)
+    outs = model(x.to(DEV))
+    loss = sum(o.float().mean() for o in outs)
+    loss.backward()
+    for h in hooks:
+        h.remove()
+    n_sites = 2 * (2 * 4 - 1)  # (pool + swin) x (4 encoder + 3 decoder GNN stages)
+    assert len(rec) == n_sites
+
+    for k in sd:
+        if sd[k].dtype.is_floating_point:
+            sd[k].requires_grad_(not k.endswith(("running_mean", "running_var", "relative_pos")))
+    replay = TO.ReplayKnn(rec, tol=1e-4)
+    want = TO.nextou_forward(sd, x, cfg["patch"], cfg["strides"], training=True, knn=replay)
+    assert replay.pos == n_sites
+    for i, (a, b) in enumerate(zip(outs, want)):
+        assert a.shape == b.shape
+        err = (a.detach().float().cpu() - b.detach()).abs().max().item()
+        assert err <= 1e-3 * max(1.0, b.abs().max().item()), (i, err)
+    wl = sum(o.float().mean() for o in want)
+    assert abs(loss.item() - wl.item()) < 1e-4
+    wl.backward()
+    worst = 0.0
+    for name, p in model.named_parameters():
+        if not p.requires_grad or name.startswith("decoder.encoder."):
+            continue
+        gref = sd[name].grad
+        assert p.grad is not None and gref is not None, name
+        scale = gref.abs().max().item() + 1e-7
+        worst = max(worst, (p.grad.float().cpu() - gref).abs().max().item() / scale)
+    assert worst < 2e-2, worst
+    # the golden outputs of the real reference, where its graphs coincide with ours
+    same_graphs = all(torch.equal(a, b) for a, b in zip(rec, H.golden_knn_list(npz)))
+    if same_graphs:
+        for i, o in enumerate(outs):
+            ref = torch.from_numpy(npz[f"out/{i}"])
+            got = o.detach().float().cpu()
+            got = got if got.numel() <= 70000 else got.reshape(-1)[::97]
+            assert torch.allclose(got, ref, rtol=1e-3, atol=2e-3)
+
+
+def test_model_running_stats_and_eval_mode():
+    """BatchNorm running statistics are updated like nn.BatchNorm (momentum 0.1) and eval uses them."""
+    cfg = H.MINI3D
+    npz = H.golden_model("model_mini3d_reference.npz")
+    model = H.build_product(cfg)
+    H.load_golden_into(model, npz)
+    sd0 = H.full_state_dict_for_oracle(model)
+    model = model.to(DEV).train()
+    g = torch.Generator().manual_seed(42)
+    x = torch.randn(1, 1, *cfg["patch"], generator=g)
+    with torch.no_grad():
+        model(x.to(DEV))
+    bn = model.encoder.stages[0][0].convs[0].norm
+    assert int(bn.num_batches_tracked) == 1
+    with torch.no_grad():
+        import torch.nn.functional as F
+        c = F.conv3d(x, sd0["encoder.stages.0.0.convs.0.conv.weight"], sd0["encoder.stages.0.0.convs.0.conv.bias"], padding=(0, 1, 1))
+        mean = c.mean((0, 2, 3, 4))
+        var = c.var((0, 2, 3, 4), unbiased=True)
+    assert torch.allclose(bn.running_mean.cpu(), 0.1 * mean, atol=1e-5)
+    assert torch.allclose(bn.running_var.cpu(), 0.9 + 0.1 * var, atol=1e-5)
+    model.eval()
+    model.decoder.deep_supervision = False
+    with torch.no_grad():
+        y = model(x.to(DEV))
+    assert tuple(y.shape) == (1, cfg["num_classes"], *cfg["patch"])
+
+
+def test_model_bf16_autocast_close_to_fp32_oracle():
+    """bf16 autocast (BASELINE config 2 numerics) against the fp32 oracle, teacher-forced: relative error of the
+    logits stays in the low percent range (bf16 has 8 mantissa bits; ~40 layers)."""
+    cfg = H.MINI3D
+    npz = H.golden_model("model_mini3d_reference.npz")
+    model = H.build_product(cfg)
+    H.load_golden_into(model, npz)
+    sd = H.full_state_dict_for_oracle(model)
+    model = model.to(DEV).train()
+    rec, hooks = _record_graphs(model)
+    g = torch.Generator().manual_seed(42)
+    x = torch.randn(1, 1, *cfg["patch"], generator=g)
+    with torch.autocast("cuda", dtype=torch.bfloat16):
+        outs = model(x.to(DEV))
+    loss = sum(o.float().mean() for o in outs)
+    loss.backward()
+    assert all(torch.isfinite(o).all() for o in outs)
+    replay = TO.ReplayKnn(rec, verify=False)
+    with torch.no_grad():
+        want = TO.nextou_forward(sd, x, cfg["patch"], cfg["strides"], training=True, knn=replay)
+    for a, b in zip(outs, want):
+        rel = (a.float().cpu() - b).norm() / b.norm()
+        assert rel < 0.08, rel
+
+
+def test_full_size_3d_forward_backward_smoke():
+    """3d_fullres_nextou 1 x 1 x 64 x 224 x 192 under bf16 autocast: shapes, finiteness, every trainable
+    parameter receives a gradient, and all 14 kNN sites return valid (in-range, duplicate-free) lists."""
+    cfg = H.FULL3D
+    model = H.build_product(cfg).to(DEV).train()
+    rec, hooks = _record_graphs(model)
+    x = torch.randn(1, 1, *cfg["patch"], device=DEV)
+    with torch.autocast("cuda", dtype=torch.bfloat16):
+        outs = model(x)
+    want_shapes = [(1, 14, 64, 224, 192), (1, 14, 64, 112, 96), (1, 14, 32, 56, 48), (1, 14, 16, 28, 24), (1, 14, 8, 14, 12)]
+    assert [tuple(o.shape) for o in outs] == want_shapes
+    sum(o.float().mean() for o in outs).backward()
+    assert all(torch.isfinite(o).all() for o in outs)
+    missing = [n for n, p in model.named_parameters() if p.requires_grad and p.grad is None]
+    assert not missing, missing[:5]
+    assert len(rec) == 14
+    sizes = {(10752, 14): 168, (168, 7): 168, (10752, 28): 1344, (168, 14): 168, (1344, 32): 1344, (168, 32): 168, (168, 28): 168}
+    for idx in rec:
+        m = sizes[(idx.shape[1], idx.shape[2])]
+        assert int(idx.min()) >= 0 and int(idx.max()) < m
+        srt = idx.sort(-1).values
+        assert bool((srt[..., 1:] != srt[..., :-1]).all())

@@ -1,0 +1,308 @@
+"""GPU parity tests of the CUDA kernels (through the C-ABI) against the CPU oracle and the reference goldens."""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import c_oracle
+from oracle import torch_oracle as TO
+from oracle.make_golden import BTI_CASES, bti_case, bti_interactions
+from tests import helpers as H
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda"
+
+
+# ------------------------------------------------------------------------------------------------
+# kNN: bit-exact vs the plain-C oracle
+# ------------------------------------------------------------------------------------------------
+def _gpu_knn(x, y, relpos, k, d, dtype=torch.float32, normalize=True):
+    from nextou_b200 import ops
+    B, N, C = x.shape
+    xt = x.to(DEV, dtype).reshape(B * N, C)
+    rp = None if relpos is None else relpos.to(DEV)
+    if y is None:
+        idx, idx32 = ops.knn_graph(xt, B, N, relpos=rp, k=k, dilation=d, normalize=normalize)
+    else:
+        M = y.shape[1]
+        idx, idx32 = ops.knn_graph(xt, B, N, y.to(DEV, dtype).reshape(B * M, C), M, relpos=rp, k=k, dilation=d,
+                                   normalize=normalize)
+    assert idx.dtype == torch.int64 and idx32.dtype == torch.int32
+    assert torch.equal(idx, idx32.long())
+    return idx.cpu().numpy()
+
+
+@pytest.mark.parametrize("case", H.KNN_CASES, ids=[c[0] for c in H.KNN_CASES])
+def test_knn_bit_exact_vs_c_oracle(case):
+    name, B, N, M, C, k, d, rp = case
+    x, y, relpos = H.knn_inputs(case)
+    want = c_oracle.knn_graph(x.numpy(), None if y is None else y.numpy(), None if relpos is None else relpos[0].numpy(), k, d)
+    got = _gpu_knn(x, y, relpos, k, d)
+    assert np.array_equal(got, want)
+
+
+def test_knn_reference_golden_tie_aware():
+    """Against the unmodified reference's own index tensors (tests/golden/knn_reference.npz)."""
+    gold = np.load(os.path.join(H.GOLDEN, "knn_reference.npz"))
+    for case in H.KNN_CASES:
+        name, B, N, M, C, k, d, rp = case
+        x, y, relpos = H.knn_inputs(case)
+        got = _gpu_knn(x, y, relpos, k, d)
+        ref = gold[name].astype(np.int64)
+        x4 = x.permute(0, 2, 1).unsqueeze(-1)
+        y4 = None if y is None else y.permute(0, 2, 1).unsqueeze(-1)
+        dist = TO.knn_distances(x4, y4, relpos)
+        for b, i in zip(*np.nonzero((got != ref).any(-1))):
+            dm = dist[b, i, torch.from_numpy(got[b, i])]
+            dr = dist[b, i, torch.from_numpy(ref[b, i])]
+            assert torch.allclose(dm, dr, rtol=0, atol=1e-5), (name, b, i)
+
+
+@pytest.mark.parametrize("shape", [(1, 10752, 1344, 264, 28), (1, 10752, 168, 132, 14), (64, 168, 0, 264, 14)],
+                         ids=["pool_s3_full", "pool_s2_full", "swin_s3_full"])
+def test_knn_full_size_sites_bit_exact(shape):
+    B, N, M, C, k = shape
+    g = torch.Generator().manual_seed(5)
+    x = torch.randn(B, N, C, generator=g)
+    y = torch.randn(B, M, C, generator=g) if M else None
+    relpos = 0.1 * torch.randn(1, N, M or N, generator=g)
+    want = c_oracle.knn_graph(x.numpy(), None if y is None else y.numpy(), relpos[0].numpy(), k, 1)
+    assert np.array_equal(_gpu_knn(x, y, relpos, k, 1), want)
+
+
+def test_knn_bf16_input_unnormalized_and_row_map():
+    from nextou_b200 import ops
+    g = torch.Generator().manual_seed(3)
+    B, N, C, k = 4, 96, 48, 6
+    x = torch.randn(B, N, C, generator=g)
+    xb = x.bfloat16()
+    want = c_oracle.knn_graph(xb.float().numpy(), None, None, k, 1)
+    assert np.array_equal(_gpu_knn(xb, None, None, k, 1, dtype=torch.bfloat16), want)
+    want_raw = c_oracle.knn_graph(x.numpy(), None, None, k, 1, normalize=False)
+    assert np.array_equal(_gpu_knn(x, None, None, k, 1, normalize=False), want_raw)
+    # gather rows through a permutation map
+    perm = torch.randperm(B * N, generator=g)
+    inv = torch.empty_like(perm)
+    inv[perm] = torch.arange(B * N)
+    shuffled = x.reshape(B * N, C)[inv]             # shuffled[perm[r]] = x_flat[r]
+    idx, _ = ops.knn_graph(shuffled.to(DEV), B, N, k=k, x_row_map=perm.to(DEV, torch.int32))
+    assert np.array_equal(idx.cpu().numpy(), c_oracle.knn_graph(x.numpy(), None, None, k, 1))
+
+
+def test_knn_rejects_bad_arguments():
+    from nextou_b200 import ops
+    from nextou_b200._lib import NextouError
+    x = torch.randn(64, 12, device=DEV)
+    with pytest.raises(NextouError):
+        ops.knn_graph(x, 1, 64, k=33)            # k*dilation > 32
+    with pytest.raises(NextouError):
+        ops.knn_graph(x, 4, 16, k=9, dilation=2)  # k*dilation > M
+    with pytest.raises(NextouError):
+        ops.knn_graph(x, 1, 64, k=4, relpos=torch.zeros(1, 64, 32, device=DEV))
+
+
+def test_dense_dilated_knn_graph_module_api():
+    """Drop-in module: (B, C, N, 1) in, (2, B, N, k) int64 edge_index out (TE:139-163)."""
+    from nextou_b200.graph import DenseDilatedKnnGraph, dense_knn_matrix, xy_dense_knn_matrix
+    case = H.KNN_CASES[1]
+    name, B, N, M, C, k, d, rp = case
+    x, y, relpos = H.knn_inputs(case)
+    x4 = x.permute(0, 2, 1).unsqueeze(-1).contiguous().to(DEV)
+    y4 = y.permute(0, 2, 1).unsqueeze(-1).contiguous().to(DEV)
+    mod = DenseDilatedKnnGraph(k, d, stochastic=False, epsilon=0.0).to(DEV)
+    e = mod(x4, y4, relpos.to(DEV))
+    assert e.shape == (2, B, N, k) and e.dtype == torch.int64
+    want = c_oracle.knn_graph(x.numpy(), y.numpy(), relpos[0].numpy(), k, d)
+    assert np.array_equal(e[0].cpu().numpy(), want)
+    assert torch.equal(e[1].cpu(), torch.arange(N).view(1, N, 1).expand(B, N, k))
+    # un-normalised helpers (TE:58-110)
+    e2 = xy_dense_knn_matrix(x4, y4, k, relpos.to(DEV))
+    assert np.array_equal(e2[0].cpu().numpy(), c_oracle.knn_graph(x.numpy(), y.numpy(), relpos[0].numpy(), k, 1, normalize=False))
+    e3 = dense_knn_matrix(x4, k)
+    assert np.array_equal(e3[0].cpu().numpy(), c_oracle.knn_graph(x.numpy(), None, None, k, 1, normalize=False))
+    # stochastic branch consumes the host RNG exactly like the reference (TE:128-130)
+    torch.manual_seed(11)
+    smod = DenseDilatedKnnGraph(k, d, stochastic=True, epsilon=0.2).to(DEV).train()
+    smod(x4, y4, relpos.to(DEV))
+    after = torch.rand(1)
+    torch.manual_seed(11)
+    if torch.rand(1) < 0.2:
+        torch.randperm(k * d)
+    assert torch.equal(after, torch.rand(1))
+
+
+# ------------------------------------------------------------------------------------------------
+# message passing
+# ------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("dtype,tol", [(torch.float32, 0.0), (torch.bfloat16, 0.0)], ids=["f32", "bf16"])
+@pytest.mark.parametrize("self_graph", [True, False], ids=["self", "xy"])
+def test_mrconv_gather_forward_backward(dtype, tol, self_graph):
+    from nextou_b200 import ops
+    g = torch.Generator().manual_seed(9)
+    B, N, M, C, k = 3, 168, (168 if self_graph else 40), 132, 7
+    x = torch.randn(B, N, C, generator=g).to(dtype)
+    y = None if self_graph else torch.randn(B, M, C, generator=g).to(dtype)
+    idx = torch.randint(0, M, (B, N, k), generator=g)
+    xg = x.to(DEV).reshape(B * N, C).requires_grad_(True)
+    yg = None if y is None else y.to(DEV).reshape(B * M, C).requires_grad_(True)
+    out = ops.mrconv_gather(xg, idx.to(DEV, torch.int32), N, M, y_tok=yg)
+    # oracle in the reference layout (B, C, N, 1)
+    xo = x.float().permute(0, 2, 1).unsqueeze(-1).requires_grad_(True)
+    yo = None if y is None else y.float().permute(0, 2, 1).unsqueeze(-1).requires_grad_(True)
+    want = TO.max_relative(xo, idx, yo)                                     # (B, 2C, N, 1)
+    want_tok = want.squeeze(-1).permute(0, 2, 1).reshape(B * N, 2 * C)
+    assert out.dtype == dtype
+    assert torch.equal(out.float().cpu(), want_tok.to(dtype).float())       # exact (max of rounded == rounded max)
+    w = torch.randn(B * N, 2 * C, generator=g)
+    (out.float() * w.to(DEV)).sum().backward()
+    (want_tok * w).sum().backward()
+    gx = xo.grad.squeeze(-1).permute(0, 2, 1).reshape(B * N, C)
+    atol = 1e-5 if dtype == torch.float32 else 0.15
+    if dtype == torch.float32:
+        assert torch.allclose(xg.grad.cpu(), gx, rtol=1e-5, atol=atol)
+        if yo is not None:
+            gy = yo.grad.squeeze(-1).permute(0, 2, 1).reshape(B * M, C)
+            assert torch.allclose(yg.grad.cpu(), gy, rtol=1e-5, atol=atol)
+    else:  # bf16: ties in the max are frequent and may route the gradient to another (equally maximal) neighbour;
+        # the total is conserved: sum(dx) + sum(dy) == sum of the upstream gradient over the x-channels
+        tot = xg.grad.float().sum() + (0 if yg is None else yg.grad.float().sum())
+        assert abs(tot.item() - w[:, 0::2].sum().item()) < 8.0
+
+
+def test_mrconv_gather_row_maps_equal_window_partition():
+    """Shifted windows through row maps == roll + partition + gather + reverse + roll of the reference."""
+    from nextou_b200 import ops
+    from nextou_b200.blocks import shifted_window_row_map
+    g = torch.Generator().manual_seed(2)
+    B, C, S, ws, sh, k = 2, 12, (4, 6, 8), (2, 3, 4), (1, 1, 2), 3
+    x = torch.randn(B, C, *S, generator=g)
+    n = int(np.prod(ws))
+    nW = B * int(np.prod(S)) // n
+    idx = torch.randint(0, n, (nW, n, k), generator=g)
+    rolled = torch.roll(x, shifts=tuple(-s for s in sh), dims=(2, 3, 4))
+    win = TO._windows(rolled, ws).reshape(nW, C, n, 1)
+    want_w = TO.max_relative(win, idx).reshape(nW, 2 * C, *ws)
+    want = torch.roll(TO._unwindows(want_w, ws, B, S), shifts=sh, dims=(2, 3, 4))
+    tok = ops.as_tokens(x.to(DEV))
+    rm = shifted_window_row_map(B, S, ws, sh, DEV)
+    out = ops.mrconv_gather(tok, idx.to(DEV, torch.int32), n, n, q_row_map=rm, y_row_map=rm)
+    got = ops.from_tokens(out, B, S)
+    assert torch.equal(got.cpu(), want)
+
+
+# ------------------------------------------------------------------------------------------------
+# pooling
+# ------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16], ids=["f32", "bf16"])
+@pytest.mark.parametrize("spatial,pool", [((8, 12, 10), (2, 2, 2)), ((6, 9, 8), (1, 3, 2)), ((12, 16), (2, 2)), ((8, 8, 8), (4, 4, 4))])
+def test_pool_unpool_forward_backward(dtype, spatial, pool):
+    import torch.nn.functional as F
+    from nextou_b200 import ops
+    g = torch.Generator().manual_seed(4)
+    B, C = 2, 12
+    dim = len(spatial)
+    x = torch.randn(B, C, *spatial, generator=g).to(dtype)
+    mp, ap, up = (F.max_pool3d, F.avg_pool3d, F.max_unpool3d) if dim == 3 else (F.max_pool2d, F.avg_pool2d, F.max_unpool2d)
+    xo = x.float().requires_grad_(True)
+    xg = x.to(DEV).requires_grad_(True)
+    tok = ops.as_tokens(xg)
+    pooled_spatial = tuple(s // p for s, p in zip(spatial, pool))
+    # max pool
+    q, arg = ops.maxpool_tokens(tok, B, spatial, pool)
+    qo, ind = mp(xo, pool, pool, return_indices=True)
+    assert torch.equal(ops.from_tokens(q, B, pooled_spatial).float().cpu(), qo.to(dtype).float())
+    # avg pool
+    a = ops.avgpool_tokens(tok, B, spatial, pool)
+    ao = ap(xo, pool, pool)
+    assert torch.allclose(ops.from_tokens(a, B, pooled_spatial).float().cpu(), ao.to(dtype).float(), rtol=1e-6, atol=1e-6)
+    # unpool of a 2C tensor with the duplicated indices (ED:536-549)
+    f = torch.randn(B, 2 * C, *pooled_spatial, generator=g).to(dtype)
+    fo = f.float().requires_grad_(True)
+    fg = f.to(DEV).requires_grad_(True)
+    u = ops.maxunpool_tokens(ops.as_tokens(fg), arg, B, spatial, pool)
+    uo = up(fo, torch.cat((ind, ind), 1), pool, pool)
+    assert torch.equal(ops.from_tokens(u, B, spatial).float().cpu(), uo.to(dtype).float())
+    # backward of everything at once
+    w1 = torch.randn(qo.shape, generator=g)
+    w2 = torch.randn(ao.shape, generator=g)
+    w3 = torch.randn(uo.shape, generator=g)
+    ((qo * w1).sum() + (ao * w2).sum() + (uo * w3).sum()).backward()
+    loss = (ops.from_tokens(q, B, pooled_spatial).float() * w1.to(DEV)).sum() \
+        + (ops.from_tokens(a, B, pooled_spatial).float() * w2.to(DEV)).sum() \
+        + (ops.from_tokens(u, B, spatial).float() * w3.to(DEV)).sum()
+    loss.backward()
+    tol = dict(rtol=1e-5, atol=1e-5) if dtype == torch.float32 else dict(rtol=2e-2, atol=2e-2)
+    assert torch.allclose(xg.grad.float().cpu(), xo.grad, **tol)
+    assert torch.allclose(fg.grad.float().cpu(), fo.grad, **tol)
+
+
+# ------------------------------------------------------------------------------------------------
+# BTI / TI loss
+# ------------------------------------------------------------------------------------------------
+@pytest.fixture(scope="module")
+def bti_gold():
+    return np.load(os.path.join(H.GOLDEN, "bti_reference.npz"))
+
+
+@pytest.mark.parametrize("case", BTI_CASES, ids=[c[0] for c in BTI_CASES])
+@pytest.mark.parametrize("layout", ["ncdhw", "channels_last"])
+def test_bti_loss_matches_reference_golden_and_oracle(case, layout, bti_gold):
+    from nextou_b200 import ops
+    from nextou_b200.losses import BTI_Loss, TI_Loss
+    name, shape, nc, seed, conn, thick, kind = case
+    logits, target = bti_case(shape, nc, seed)
+    inc, exc = bti_interactions(kind, nc)
+    dim = len(shape) - 1
+    lg = logits.to(DEV)
+    if layout == "channels_last":
+        lg = ops.channels_last(lg)
+    lg.requires_grad_(True)
+    mod = BTI_Loss(dim=dim, connectivity=conn, inclusion=inc, exclusion=exc, min_thick=thick)
+    val = mod(lg, target.to(DEV))
+    assert val.dtype == torch.float64 and val.dim() == 0
+    ref = float(bti_gold[f"{name}.bti.loss"])
+    assert abs(val.item() - ref) <= 1e-9 * max(1.0, abs(ref))               # fp64 scalar vs the reference
+    labels = ops.bti_labels(lg.detach())
+    assert np.array_equal(labels.cpu().numpy(), logits.argmax(1).numpy().astype(np.uint8))
+    crit = mod.binary_topological_interaction_module(labels.unsqueeze(1))
+    ref_crit = np.unpackbits(bti_gold[f"{name}.bti.crit"])[: labels.numel()].reshape(labels.shape)
+    assert np.array_equal(crit[:, 0].cpu().numpy().astype(np.uint8), ref_crit)  # bit-exact critical map
+    (val * 3.0).backward()
+    gr = lg.grad.double().cpu() / 3.0
+    assert abs(gr.sum().item() - float(bti_gold[f"{name}.bti.grad_sum"])) < 1e-3
+    assert abs(gr.abs().sum().item() - float(bti_gold[f"{name}.bti.grad_abs_sum"])) < 1e-4 * float(bti_gold[f"{name}.bti.grad_abs_sum"]) + 1e-6
+    probe = gr.reshape(-1)[:: max(1, gr.numel() // 4096)].float().numpy()
+    assert np.allclose(probe, bti_gold[f"{name}.bti.grad_probe"], rtol=1e-5, atol=1e-6)
+    if kind == "pairs":
+        ti = TI_Loss(dim=dim, connectivity=conn, inclusion=inc, exclusion=exc, min_thick=thick)
+        tv = ti(logits.to(DEV), target.to(DEV))
+        assert abs(tv.item() - float(bti_gold[f"{name}.ti.loss"])) <= 1e-9 * max(1.0, abs(ref))
+
+
+def test_bti_full_size_properties():
+    """BASELINE config 4 size (14 x 64 x 224 x 192): map vs the C oracle bit-exact, loss vs the torch oracle, plus
+    size-independent properties: swapping A and C leaves the map unchanged; a constant label volume has no
+    critical voxel; the loss is linear in the batch mean."""
+    from nextou_b200 import ops
+    from nextou_b200.losses import BTI_Loss
+    from oracle.ref_shims import SYNAPSE_EXCLUSION, make_tensors
+    exc = make_tensors(SYNAPSE_EXCLUSION)
+    shape = (1, 64, 224, 192)
+    logits, target = bti_case(shape, 14, 21)
+    mod = BTI_Loss(dim=3, connectivity=26, inclusion=[], exclusion=exc, min_thick=1)
+    lg = logits.to(DEV).bfloat16()
+    val = mod(lg, target.to(DEV))
+    labels = ops.bti_labels(lg)
+    lab_cpu = lg.float().cpu().argmax(1)
+    assert np.array_equal(labels.cpu().numpy(), lab_cpu.numpy().astype(np.uint8))
+    ma, mc, flags = mod.interaction_table()
+    crit = ops.bti_critical_map(labels, ma, mc, flags, 26, 1)
+    want = c_oracle.bti_critical(lab_cpu.numpy().astype(np.uint8), ma, mc, flags, 26, 1)
+    assert np.array_equal(crit.cpu().numpy(), want)
+    ref = TO.bti_loss(lg.float().cpu(), target, [], exc, 3, 26, 1)
+    assert abs(val.item() - ref.item()) <= 1e-9 * abs(ref.item())
+    swapped = ops.bti_critical_map(labels, mc, ma, flags, 26, 1)
+    assert torch.equal(swapped, crit)
+    const = ops.bti_critical_map(torch.full_like(labels, 3), ma, mc, flags, 26, 1)
+    assert int(const.sum()) == 0
