@@ -1,0 +1,317 @@
+#!/usr/bin/env python
+"""Benchmark of the NexToU hot path: training steps/s on 3d_fullres_nextou (1 x 1 x 64 x 224 x 192 per GPU).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl own|reference]
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node N --master-addr 127.0.0.1 --master-port P \
+        bench.py --gpus N --steps K --warmup W
+
+A "step" = one training step on one synthetic patch per GPU: forward (bf16 autocast) -> deep-supervision
+Dice + CE + BTI loss -> backward -> (N > 1: NCCL all-reduce of the gradients) -> clip 12 -> SGD-Nesterov update.
+`value` = patches/s over all GPUs with the batch resident in HBM; `e2e` = the same step fed from pinned host
+memory (H2D of input + targets every step, D2H read of the loss).  Rank 0 prints ONE JSON line.
+
+`--impl reference` times the reference's own CPU implementation of the path (the torch-CPU oracle port of the
+reference model + loss: the reference itself is Python and cannot travel to the GPU box) on all host threads.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+import numpy as np
+import torch
+
+CFG = dict(patch=(64, 224, 192), feats=(33, 66, 132, 264, 324, 324), num_classes=14,
+           strides=[[1, 1, 1], [1, 2, 2]] + [[2, 2, 2]] * 4, kernels=[[1, 3, 3]] + [[3, 3, 3]] * 5)
+SYNAPSE_EXCLUSION = [[[1, 3, 5, 7, 8, 11, 13], [2, 4, 6, 9, 10, 12]], [[1, 3, 11, 13], [5, 7, 8]], [[1, 3], [11, 13]],
+                     [1, 3], [11, 13], [[5, 8], [7]], [5, 8], [[4, 6, 10], [2, 9, 12]], [[4, 6], [10]], [4, 6],
+                     [[9, 12], [2]], [9, 12]]
+METRIC = "patches/sec 3d_fullres_nextou 64x224x192 fwd+bwd"
+WORKLOAD = "3d_fullres_nextou 1x1x64x224x192 per GPU, 33->324 feats, 14 classes, bf16 autocast, train step"
+
+
+def make_tensors(lists):
+    if not lists:
+        return lists
+    if isinstance(lists[0], list):
+        return [make_tensors(s) for s in lists]
+    return torch.tensor(lists)
+
+
+def synthetic_batch(seed: int):
+    """Input volume + deep-supervision label maps (blocky synthetic organs so the BTI critical set is boundary-like)."""
+    g = torch.Generator().manual_seed(seed)
+    x = torch.randn(1, 1, *CFG["patch"], generator=g)
+    coarse = torch.randint(0, CFG["num_classes"], (1, 1, 8, 14, 12), generator=g).float()
+    full = torch.nn.functional.interpolate(coarse, size=CFG["patch"], mode="nearest")
+    targets = []
+    shape = list(CFG["patch"])
+    for i, st in enumerate(CFG["strides"][:-1]):
+        shape = [a // b for a, b in zip(shape, st)]
+        targets.append(torch.nn.functional.interpolate(full, size=shape, mode="nearest").contiguous())
+    return x, targets
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled every 200 ms during the timed region."""
+    Q = "clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown," \
+        "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
+
+    def __init__(self, index: int):
+        self.index, self.rows, self.proc = index, [], None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), f"--query-gpu={self.Q}",
+                                          "--format=csv,noheader,nounits", "-lms", "200"], stdout=subprocess.PIPE,
+                                         stderr=subprocess.DEVNULL, text=True)
+            threading.Thread(target=self._read, daemon=True).start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.split(",")])
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        time.sleep(0.05)
+        sm = [float(r[0]) for r in self.rows if len(r) >= 7 and r[0].replace(".", "").isdigit()]
+        mx = [float(r[1]) for r in self.rows if len(r) >= 7 and r[1].replace(".", "").isdigit()]
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = [n for j, n in enumerate(names) if any(len(r) >= 7 and r[3 + j].lower().startswith("active") for r in self.rows)]
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": reasons, "samples": len(sm)}
+
+
+# ------------------------------------------------------------------------------------------------------
+# reference arm: the reference's CPU implementation (oracle port), all host threads
+# ------------------------------------------------------------------------------------------------------
+def cpu_reference_step(sd, x, targets, exclusion, TO):
+    for v in sd.values():
+        if v.grad is not None:
+            v.grad = None
+    outs = TO.nextou_forward(sd, x, CFG["patch"], CFG["strides"], training=True)
+    loss = TO.training_loss(outs, targets, exclusion)
+    loss.backward()
+    return float(loss)
+
+
+def build_cpu_reference():
+    from oracle import torch_oracle as TO
+    from tests import helpers as H
+    model = H.build_product(CFG)          # parameter container only: init + state_dict layout; never run on CPU
+    sd = {k: v.detach().clone() for k, v in model.state_dict().items()}
+    for k, v in sd.items():
+        if v.dtype.is_floating_point and not k.endswith(("running_mean", "running_var", "relative_pos")):
+            v.requires_grad_(True)
+    return TO, sd
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    TO, sd = build_cpu_reference()
+    x, targets = synthetic_batch(0)
+    exclusion = make_tensors(SYNAPSE_EXCLUSION)
+    budget_s = 170.0
+    t0 = time.time()
+    cpu_reference_step(sd, x, targets, exclusion, TO)       # warm-up (also calibrates the step time)
+    first = time.time() - t0
+    n_timed = int(max(1, min(args.steps, (budget_s - first) // max(first, 1e-3))))
+    t0 = time.time()
+    for _ in range(n_timed):
+        cpu_reference_step(sd, x, targets, exclusion, TO)
+    dt = (time.time() - t0) / n_timed
+    val = 1.0 / dt
+    sample = f"{n_timed} full training step(s) of the {args.steps} requested (1 warm-up), full 64x224x192 patch, " \
+             f"fp32, torch {torch.__version__} CPU, {cores} threads; bounded to ~3 min of CPU time"
+    line = {"impl": "reference", "metric": METRIC, "value": val, "unit": "patches/s", "n_gpus": args.gpus,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": dt * 1e3, "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": WORKLOAD, "device": "host CPU"},
+            "cpu_baseline": {"value": val, "unit": "patches/s", "cores": cores, "kind": "port", "sample": sample},
+            "e2e": {"value": val, "unit": "patches/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    print(json.dumps(line), flush=True)
+
+
+# ------------------------------------------------------------------------------------------------------
+# own arm
+# ------------------------------------------------------------------------------------------------------
+def run_own(args):
+    import torch.distributed as dist
+    from nextou_b200 import _lib, dense
+    from nextou_b200.losses import DC_and_CE_and_BTI_Loss, DeepSupervisionWrapper, MemoryEfficientSoftDiceLoss
+    from nextou_b200.parallel import GradientAllReducer
+    from tests import helpers as H
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    assert torch.cuda.is_available(), "bench.py needs a CUDA device (there is no CPU fallback for the product path)"
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    _lib.lib()  # fail loudly if the CUDA library is missing
+
+    model = H.build_product(CFG, seed=0).to(dev).train()
+    exclusion = make_tensors(SYNAPSE_EXCLUSION)
+    exclusion_dev = [[e.to(dev) for e in p] if isinstance(p, list) else p.to(dev) for p in exclusion]
+    inner = DC_and_CE_and_BTI_Loss({"batch_dice": True, "smooth": 1e-5, "do_bg": False, "ddp": world > 1}, {},
+                                   {"dim": 3, "connectivity": 26, "inclusion": [], "exclusion": exclusion_dev, "min_thick": 1},
+                                   weight_ce=1, weight_dice=1, weight_ti=1e-6, ignore_label=None,
+                                   dice_class=MemoryEfficientSoftDiceLoss)
+    w = np.array([1 / (2 ** i) for i in range(5)])
+    w[-1] = 0
+    loss_fn = DeepSupervisionWrapper(inner, (w / w.sum()).tolist())
+    params = [p for p in model.parameters() if p.requires_grad]
+    opt = torch.optim.SGD(params, lr=1e-2, momentum=0.99, nesterov=True, weight_decay=3e-5)
+    reducer = GradientAllReducer(params, world) if world > 1 else None
+
+    x_host, t_host = synthetic_batch(rank)
+    x_host = x_host.pin_memory()
+    t_host = [t.pin_memory() for t in t_host]
+    x_dev = x_host.to(dev, non_blocking=True)
+    t_dev = [t.to(dev, non_blocking=True) for t in t_host]
+    h2d = x_host.numel() * 4 + sum(t.numel() * 4 for t in t_host)
+
+    def step(x, targets):
+        if reducer is not None:
+            reducer.zero_grad()           # gradients live in flat NCCL buckets (views)
+        else:
+            opt.zero_grad(set_to_none=True)
+        with torch.autocast("cuda", dtype=torch.bfloat16):
+            outs = model(x)
+            loss = loss_fn(outs, targets)
+        loss.backward()
+        if reducer is not None:
+            reducer.all_reduce()
+        torch.nn.utils.clip_grad_norm_(params, 12)
+        opt.step()
+        return loss
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for _ in range(max(args.warmup, 3)):
+        step(x_dev, t_dev)
+    barrier()
+
+    # ---- device-resident timing (value) -------------------------------------------------------------
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    _lib.KernelTimers.enabled = {"knn_topk"}
+    _lib.KernelTimers.reset()
+    dense.stats.clear()
+    launches0 = _lib.launch_count()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    e0.record()
+    for _ in range(args.steps):
+        step(x_dev, t_dev)
+    e1.record()
+    barrier()
+    ms = e0.elapsed_time(e1)
+    launches = _lib.launch_count() - launches0
+    lib_calls = dict(dense.stats)
+    ktimes = _lib.KernelTimers.summary()
+    _lib.KernelTimers.enabled = set()
+    clocks = sampler.stop() if rank == 0 else None
+
+    # ---- end-to-end timing (host buffers, H2D + D2H inside the timed region) -------------------------
+    barrier()
+    f0, f1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    f0.record()
+    last = 0.0
+    for _ in range(args.steps):
+        xd = x_host.to(dev, non_blocking=True)
+        td = [t.to(dev, non_blocking=True) for t in t_host]
+        last = step(xd, td).item()          # D2H read of the loss
+    f1.record()
+    barrier()
+    ms_e2e = f0.elapsed_time(f1)
+
+    if world > 1:
+        t = torch.tensor([ms, ms_e2e], device=dev, dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms, ms_e2e = float(t[0]), float(t[1])
+
+    if rank == 0:
+        peaks = {}
+        pk_path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+        if os.path.exists(pk_path):
+            peaks = json.load(open(pk_path))
+        hbm_peak = float(peaks.get("hbm_gbs", 6650.0))
+        kt = ktimes.get("knn_topk", dict(launches=0, ms=0.0, bytes=0, flops=0))
+        per_launch_ms = kt["ms"] / max(kt["launches"], 1)
+        achieved = (kt["bytes"] / max(kt["launches"], 1)) / 1e9 / max(per_launch_ms * 1e-3, 1e-12)
+        roofline = {"kernel": "knn_topk_kernel (fused distance + top-k, csrc/knn.cu)", "bound": "hbm",
+                    "achieved": achieved, "peak": hbm_peak, "unit": "GB/s", "frac": achieved / hbm_peak,
+                    "traffic": None, "peak_source": "measured (MEASURED_PEAKS.json)" if peaks else "fallback",
+                    "launches_timed": kt["launches"], "avg_launch_ms": per_launch_ms,
+                    "share_of_step": kt["ms"] / max(ms, 1e-9),
+                    "fp32_tflops_achieved": kt["flops"] / 1e12 / max(kt["ms"] * 1e-3, 1e-12),
+                    "note": "fp32-FMA distances (bit-exact contract) make this kernel FMA-bound, not HBM-bound; "
+                            "the step itself is dominated by cuDNN conv kernels (library) until csrc/conv lands"}
+        line = {"metric": METRIC, "value": world * args.steps / (ms * 1e-3), "unit": "patches/s", "n_gpus": world,
+                "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": ms / args.steps,
+                "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
+                "config": {"workload": WORKLOAD, "global_batch": world, "parallelism": f"dp{world}",
+                           "loss": "DeepSupervision(Dice+CE+1e-6*BTI, Synapse interactions)",
+                           "optimizer": "SGD nesterov 0.99, clip 12",
+                           "l2": "no flush needed: per-step working set (activations, several GB) >> 126 MB L2",
+                           "library_calls_per_step": {k: v / args.steps for k, v in lib_calls.items()}},
+                "clocks": clocks,
+                "e2e": {"value": world * args.steps / (ms_e2e * 1e-3), "unit": "patches/s", "h2d_bytes_per_step": h2d,
+                        "d2h_bytes_per_step": 8, "ms_per_step": ms_e2e / args.steps, "last_loss": last},
+                "gpu_launches": launches, "roofline": roofline}
+        if world == 1 and not args.no_cpu_baseline:
+            cores = os.cpu_count() or 1
+            torch.set_num_threads(cores)
+            TO, sd = build_cpu_reference()
+            xs, ts = synthetic_batch(0)
+            t0 = time.time()
+            cpu_reference_step(sd, xs, ts, exclusion, TO)
+            dt = time.time() - t0
+            line["cpu_baseline"] = {"value": 1.0 / dt, "unit": "patches/s", "cores": cores, "kind": "port",
+                                    "sample": "1 full training step (fwd + Dice/CE/BTI loss + bwd) of the torch-CPU oracle "
+                                              "port on the full 64x224x192 patch, fp32, no warm-up"}
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="own", choices=["own", "reference"])
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_own(args)
+
+
+if __name__ == "__main__":
+    main()

@@ -41,6 +41,46 @@ def launch_count() -> int:
     return int(lib().nextou_launch_count())
 
 
+class KernelTimers:
+    """Optional CUDA-event timing of selected kernel families on the launching stream (bench.py's roofline leg).
+    Disabled (zero overhead) unless a family name is put into `enabled`."""
+    enabled: set = set()
+    records: dict = {}
+
+    @classmethod
+    def reset(cls):
+        cls.records = {}
+
+    @classmethod
+    def summary(cls):
+        """name -> dict(launches, ms, bytes, flops); call after torch.cuda.synchronize()."""
+        out = {}
+        for name, recs in cls.records.items():
+            ms = sum(a.elapsed_time(b) for a, b, _, _ in recs)
+            out[name] = dict(launches=len(recs), ms=ms, bytes=sum(r[2] for r in recs), flops=sum(r[3] for r in recs))
+        return out
+
+
+class timed:
+    def __init__(self, name, nbytes=0, flops=0):
+        self.on = name in KernelTimers.enabled
+        self.name, self.nbytes, self.flops = name, nbytes, flops
+
+    def __enter__(self):
+        if self.on:
+            import torch
+            self.e0 = torch.cuda.Event(enable_timing=True)
+            self.e1 = torch.cuda.Event(enable_timing=True)
+            self.e0.record()
+        return self
+
+    def __exit__(self, *exc):
+        if self.on:
+            self.e1.record()
+            KernelTimers.records.setdefault(self.name, []).append((self.e0, self.e1, self.nbytes, self.flops))
+        return False
+
+
 def ptr(t):
     """Device pointer of a torch tensor (or NULL)."""
     return ctypes.c_void_p(t.data_ptr()) if t is not None else ctypes.c_void_p(0)

@@ -99,8 +99,11 @@ def knn_topk(xn, sqx, yn=None, sqy=None, relpos: Optional[torch.Tensor] = None, 
         relpos = relpos.contiguous().float()
     out = torch.empty((B, N, k), device=xn.device, dtype=torch.int64)
     out32 = torch.empty((B, N, k), device=xn.device, dtype=torch.int32) if want_i32 else None
-    check(_lib.lib().nextou_knn_topk(ptr(xn), ptr(sqx), ldn, ptr(yn), ptr(sqy), ldm, ptr(relpos), B, N, M, C, k, dilation,
-                                     ptr(out), ptr(out32), cstream()), "nextou_knn_topk")
+    # algorithmic traffic / work of this launch: operands once + relpos once + int64 indices
+    nbytes = 4 * B * C * (N + (M if yn is not xn else 0)) + (4 * N * M if relpos is not None else 0) + 8 * B * N * k
+    with _lib.timed("knn_topk", nbytes, 2 * B * N * M * C):
+        check(_lib.lib().nextou_knn_topk(ptr(xn), ptr(sqx), ldn, ptr(yn), ptr(sqy), ldm, ptr(relpos), B, N, M, C, k,
+                                         dilation, ptr(out), ptr(out32), cstream()), "nextou_knn_topk")
     return out, out32
 
 

@@ -1,0 +1,90 @@
+"""Data-parallel plumbing: one process per GPU, one patch per rank, gradients averaged over NCCL / NVLink.
+
+The reference has no collective code of its own: it inherits nnU-Net's DistributedDataParallel.
+The path shards by independent patches, so the only exchange step is the gradient all-reduce, done here with
+`GradientAllReducer`: gradients live permanently inside a few flat fp32 buckets (param.grad are views), each bucket
+is all-reduced asynchronously as soon as autograd has produced all of its gradients (reverse registration order
+~ backward order: decoder first), so the transfer of bucket i overlaps the backward compute of bucket i+1, and
+no copy into / out of communication buffers ever happens.
+"""
+from __future__ import annotations
+
+from typing import Iterable, List
+
+import torch
+import torch.distributed as dist
+
+
+class GradientAllReducer:
+    def __init__(self, params: Iterable[torch.nn.Parameter], world_size: int, bucket_mb: float = 32.0,
+                 overlap: bool = True):
+        self.world = world_size
+        self.params: List[torch.nn.Parameter] = [p for p in params if p.requires_grad]
+        self.overlap = overlap and world_size > 1
+        cap = int(bucket_mb * 1024 * 1024 // 4)
+        order = list(reversed(self.params))                 # backward produces the last layers' gradients first
+        self.buckets: List[torch.Tensor] = []
+        self._bucket_of = {}
+        self._slices = {}
+        cur, cur_n = [], 0
+        groups = []
+        for p in order:
+            if cur and cur_n + p.numel() > cap:
+                groups.append(cur)
+                cur, cur_n = [], 0
+            cur.append(p)
+            cur_n += p.numel()
+        if cur:
+            groups.append(cur)
+        for b, grp in enumerate(groups):
+            n = sum(p.numel() for p in grp)
+            flat = torch.zeros(n, device=grp[0].device, dtype=torch.float32)
+            off = 0
+            for p in grp:
+                self._bucket_of[p] = b
+                self._slices[p] = (off, off + p.numel())
+                off += p.numel()
+            self.buckets.append(flat)
+        self._pending = [0] * len(self.buckets)
+        self._sizes = [len(g) for g in groups]
+        self._handles = []
+        self.attach()
+        if self.overlap:
+            for p in self.params:
+                p.register_post_accumulate_grad_hook(self._on_grad_ready)
+
+    def attach(self):
+        """(Re)bind every param.grad to its slice of the flat buckets."""
+        for p in self.params:
+            a, b = self._slices[p]
+            p.grad = self.buckets[self._bucket_of[p]][a:b].view_as(p)
+
+    def zero_grad(self):
+        for flat in self.buckets:
+            flat.zero_()
+        self.attach()
+        self._pending = [0] * len(self.buckets)
+        self._handles = []
+
+    def _on_grad_ready(self, p):
+        b = self._bucket_of[p]
+        self._pending[b] += 1
+        if self._pending[b] == self._sizes[b]:
+            self._handles.append(dist.all_reduce(self.buckets[b], op=dist.ReduceOp.SUM, async_op=True))
+
+    def all_reduce(self):
+        """Finish the step's gradient exchange: afterwards every param.grad holds the mean over ranks."""
+        if self.world <= 1:
+            return
+        launched = len(self._handles)
+        if not self.overlap or launched != len(self.buckets):
+            # parameters without a gradient this step (or overlap disabled): reduce what has not been launched
+            done = {i for i in range(len(self.buckets)) if self.overlap and self._pending[i] == self._sizes[i]}
+            for i, flat in enumerate(self.buckets):
+                if i not in done:
+                    self._handles.append(dist.all_reduce(flat, op=dist.ReduceOp.SUM, async_op=True))
+        for h in self._handles:
+            h.wait()
+        self._handles = []
+        self._pending = [0] * len(self.buckets)
+        torch._foreach_mul_(self.buckets, 1.0 / self.world)

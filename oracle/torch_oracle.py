@@ -370,7 +370,43 @@ class ReplayKnn:
 def knn_excess(x, y, relpos, idx, k, dilation=1) -> float:
     """max over rows of (largest chosen distance - true (k*dilation)-th smallest distance), fp64; <= 0 up to ties.
     Only meaningful for dilation == 1 (a dilated list skips neighbours by construction)."""
-    d = knn_distances(x, y, relpos)
-    kth = d.kthvalue(k * dilation, dim=-1).values
-    chosen = d.gather(-1, idx.long()).max(-1).values
-    return float((chosen - kth).max())
+    with torch.no_grad():
+        d = knn_distances(x, y, relpos)
+        kth = d.kthvalue(k * dilation, dim=-1).values
+        chosen = d.gather(-1, idx.long()).max(-1).values
+        return float((chosen - kth).max())
+
+
+# ----------------------------------------------------------------------------------------------------
+# training loss of the reference trainers (…_BTI_Synapse.py:17-64; compound_bti_loss.py:33-61): deep-supervision
+# weighted sum of CE + soft Dice (batch_dice, no background, smooth 1e-5 — upstream nnU-Net semantics, parity
+# unpinned) + 1e-6 * BTI.  Used for the CPU baseline arm of bench.py.
+# ----------------------------------------------------------------------------------------------------
+def soft_dice_loss(logits, target, smooth=1e-5):
+    p = torch.softmax(logits, 1)
+    axes = tuple(range(2, p.ndim))
+    with torch.no_grad():
+        onehot = torch.zeros_like(p, dtype=torch.bool).scatter_(1, target.long(), 1)[:, 1:]
+        sum_gt = onehot.sum(axes).sum(0)
+    p = p[:, 1:]
+    inter = (p * onehot).sum(axes).sum(0)
+    sum_pred = p.sum(axes).sum(0)
+    return -((2 * inter + smooth) / torch.clip(sum_gt + sum_pred + smooth, 1e-8)).mean()
+
+
+def deep_supervision_weights(n_outputs: int):
+    w = np.array([1 / (2 ** i) for i in range(n_outputs)])
+    w[-1] = 0
+    return (w / w.sum()).tolist()
+
+
+def training_loss(outs, targets, exclusion, inclusion=(), dim=3, connectivity=26, weight_ti=1e-6):
+    total = 0
+    for w, o, t in zip(deep_supervision_weights(len(outs)), outs, targets):
+        if w == 0:
+            continue
+        ce = F.cross_entropy(o, t[:, 0].long())
+        dc = soft_dice_loss(o, t)
+        ti = bti_loss(o, t, list(inclusion), exclusion, dim, connectivity, 1)
+        total = total + w * (ce + dc + weight_ti * ti)
+    return total

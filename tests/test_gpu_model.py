@@ -60,10 +60,15 @@ def test_model_fp32_forward_backward_vs_oracle(fname, cfg):
     replay = TO.ReplayKnn(rec, tol=1e-4)
     want = TO.nextou_forward(sd, x, cfg["patch"], cfg["strides"], training=True, knn=replay)
     assert replay.pos == n_sites
+    # Per-module parity is 1e-5 (test_every_module_fp32_vs_oracle).  End to end a few voxels differ more: besides the
+    # neighbour lists the network has other discrete choices (arg-max of the 2x2x2 max-pool decides WHERE max-unpool
+    # writes, ED:524-549), which flip on 1e-7 differences.  So: relative L2 error and a bound on the outlier fraction.
     for i, (a, b) in enumerate(zip(outs, want)):
         assert a.shape == b.shape
-        err = (a.detach().float().cpu() - b.detach()).abs().max().item()
-        assert err <= 1e-3 * max(1.0, b.abs().max().item()), (i, err)
+        diff = (a.detach().float().cpu() - b.detach()).abs()
+        rel = (diff.norm() / b.detach().norm()).item()
+        frac = (diff > 1e-3 * max(1.0, b.abs().max().item())).float().mean().item()
+        assert rel <= 2e-4 and frac <= 1e-3, (i, rel, frac, diff.max().item())
     wl = sum(o.float().mean() for o in want)
     assert abs(loss.item() - wl.item()) < 1e-4
     wl.backward()
@@ -73,9 +78,8 @@ def test_model_fp32_forward_backward_vs_oracle(fname, cfg):
             continue
         gref = sd[name].grad
         assert p.grad is not None and gref is not None, name
-        scale = gref.abs().max().item() + 1e-7
-        worst = max(worst, (p.grad.float().cpu() - gref).abs().max().item() / scale)
-    assert worst < 2e-2, worst
+        worst = max(worst, ((p.grad.float().cpu() - gref).norm() / (gref.norm() + 1e-12)).item())
+    assert worst < 2e-2, worst  # relative L2 per parameter tensor
     # the golden outputs of the real reference, where its graphs coincide with ours
     same_graphs = all(torch.equal(a, b) for a, b in zip(rec, H.golden_knn_list(npz)))
     if same_graphs:
@@ -84,6 +88,50 @@ def test_model_fp32_forward_backward_vs_oracle(fname, cfg):
             got = o.detach().float().cpu()
             got = got if got.numel() <= 70000 else got.reshape(-1)[::97]
             assert torch.allclose(got, ref, rtol=1e-3, atol=2e-3)
+
+
+@pytest.mark.parametrize("fname,cfg", [("model_mini3d_reference.npz", H.MINI3D), ("model_mini2d_reference.npz", H.MINI2D)],
+                         ids=["mini3d", "mini2d"])
+def test_every_module_fp32_vs_oracle(fname, cfg):
+    """Each conv stack / PoolGrapher / SwinGrapher / FFN of the network, fed the SAME input as the oracle:
+    |err| <= 1e-5 * max(1, max|ref|)  (north-star fp32 tolerance), kNN lists exactly optimal (excess 0)."""
+    from nextou_b200.blocks import FFN, PoolGrapher, SwinGrapher
+    from nextou_b200.conv_blocks import StackedConvBlocks
+    npz = H.golden_model(fname)
+    model = H.build_product(cfg)
+    H.load_golden_into(model, npz)
+    sd = H.full_state_dict_for_oracle(model)
+    model = model.to(DEV).train()
+    dim = len(cfg["patch"])
+    plan = TO.derive_plan(cfg["patch"], cfg["strides"])
+    caps = []
+    for name, mod in model.named_modules():
+        if not name.startswith("decoder.encoder") and isinstance(mod, (PoolGrapher, SwinGrapher, FFN, StackedConvBlocks)):
+            mod.register_forward_hook(lambda m, i, o, name=name: caps.append((name, m, i[0].detach(), o.detach(),
+                                      getattr(getattr(m, "graph_conv", None), "last_nn_idx", None))))
+    g = torch.Generator().manual_seed(42)
+    x = torch.randn(1, 1, *cfg["patch"], generator=g)
+    with torch.no_grad():
+        model(x.to(DEV))
+    assert len(caps) >= 35
+    for name, mod, inp, out, idx in caps:
+        xin = inp.float().cpu()
+        s = int(name.split(".")[2])
+        level = s if name.startswith("encoder") else len(cfg["feats"]) - 2 - s
+        st = plan["stages"][level]
+        with torch.no_grad():
+            if isinstance(mod, (PoolGrapher, SwinGrapher)):
+                rk = TO.ReplayKnn([idx.long().cpu()], tol=1e-6)
+                fn = TO.pool_grapher if isinstance(mod, PoolGrapher) else TO.swin_grapher
+                want = fn(xin, sd, name, dim, st, True, rk)
+            elif isinstance(mod, FFN):
+                want = TO.ffn(xin, sd, name, dim, True)
+            else:
+                want = xin
+                for i in range(len(mod.convs)):
+                    want = TO._conv_block(want, sd, f"{name}.convs.{i}", dim, tuple(mod.convs[i].conv.stride), True)
+        err = (out.float().cpu() - want).abs().max().item()
+        assert err <= 1e-5 * max(1.0, want.abs().max().item()), (name, err)
 
 
 def test_model_running_stats_and_eval_mode():

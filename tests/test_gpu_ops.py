@@ -148,8 +148,8 @@ def test_mrconv_gather_forward_backward(dtype, tol, self_graph):
     yg = None if y is None else y.to(DEV).reshape(B * M, C).requires_grad_(True)
     out = ops.mrconv_gather(xg, idx.to(DEV, torch.int32), N, M, y_tok=yg)
     # oracle in the reference layout (B, C, N, 1)
-    xo = x.float().permute(0, 2, 1).unsqueeze(-1).requires_grad_(True)
-    yo = None if y is None else y.float().permute(0, 2, 1).unsqueeze(-1).requires_grad_(True)
+    xo = x.float().permute(0, 2, 1).unsqueeze(-1).clone().requires_grad_(True)
+    yo = None if y is None else y.float().permute(0, 2, 1).unsqueeze(-1).clone().requires_grad_(True)
     want = TO.max_relative(xo, idx, yo)                                     # (B, 2C, N, 1)
     want_tok = want.squeeze(-1).permute(0, 2, 1).reshape(B * N, 2 * C)
     assert out.dtype == dtype
@@ -204,8 +204,8 @@ def test_pool_unpool_forward_backward(dtype, spatial, pool):
     dim = len(spatial)
     x = torch.randn(B, C, *spatial, generator=g).to(dtype)
     mp, ap, up = (F.max_pool3d, F.avg_pool3d, F.max_unpool3d) if dim == 3 else (F.max_pool2d, F.avg_pool2d, F.max_unpool2d)
-    xo = x.float().requires_grad_(True)
-    xg = x.to(DEV).requires_grad_(True)
+    xo = x.float().clone().requires_grad_(True)
+    xg = x.clone().to(DEV).requires_grad_(True)
     tok = ops.as_tokens(xg)
     pooled_spatial = tuple(s // p for s, p in zip(spatial, pool))
     # max pool
@@ -218,8 +218,8 @@ def test_pool_unpool_forward_backward(dtype, spatial, pool):
     assert torch.allclose(ops.from_tokens(a, B, pooled_spatial).float().cpu(), ao.to(dtype).float(), rtol=1e-6, atol=1e-6)
     # unpool of a 2C tensor with the duplicated indices (ED:536-549)
     f = torch.randn(B, 2 * C, *pooled_spatial, generator=g).to(dtype)
-    fo = f.float().requires_grad_(True)
-    fg = f.to(DEV).requires_grad_(True)
+    fo = f.float().clone().requires_grad_(True)
+    fg = f.clone().to(DEV).requires_grad_(True)
     u = ops.maxunpool_tokens(ops.as_tokens(fg), arg, B, spatial, pool)
     uo = up(fo, torch.cat((ind, ind), 1), pool, pool)
     assert torch.equal(ops.from_tokens(u, B, spatial).float().cpu(), uo.to(dtype).float())
