@@ -138,6 +138,33 @@ int nextou_bti_ce_bwd(const void* logits, int dtype, long long stride_b, long lo
                       const double* grad_out, void* dlogits, long long dstride_b, long long dstride_c,
                       long long dstride_v, void* stream);
 
+/* ------------------------------------------------------------------------------------------
+ * Batch / instance normalisation (+ LeakyReLU) on a dense token-major matrix x[instances][rows][C]
+ * (C = physical row pitch).  Replaces nn.BatchNorm{2,3}d in train mode (nnUNetTrainer_NexToU.py:54-55),
+ * nn.InstanceNorm{2,3}d(affine) (torch_nn.py:42-46) and the LeakyReLU(0.01) behind them (torch_nn.py:16-17).
+ * Batch norm = 1 instance spanning every token of the batch; instance norm = 1 instance per batch item.
+ * slope = 1 disables the activation.  If instances > 1, rows*C must be a multiple of 4.
+ * ------------------------------------------------------------------------------------------ */
+/* number of CTA partial rows the stats / bwd kernels write: partial must hold instances*nblk*2*C floats */
+int nextou_norm_plan(int C, long long rows, int instances, int* nblk_out);
+/* mean / invstd [instances][C] (biased variance, eps inside the sqrt); running_* (may be NULL) are updated
+ * in place with `momentum` and the UNBIASED variance, like nn.BatchNorm. */
+int nextou_norm_stats(const void* x, int dtype, int C, long long rows, int instances, float eps, float* partial,
+                      float* mean, float* invstd, float* running_mean, float* running_var, float momentum,
+                      void* stream);
+/* y = lrelu((x - mean) * invstd * gamma + beta, slope); gamma / beta [C] fp32 or NULL */
+int nextou_norm_apply(const void* x, int dtype, int C, long long rows, int instances, const float* mean,
+                      const float* invstd, const float* gamma, const float* beta, float slope, void* y,
+                      void* stream);
+/* backward through activation + normalisation: sums[inst][0][C] = sum dy' (= d beta), sums[inst][1][C] =
+ * sum dy'*xhat (= d gamma), dx = gamma*invstd*(dy' - sums0/rows - xhat*sums1/rows), dy' = dy*lrelu'(pre). */
+int nextou_norm_bwd(const void* x, const void* dy, int dtype, int C, long long rows, int instances,
+                    const float* mean, const float* invstd, const float* gamma, const float* beta, float slope,
+                    float* partial, float* sums, void* dx, void* stream);
+/* eval-mode batch norm: y = lrelu(x*scale[c] + shift[c]) with the running statistics folded by the caller */
+int nextou_affine_act(const void* x, int dtype, int C, long long rows, const float* scale, const float* shift,
+                      float slope, void* y, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

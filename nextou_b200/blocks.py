@@ -72,10 +72,10 @@ class DropPath(nn.Module):
         return x * mask / keep
 
 
-def _fc_bn(seq: nn.Sequential, x: torch.Tensor, act_slope=None) -> torch.Tensor:
-    """nn.Sequential(1x1 conv, norm) as used for fc1 / fc2 everywhere (ED:373-381, 710-720, 833-842)."""
-    conv, norm = seq[0], seq[1]
-    return dense.batch_norm(dense.conv_nd(x, conv.weight, conv.bias, 1, 0), norm, act_slope)
+def _fc_bn(seq: nn.Sequential, tok: torch.Tensor, batch: int, act_slope=None) -> torch.Tensor:
+    """nn.Sequential(1x1 conv, norm) as used for fc1 / fc2 everywhere (ED:373-381, 710-720, 833-842), on token rows:
+    a GEMM followed by the fused norm (+ LeakyReLU) kernel."""
+    return dense.norm_tokens(dense.linear_tokens(tok, seq[0]), seq[1], batch, act_slope)
 
 
 class FFN(nn.Module):
@@ -95,11 +95,14 @@ class FFN(nn.Module):
         self.drop_path = DropPath(drop_path) if drop_path > 0. else nn.Identity()
 
     def forward(self, x):
+        B, spatial = x.shape[0], tuple(x.shape[2:])
+        tok = ops.as_tokens(x)
         if isinstance(self.act, nn.LeakyReLU):
-            h = _fc_bn(self.fc1, x, self.act.negative_slope)
+            h = _fc_bn(self.fc1, tok, B, self.act.negative_slope)
         else:
-            h = self.act(_fc_bn(self.fc1, x))
-        return self.drop_path(_fc_bn(self.fc2, h)) + x
+            h = self.act(_fc_bn(self.fc1, tok, B))
+        out = ops.from_tokens(_fc_bn(self.fc2, h, B), B, spatial)
+        return self.drop_path(out) + x
 
 
 # ------------------------------------------------------------------------------------------------------
@@ -179,17 +182,23 @@ class DyGraphConv(GraphConv):
         self.ndim = _ndim(conv_op)
         self.avg_pool = F.avg_pool2d if self.ndim == 2 else F.avg_pool3d
 
-    def forward(self, x, relative_pos=None):
-        B = x.shape[0]
-        spatial = tuple(x.shape[2:])
-        tok = ops.as_tokens(x)
-        n = _prod(spatial)
+    def forward_tokens(self, tok, B, spatial, relative_pos=None, row_map=None, graphs=None, n=None):
+        """[B*prod(spatial), C] -> [.., 2C] token rows.  With `row_map` the rows are regrouped into `graphs` graphs of
+        `n` tokens each by pure indexing (shifted windows)."""
+        if graphs is None:
+            graphs, n = B, _prod(spatial)
         y_tok, m = None, n
         if self.r > 1:
+            if row_map is not None:
+                raise NotImplementedError("reduce ratio r > 1 inside windows (never built by NexToU, ED:1003)")
             y_tok = ops.avgpool_tokens(tok, B, spatial, (self.r,) * self.ndim)
             m = y_tok.shape[0] // B
-        feat = _dyn_graph_features(self, tok, B, n, y_tok, m, relative_pos)
-        return self.gconv.nn(ops.from_tokens(feat, B, spatial))
+        feat = _dyn_graph_features(self, tok, graphs, n, y_tok, m, relative_pos, q_row_map=row_map)
+        return self.gconv.nn.forward_tokens(feat, B)
+
+    def forward(self, x, relative_pos=None):
+        B, spatial = x.shape[0], tuple(x.shape[2:])
+        return ops.from_tokens(self.forward_tokens(ops.as_tokens(x), B, spatial, relative_pos), B, spatial)
 
 
 def _pool_size_for(img_shape, img_min_shape):
@@ -223,10 +232,8 @@ class PoolDyGraphConv(GraphConv):
         self.max_pool_input = pool_cls(self.pool_size, stride=self.pool_size, return_indices=True)
         self.max_unpool_output = unpool_cls(self.pool_size, stride=self.pool_size)
 
-    def forward(self, x, relative_pos=None):
-        B = x.shape[0]
-        spatial = tuple(x.shape[2:])
-        tok = ops.as_tokens(x)
+    def forward_tokens(self, tok, B, spatial, relative_pos=None):
+        """[B*prod(spatial), C] -> [B*prod(spatial), 2C] token rows (un-pooled back to full resolution)."""
         pooled = any(p > 1 for p in self.pool_size)
         if pooled:
             q_tok, arg = ops.maxpool_tokens(tok, B, spatial, self.pool_size)
@@ -239,10 +246,14 @@ class PoolDyGraphConv(GraphConv):
             y_tok = ops.avgpool_tokens(q_tok, B, q_spatial, (self.r,) * self.ndim)
             m = y_tok.shape[0] // B
         feat = _dyn_graph_features(self, q_tok, B, n, y_tok, m, relative_pos)
-        g = self.gconv.nn(ops.from_tokens(feat, B, q_spatial))
+        g = self.gconv.nn.forward_tokens(feat, B)
         if pooled:
-            g = ops.from_tokens(ops.maxunpool_tokens(ops.as_tokens(g), arg, B, spatial, self.pool_size), B, spatial)
+            g = ops.maxunpool_tokens(g, arg, B, spatial, self.pool_size)
         return g
+
+    def forward(self, x, relative_pos=None):
+        B, spatial = x.shape[0], tuple(x.shape[2:])
+        return ops.from_tokens(self.forward_tokens(ops.as_tokens(x), B, spatial, relative_pos), B, spatial)
 
 
 def _make_relative_pos(in_channels, n, r, ndim):
@@ -276,10 +287,11 @@ class Grapher(nn.Module):
         self.relative_pos = _make_relative_pos(in_channels, n, r, self.ndim) if relative_pos else None
 
     def forward(self, x):
-        h = _fc_bn(self.fc1, x)
-        rp = _resized_relative_pos(self.relative_pos, _prod(h.shape[2:]), self.n, self.r, self.ndim)
-        h = _fc_bn(self.fc2, self.graph_conv(h, rp))
-        return self.drop_path(h) + x
+        B, spatial = x.shape[0], tuple(x.shape[2:])
+        h = _fc_bn(self.fc1, ops.as_tokens(x), B)
+        rp = _resized_relative_pos(self.relative_pos, _prod(spatial), self.n, self.r, self.ndim)
+        h = _fc_bn(self.fc2, self.graph_conv.forward_tokens(h, B, spatial, rp), B)
+        return self.drop_path(ops.from_tokens(h, B, spatial)) + x
 
 
 # ------------------------------------------------------------------------------------------------------
@@ -369,15 +381,12 @@ class SwinGrapher(nn.Module):
         if self.r != 1:
             raise NotImplementedError("SwinGrapher with reduce ratio r > 1 (never built by NexToU, ED:1003)")
         # fc1 (1x1 conv + BN) is order-invariant over tokens: run it on the un-partitioned volume
-        h = _fc_bn(self.fc1, x)
-        tok = ops.as_tokens(h)
+        h = _fc_bn(self.fc1, ops.as_tokens(x), B)
         row_map = self._row_map(B, spatial, x.device)
         n_windows = B * _prod(spatial) // self.n
-        feat = _dyn_graph_features(self.graph_conv, tok, n_windows, self.n, None, self.n, self.relative_pos,
-                                   q_row_map=row_map)
-        g = self.graph_conv.gconv.nn(ops.from_tokens(feat, B, spatial))
-        g = _fc_bn(self.fc2, g)
-        return self.drop_path(g) + x
+        g = self.graph_conv.forward_tokens(h, B, spatial, self.relative_pos, row_map=row_map, graphs=n_windows, n=self.n)
+        g = _fc_bn(self.fc2, g, B)
+        return self.drop_path(ops.from_tokens(g, B, spatial)) + x
 
 
 class PoolGrapher(nn.Module):
@@ -407,11 +416,12 @@ class PoolGrapher(nn.Module):
         self.relative_pos = _make_relative_pos(in_channels, self.n, r, self.ndim) if relative_pos else None
 
     def forward(self, x):
-        h = _fc_bn(self.fc1, x)
-        n_now = _prod([s // p for s, p in zip(h.shape[2:], self.pool_size)])
+        B, spatial = x.shape[0], tuple(x.shape[2:])
+        h = _fc_bn(self.fc1, ops.as_tokens(x), B)
+        n_now = _prod([s // p for s, p in zip(spatial, self.pool_size)])
         rp = _resized_relative_pos(self.relative_pos, n_now, self.n, self.r, self.ndim)
-        h = _fc_bn(self.fc2, self.graph_conv(h, rp))
-        return self.drop_path(h) + x
+        h = _fc_bn(self.fc2, self.graph_conv.forward_tokens(h, B, spatial, rp), B)
+        return self.drop_path(ops.from_tokens(h, B, spatial)) + x
 
 
 # ------------------------------------------------------------------------------------------------------
@@ -664,7 +674,8 @@ class NexToU_Decoder(nn.Module):
             x = self.stages[s](torch.cat((up, skips[-(s + 2)]), 1))
             if self.deep_supervision or s == last:
                 head = self.seg_layers[s if self.deep_supervision else -1]
-                seg_outputs.append(dense.conv_nd(x, head.weight, head.bias, 1, 0))
+                B, spatial = x.shape[0], tuple(x.shape[2:])
+                seg_outputs.append(ops.from_tokens(dense.linear_tokens(ops.as_tokens(x), head), B, spatial))
             low = x
         seg_outputs = seg_outputs[::-1]  # highest resolution first
         return seg_outputs if self.deep_supervision else seg_outputs[0]

@@ -11,7 +11,7 @@ import numpy as np
 import torch
 from torch import nn
 
-from . import dense
+from . import dense, ops
 
 
 def convert_conv_op_to_dim(conv_op) -> int:
@@ -97,13 +97,11 @@ class ConvDropoutNormReLU(nn.Module):
             nxt = mods[i + 1] if i + 1 < len(mods) else None
             if m is self.conv:
                 x = dense.conv_nd(x, m.weight, m.bias, tuple(m.stride), tuple(m.padding))
-            elif isinstance(m, nn.modules.batchnorm._BatchNorm):
+            elif isinstance(m, (nn.modules.batchnorm._BatchNorm, nn.modules.instancenorm._InstanceNorm)):
                 fuse = isinstance(nxt, nn.LeakyReLU)
-                x = dense.batch_norm(x, m, nxt.negative_slope if fuse else None)
-                i += 1 if fuse else 0
-            elif isinstance(m, nn.modules.instancenorm._InstanceNorm):
-                fuse = isinstance(nxt, nn.LeakyReLU)
-                x = dense.instance_norm(x, m, nxt.negative_slope if fuse else None)
+                B, spatial = x.shape[0], tuple(x.shape[2:])
+                tok = dense.norm_tokens(ops.as_tokens(x), m, B, nxt.negative_slope if fuse else None)
+                x = ops.from_tokens(tok, B, spatial)
                 i += 1 if fuse else 0
             else:
                 x = m(x)

@@ -1,0 +1,389 @@
+// Batch / instance normalisation (+ LeakyReLU) on token-major activations, forward and backward.
+// Replaces nn.BatchNorm{2,3}d (train-mode batch statistics, TR:54-55; 78 layers in 3d_fullres_nextou),
+// nn.InstanceNorm{2,3}d(affine) of the Pool graph convs (ED:22, TN:42-46) and the LeakyReLU(0.01) that follows
+// most of them (TR:57, TN:16-17).
+//
+// All kernels are HBM-bound streaming passes over a dense [rows][C] matrix (C = physical row pitch; zero padded
+// channels are simply extra channels).  The matrix is walked as a FLAT array in "sweeps" of R rows, R chosen on the
+// host so that C*R is a multiple of VEC and a CTA of C*R/VEC threads covers one sweep with one VEC-wide load per
+// thread: every thread then sees the same VEC channels in every sweep (its flat offset advances by a multiple of
+// C), keeps their statistics / scale+shift in registers, and all loads are full-width and perfectly coalesced no
+// matter how odd C is (33, 66, 132, 324 ...).  Reductions are deterministic: per-thread partials -> shared memory
+// -> fixed-order per-channel sums -> per-CTA partial rows in global memory -> fixed-order finalize.
+#include "common.cuh"
+
+namespace nextou {
+
+constexpr int NV = 4;  // elements per thread per sweep (8-byte bf16 / 16-byte fp32 loads)
+
+template <typename T> struct VecIO;
+template <> struct VecIO<float> {
+  static __device__ __forceinline__ void load(const float* p, float (&v)[NV]) {
+    const float4 t = *reinterpret_cast<const float4*>(p);
+    v[0] = t.x; v[1] = t.y; v[2] = t.z; v[3] = t.w;
+  }
+  static __device__ __forceinline__ void store(float* p, const float (&v)[NV]) {
+    *reinterpret_cast<float4*>(p) = make_float4(v[0], v[1], v[2], v[3]);
+  }
+};
+template <> struct VecIO<__nv_bfloat16> {
+  static __device__ __forceinline__ void load(const __nv_bfloat16* p, float (&v)[NV]) {
+    const uint2 u = *reinterpret_cast<const uint2*>(p);
+    const float2 a = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&u.x));
+    const float2 b = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&u.y));
+    v[0] = a.x; v[1] = a.y; v[2] = b.x; v[3] = b.y;
+  }
+  static __device__ __forceinline__ void store(__nv_bfloat16* p, const float (&v)[NV]) {
+    __nv_bfloat162 lo = __floats2bfloat162_rn(v[0], v[1]), hi = __floats2bfloat162_rn(v[2], v[3]);
+    uint2 u;
+    u.x = *reinterpret_cast<unsigned*>(&lo);
+    u.y = *reinterpret_cast<unsigned*>(&hi);
+    *reinterpret_cast<uint2*>(p) = u;
+  }
+};
+
+// guarded load / store for the ragged tail of an instance (total not a multiple of the sweep)
+template <typename T>
+__device__ __forceinline__ void load_guard(const T* base, long long off, long long total, float (&v)[NV]) {
+  if (off + NV <= total) {
+    VecIO<T>::load(base + off, v);
+  } else {
+#pragma unroll
+    for (int e = 0; e < NV; ++e) v[e] = (off + e < total) ? to_f(base[off + e]) : 0.f;
+  }
+}
+template <typename T>
+__device__ __forceinline__ void store_guard(T* base, long long off, long long total, const float (&v)[NV]) {
+  if (off + NV <= total) {
+    VecIO<T>::store(base + off, v);
+  } else {
+#pragma unroll
+    for (int e = 0; e < NV; ++e)
+      if (off + e < total) base[off + e] = from_f<T>(v[e]);
+  }
+}
+
+__device__ __forceinline__ float lrelu_grad(float pre, float slope) { return pre > 0.f ? 1.f : slope; }
+
+// ---- two-value per-channel reduction shared by the statistics and the backward-reduce kernels ---------------
+// acc[e][0..1] are this thread's partial sums for channel (NV*tid + e) % C.  Writes partial[blk][2][C].
+__device__ __forceinline__ void block_channel_reduce(float (&acc)[NV][2], int C, int R, float* smem,
+                                                     float* __restrict__ out) {
+  const int tid = threadIdx.x;
+  const int S = C * R;  // == NV * blockDim.x
+#pragma unroll
+  for (int e = 0; e < NV; ++e) {
+    smem[NV * tid + e] = acc[e][0];
+    smem[S + NV * tid + e] = acc[e][1];
+  }
+  __syncthreads();
+  for (int c = tid; c < 2 * C; c += blockDim.x) {
+    const int which = c / C, ch = c % C;
+    float s = 0.f;
+    for (int r = 0; r < R; ++r) s += smem[which * S + ch + r * C];
+    out[c] = s;
+  }
+}
+
+// grid (nblk, instances); block C*R/NV threads; dynamic smem 2*C*R floats
+template <typename T>
+__global__ void norm_stats_kernel(const T* __restrict__ x, int C, int R, long long rows, float* __restrict__ partial) {
+  extern __shared__ float smem[];
+  const long long total = rows * C;
+  const T* base = x + (long long)blockIdx.y * total;
+  const long long S = (long long)C * R;
+  float acc[NV][2] = {};
+  for (long long off = (long long)blockIdx.x * S + NV * threadIdx.x; off < total; off += (long long)gridDim.x * S) {
+    float v[NV];
+    load_guard(base, off, total, v);
+#pragma unroll
+    for (int e = 0; e < NV; ++e) {
+      acc[e][0] += v[e];
+      acc[e][1] = fmaf(v[e], v[e], acc[e][1]);
+    }
+  }
+  block_channel_reduce(acc, C, R, smem, partial + ((long long)blockIdx.y * gridDim.x + blockIdx.x) * 2 * C);
+}
+
+// one thread per (instance, channel): fixed-order sum of the CTA partials in fp64, mean / invstd, running stats
+__global__ void norm_finalize_kernel(const float* __restrict__ partial, int nblk, int C, long long rows, int instances,
+                                     float eps, float* __restrict__ mean, float* __restrict__ invstd,
+                                     float* __restrict__ running_mean, float* __restrict__ running_var,
+                                     float momentum) {
+  const int t = blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= instances * C) return;
+  const int inst = t / C, c = t % C;
+  double s1 = 0.0, s2 = 0.0;
+  for (int b = 0; b < nblk; ++b) {
+    const float* p = partial + ((long long)inst * nblk + b) * 2 * C;
+    s1 += (double)p[c];
+    s2 += (double)p[C + c];
+  }
+  const double n = (double)rows;
+  const double m = s1 / n;
+  double var = s2 / n - m * m;  // biased variance (what normalisation uses)
+  if (var < 0.0) var = 0.0;
+  mean[t] = (float)m;
+  invstd[t] = (float)(1.0 / sqrt(var + (double)eps));
+  if (running_mean != nullptr && inst == 0) {  // batch norm: a single instance spans the whole batch
+    const double unbiased = rows > 1 ? var * n / (n - 1.0) : var;
+    running_mean[c] = (float)((1.0 - momentum) * (double)running_mean[c] + momentum * m);
+    running_var[c] = (float)((1.0 - momentum) * (double)running_var[c] + momentum * unbiased);
+  }
+}
+
+// y = lrelu((x - mean) * invstd * gamma + beta); slope == 1 -> no activation
+template <typename T>
+__global__ void norm_apply_kernel(const T* __restrict__ x, int C, int R, long long rows, const float* __restrict__ mean,
+                                  const float* __restrict__ invstd, const float* __restrict__ gamma,
+                                  const float* __restrict__ beta, float slope, T* __restrict__ y) {
+  const long long total = rows * C;
+  const T* base = x + (long long)blockIdx.y * total;
+  T* obase = y + (long long)blockIdx.y * total;
+  const long long S = (long long)C * R;
+  float sc[NV], sh[NV];
+#pragma unroll
+  for (int e = 0; e < NV; ++e) {
+    const int ch = (NV * threadIdx.x + e) % C;
+    const float g = gamma ? gamma[ch] : 1.f, b = beta ? beta[ch] : 0.f;
+    sc[e] = invstd[blockIdx.y * C + ch] * g;
+    sh[e] = b - mean[blockIdx.y * C + ch] * sc[e];
+  }
+  for (long long off = (long long)blockIdx.x * S + NV * threadIdx.x; off < total; off += (long long)gridDim.x * S) {
+    float v[NV];
+    load_guard(base, off, total, v);
+#pragma unroll
+    for (int e = 0; e < NV; ++e) {
+      const float t = fmaf(v[e], sc[e], sh[e]);
+      v[e] = t > 0.f ? t : t * slope;
+    }
+    store_guard(obase, off, total, v);
+  }
+}
+
+// backward pass 1: per channel  s1 = sum dy',  s2 = sum dy' * xhat,  dy' = dy * lrelu'(pre-activation)
+template <typename T>
+__global__ void norm_bwd_reduce_kernel(const T* __restrict__ x, const T* __restrict__ dy, int C, int R, long long rows,
+                                       const float* __restrict__ mean, const float* __restrict__ invstd,
+                                       const float* __restrict__ gamma, const float* __restrict__ beta, float slope,
+                                       float* __restrict__ partial) {
+  extern __shared__ float smem[];
+  const long long total = rows * C;
+  const T* xb = x + (long long)blockIdx.y * total;
+  const T* db = dy + (long long)blockIdx.y * total;
+  const long long S = (long long)C * R;
+  float mu[NV], is[NV], g[NV], b[NV];
+#pragma unroll
+  for (int e = 0; e < NV; ++e) {
+    const int ch = (NV * threadIdx.x + e) % C;
+    mu[e] = mean[blockIdx.y * C + ch];
+    is[e] = invstd[blockIdx.y * C + ch];
+    g[e] = gamma ? gamma[ch] : 1.f;
+    b[e] = beta ? beta[ch] : 0.f;
+  }
+  float acc[NV][2] = {};
+  for (long long off = (long long)blockIdx.x * S + NV * threadIdx.x; off < total; off += (long long)gridDim.x * S) {
+    float v[NV], d[NV];
+    load_guard(xb, off, total, v);
+    load_guard(db, off, total, d);
+#pragma unroll
+    for (int e = 0; e < NV; ++e) {
+      const float xh = (v[e] - mu[e]) * is[e];
+      const float dd = d[e] * lrelu_grad(fmaf(xh, g[e], b[e]), slope);
+      acc[e][0] += dd;
+      acc[e][1] = fmaf(dd, xh, acc[e][1]);
+    }
+  }
+  block_channel_reduce(acc, C, R, smem, partial + ((long long)blockIdx.y * gridDim.x + blockIdx.x) * 2 * C);
+}
+
+// sums[inst][2][C] (fp32) from the CTA partials, fixed order, fp64 accumulation
+__global__ void norm_bwd_finalize_kernel(const float* __restrict__ partial, int nblk, int C, int instances,
+                                         float* __restrict__ sums) {
+  const int t = blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= instances * 2 * C) return;
+  const int inst = t / (2 * C), c = t % (2 * C);
+  double s = 0.0;
+  for (int b = 0; b < nblk; ++b) s += (double)partial[((long long)inst * nblk + b) * 2 * C + c];
+  sums[t] = (float)s;
+}
+
+// backward pass 2: dx = gamma * invstd * (dy' - s1/n - xhat * s2/n)
+template <typename T>
+__global__ void norm_bwd_apply_kernel(const T* __restrict__ x, const T* __restrict__ dy, int C, int R, long long rows,
+                                      const float* __restrict__ mean, const float* __restrict__ invstd,
+                                      const float* __restrict__ gamma, const float* __restrict__ beta, float slope,
+                                      const float* __restrict__ sums, T* __restrict__ dx) {
+  const long long total = rows * C;
+  const T* xb = x + (long long)blockIdx.y * total;
+  const T* db = dy + (long long)blockIdx.y * total;
+  T* ob = dx + (long long)blockIdx.y * total;
+  const long long S = (long long)C * R;
+  const float inv_n = 1.f / (float)rows;
+  float mu[NV], is[NV], g[NV], b[NV], m1[NV], m2[NV];
+#pragma unroll
+  for (int e = 0; e < NV; ++e) {
+    const int ch = (NV * threadIdx.x + e) % C;
+    mu[e] = mean[blockIdx.y * C + ch];
+    is[e] = invstd[blockIdx.y * C + ch];
+    g[e] = gamma ? gamma[ch] : 1.f;
+    b[e] = beta ? beta[ch] : 0.f;
+    m1[e] = sums[(long long)blockIdx.y * 2 * C + ch] * inv_n;
+    m2[e] = sums[(long long)blockIdx.y * 2 * C + C + ch] * inv_n;
+  }
+  for (long long off = (long long)blockIdx.x * S + NV * threadIdx.x; off < total; off += (long long)gridDim.x * S) {
+    float v[NV], d[NV];
+    load_guard(xb, off, total, v);
+    load_guard(db, off, total, d);
+#pragma unroll
+    for (int e = 0; e < NV; ++e) {
+      const float xh = (v[e] - mu[e]) * is[e];
+      const float dd = d[e] * lrelu_grad(fmaf(xh, g[e], b[e]), slope);
+      v[e] = g[e] * is[e] * (dd - m1[e] - xh * m2[e]);
+    }
+    store_guard(ob, off, total, v);
+  }
+}
+
+// eval-mode affine: y = lrelu(x * scale[c] + shift[c])  (running statistics folded by the caller)
+template <typename T>
+__global__ void affine_act_kernel(const T* __restrict__ x, int C, int R, long long rows, const float* __restrict__ scale,
+                                  const float* __restrict__ shift, float slope, T* __restrict__ y) {
+  const long long total = rows * C;
+  const long long S = (long long)C * R;
+  float sc[NV], sh[NV];
+#pragma unroll
+  for (int e = 0; e < NV; ++e) {
+    const int ch = (NV * threadIdx.x + e) % C;
+    sc[e] = scale[ch];
+    sh[e] = shift[ch];
+  }
+  for (long long off = (long long)blockIdx.x * S + NV * threadIdx.x; off < total; off += (long long)gridDim.x * S) {
+    float v[NV];
+    load_guard(x, off, total, v);
+#pragma unroll
+    for (int e = 0; e < NV; ++e) {
+      const float t = fmaf(v[e], sc[e], sh[e]);
+      v[e] = t > 0.f ? t : t * slope;
+    }
+    store_guard(y, off, total, v);
+  }
+}
+
+struct SweepPlan {
+  int R, threads, nblk;
+  size_t smem;
+};
+
+// R rows per sweep: C*R % NV == 0, C*R/NV <= 1024 threads, aim for ~512 threads
+static int plan_sweep(int C, long long rows, int instances, SweepPlan& p) {
+  if (C <= 0 || C > 4096 || rows <= 0 || instances <= 0 || instances > 65535) {
+    set_error("norm: unsupported shape C=%d rows=%lld instances=%d (C <= 4096)", C, rows, instances);
+    return NEXTOU_ERR_INVALID;
+  }
+  if (instances > 1 && (rows * C) % NV) {
+    set_error("norm: rows*C=%lld must be a multiple of %d when instances > 1 (vector alignment)", rows * C, NV);
+    return NEXTOU_ERR_INVALID;
+  }
+  int r0 = 1;
+  while ((C * r0) % NV) ++r0;
+  int R = r0;
+  while ((long long)C * (R + r0) / NV <= 512) R += r0;
+  if ((long long)C * R / NV > 1024) {
+    set_error("norm: C=%d needs more than 1024 threads per sweep", C);
+    return NEXTOU_ERR_INVALID;
+  }
+  p.R = R;
+  p.threads = C * R / NV;
+  const long long sweeps = (rows + R - 1) / R;
+  long long nblk = (4LL * num_sms() + instances - 1) / instances;
+  if (nblk > sweeps) nblk = sweeps;
+  if (nblk < 1) nblk = 1;
+  p.nblk = (int)nblk;
+  p.smem = sizeof(float) * 2 * (size_t)C * R;
+  return 0;
+}
+
+}  // namespace nextou
+
+using namespace nextou;
+
+extern "C" int nextou_norm_plan(int C, long long rows, int instances, int* nblk_out) {
+  SweepPlan p;
+  int rc = plan_sweep(C, rows, instances, p);
+  if (rc) return rc;
+  *nblk_out = p.nblk;
+  return 0;
+}
+
+extern "C" int nextou_norm_stats(const void* x, int dtype, int C, long long rows, int instances, float eps,
+                                 float* partial, float* mean, float* invstd, float* running_mean, float* running_var,
+                                 float momentum, void* stream) {
+  NEXTOU_REQUIRE(x && partial && mean && invstd, "norm_stats: null pointer");
+  SweepPlan p;
+  int rc = plan_sweep(C, rows, instances, p);
+  if (rc) return rc;
+  cudaStream_t st = (cudaStream_t)stream;
+  dim3 grid(p.nblk, instances);
+  DISPATCH_T(dtype, {
+    rc = ensure_smem(norm_stats_kernel<T>, p.smem);
+    if (rc) return rc;
+    norm_stats_kernel<T><<<grid, p.threads, p.smem, st>>>((const T*)x, C, p.R, rows, partial);
+  })
+  rc = check_launch("norm_stats_kernel");
+  if (rc) return rc;
+  const int n = instances * C;
+  norm_finalize_kernel<<<(n + 127) / 128, 128, 0, st>>>(partial, p.nblk, C, rows, instances, eps, mean, invstd,
+                                                       running_mean, running_var, momentum);
+  return check_launch("norm_finalize_kernel");
+}
+
+extern "C" int nextou_norm_apply(const void* x, int dtype, int C, long long rows, int instances, const float* mean,
+                                 const float* invstd, const float* gamma, const float* beta, float slope, void* y,
+                                 void* stream) {
+  NEXTOU_REQUIRE(x && y && mean && invstd, "norm_apply: null pointer");
+  SweepPlan p;
+  int rc = plan_sweep(C, rows, instances, p);
+  if (rc) return rc;
+  dim3 grid(p.nblk, instances);
+  DISPATCH_T(dtype, norm_apply_kernel<T><<<grid, p.threads, 0, (cudaStream_t)stream>>>(
+                        (const T*)x, C, p.R, rows, mean, invstd, gamma, beta, slope, (T*)y);)
+  return check_launch("norm_apply_kernel");
+}
+
+extern "C" int nextou_norm_bwd(const void* x, const void* dy, int dtype, int C, long long rows, int instances,
+                               const float* mean, const float* invstd, const float* gamma, const float* beta,
+                               float slope, float* partial, float* sums, void* dx, void* stream) {
+  NEXTOU_REQUIRE(x && dy && dx && mean && invstd && partial && sums, "norm_bwd: null pointer");
+  SweepPlan p;
+  int rc = plan_sweep(C, rows, instances, p);
+  if (rc) return rc;
+  cudaStream_t st = (cudaStream_t)stream;
+  dim3 grid(p.nblk, instances);
+  DISPATCH_T(dtype, {
+    rc = ensure_smem(norm_bwd_reduce_kernel<T>, p.smem);
+    if (rc) return rc;
+    norm_bwd_reduce_kernel<T><<<grid, p.threads, p.smem, st>>>((const T*)x, (const T*)dy, C, p.R, rows, mean, invstd,
+                                                              gamma, beta, slope, partial);
+  })
+  rc = check_launch("norm_bwd_reduce_kernel");
+  if (rc) return rc;
+  const int n = instances * 2 * C;
+  norm_bwd_finalize_kernel<<<(n + 127) / 128, 128, 0, st>>>(partial, p.nblk, C, instances, sums);
+  rc = check_launch("norm_bwd_finalize_kernel");
+  if (rc) return rc;
+  DISPATCH_T(dtype, norm_bwd_apply_kernel<T><<<grid, p.threads, 0, st>>>((const T*)x, (const T*)dy, C, p.R, rows, mean,
+                                                                        invstd, gamma, beta, slope, sums, (T*)dx);)
+  return check_launch("norm_bwd_apply_kernel");
+}
+
+extern "C" int nextou_affine_act(const void* x, int dtype, int C, long long rows, const float* scale,
+                                 const float* shift, float slope, void* y, void* stream) {
+  NEXTOU_REQUIRE(x && y && scale && shift, "affine_act: null pointer");
+  SweepPlan p;
+  int rc = plan_sweep(C, rows, 1, p);
+  if (rc) return rc;
+  DISPATCH_T(dtype, affine_act_kernel<T><<<p.nblk, p.threads, 0, (cudaStream_t)stream>>>((const T*)x, C, p.R, rows,
+                                                                                        scale, shift, slope, (T*)y);)
+  return check_launch("affine_act_kernel");
+}

@@ -85,24 +85,29 @@ class BasicConv(Seq):
                 m.append(act_layer(act))
         super().__init__(*m)
 
-    def forward(self, x):
+    def forward_tokens(self, tok, batch: int):
+        """Token-major fast path: [rows, Cin] -> [rows, Cout]; `batch` = number of instance-norm instances."""
         mods = list(self)
         i = 0
         while i < len(mods):
             m = mods[i]
             nxt = mods[i + 1] if i + 1 < len(mods) else None
             if isinstance(m, (nn.Conv2d, nn.Conv3d)):
-                x = dense.conv_nd(x, m.weight, m.bias, 1, 0, m.groups)
+                tok = dense.grouped_linear_tokens(tok, m) if m.groups > 1 else dense.linear_tokens(tok, m)
             elif isinstance(m, (nn.modules.batchnorm._BatchNorm, nn.modules.instancenorm._InstanceNorm)):
                 slope = nxt.negative_slope if isinstance(nxt, nn.LeakyReLU) else None
-                fn = dense.batch_norm if isinstance(m, nn.modules.batchnorm._BatchNorm) else dense.instance_norm
-                x = fn(x, m, slope)
+                tok = dense.norm_tokens(tok, m, batch, slope)
                 if slope is not None:
                     i += 1
             else:
-                x = m(x)
+                tok = m(tok)
             i += 1
-        return x
+        return tok
+
+    def forward(self, x):
+        from . import ops
+        B, spatial = x.shape[0], tuple(x.shape[2:])
+        return ops.from_tokens(self.forward_tokens(ops.as_tokens(x), B), B, spatial)
 
 
 def batched_index_select(x, idx):

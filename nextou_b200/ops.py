@@ -360,3 +360,81 @@ class _BTILoss(torch.autograd.Function):
 def bti_loss(logits, target, mask_a, mask_c, inclusion, connectivity: int, min_thick: int = 1) -> torch.Tensor:
     """fp64 scalar: mean_b sum_v CE(logits, target)[b, v] * critical[b, v]  (bti_loss.py:141-143)."""
     return _BTILoss.apply(logits, target, (list(mask_a), list(mask_c), list(inclusion)), connectivity, min_thick)
+
+
+# ----------------------------------------------------------------------------------------------
+# batch / instance norm (+ LeakyReLU) on dense token-major matrices (TR:54-55, TN:32-51)
+# ----------------------------------------------------------------------------------------------
+def _dense_tokens(t: torch.Tensor) -> torch.Tensor:
+    t = _tok2d(_work_dtype(t))
+    if t.stride(0) != t.shape[1]:
+        t = t.contiguous()
+    return t
+
+
+def _norm_partial(C, rows, instances, device):
+    nblk = ctypes.c_int(0)
+    check(_lib.lib().nextou_norm_plan(C, ll(rows), instances, ctypes.byref(nblk)), "nextou_norm_plan")
+    return torch.empty(instances * nblk.value * 2 * C, device=device, dtype=torch.float32)
+
+
+class _NormAct(torch.autograd.Function):
+    """Train-mode normalisation with batch statistics + optional LeakyReLU (slope 1.0 = none)."""
+
+    @staticmethod
+    def forward(ctx, x, gamma, beta, running_mean, running_var, momentum, eps, slope, instances):
+        x = _dense_tokens(x)
+        _need_cuda(x)
+        T, C = x.shape
+        rows = T // instances
+        assert rows * instances == T
+        L = _lib.lib()
+        g32 = None if gamma is None else gamma.detach().float().contiguous()
+        b32 = None if beta is None else beta.detach().float().contiguous()
+        partial = _norm_partial(C, rows, instances, x.device)
+        mean = torch.empty(instances * C, device=x.device, dtype=torch.float32)
+        invstd = torch.empty_like(mean)
+        check(L.nextou_norm_stats(ptr(x), dtype_code(x), C, ll(rows), instances, cf(eps), ptr(partial), ptr(mean), ptr(invstd),
+                                  ptr(running_mean), ptr(running_var), cf(momentum if momentum is not None else 0.0),
+                                  cstream()), "nextou_norm_stats")
+        y = torch.empty_like(x)
+        check(L.nextou_norm_apply(ptr(x), dtype_code(x), C, ll(rows), instances, ptr(mean), ptr(invstd), ptr(g32), ptr(b32),
+                                  cf(slope), ptr(y), cstream()), "nextou_norm_apply")
+        ctx.save_for_backward(x, mean, invstd, g32, b32)
+        ctx.meta = (C, rows, instances, slope, gamma is not None, None if gamma is None else gamma.dtype)
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        x, mean, invstd, g32, b32 = ctx.saved_tensors
+        C, rows, instances, slope, affine, pdt = ctx.meta
+        dy = _dense_tokens(dy.to(x.dtype))
+        partial = _norm_partial(C, rows, instances, x.device)
+        sums = torch.empty(instances * 2 * C, device=x.device, dtype=torch.float32)
+        dx = torch.empty_like(x)
+        check(_lib.lib().nextou_norm_bwd(ptr(x), ptr(dy), dtype_code(x), C, ll(rows), instances, ptr(mean), ptr(invstd),
+                                         ptr(g32), ptr(b32), cf(slope), ptr(partial), ptr(sums), ptr(dx), cstream()),
+              "nextou_norm_bwd")
+        dgamma = dbeta = None
+        if affine:
+            s = sums.view(instances, 2, C).sum(0)
+            dbeta, dgamma = s[0].to(pdt), s[1].to(pdt)
+        return dx, dgamma, dbeta, None, None, None, None, None, None
+
+
+def norm_act_tokens(x_tok, gamma, beta, running_mean=None, running_var=None, momentum=0.1, eps=1e-5, slope=1.0,
+                    instances=1):
+    """Batch norm (instances=1) / instance norm (instances=batch) with batch statistics, + LeakyReLU(slope)."""
+    return _NormAct.apply(x_tok, gamma, beta, running_mean, running_var, momentum, eps, float(slope), int(instances))
+
+
+def affine_act_tokens(x_tok, scale, shift, slope=1.0):
+    """Eval-mode batch norm: y = lrelu(x * scale[c] + shift[c]) (no autograd: inference only)."""
+    x = _dense_tokens(x_tok)
+    _need_cuda(x)
+    if torch.is_grad_enabled() and x_tok.requires_grad:
+        raise NextouError("affine_act_tokens (eval-mode norm) does not implement a backward pass")
+    y = torch.empty_like(x)
+    check(_lib.lib().nextou_affine_act(ptr(x), dtype_code(x), x.shape[1], ll(x.shape[0]), ptr(scale.float().contiguous()),
+                                       ptr(shift.float().contiguous()), cf(slope), ptr(y), cstream()), "nextou_affine_act")
+    return y

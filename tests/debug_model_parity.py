@@ -9,7 +9,7 @@ from oracle import torch_oracle as TO
 from tests import helpers as H
 
 
-def main(which="mini3d"):
+def main(which="mini3d", precision="fp32"):
     cfg, fname = (H.MINI3D, "model_mini3d_reference.npz") if which == "mini3d" else (H.MINI2D, "model_mini2d_reference.npz")
     torch.backends.cudnn.allow_tf32 = False
     torch.backends.cuda.matmul.allow_tf32 = False
@@ -37,7 +37,7 @@ def main(which="mini3d"):
             continue
         if isinstance(mod, (PoolGrapher, SwinGrapher, FFN, StackedConvBlocks)):
             mod.register_forward_hook(hook(name))
-    with torch.no_grad():
+    with torch.no_grad(), torch.autocast("cuda", dtype=torch.bfloat16, enabled=precision == "bf16"):
         outs = model(x.cuda())
 
     print(f"{'module':58s} {'max|err|':>10s} {'max|ref|':>10s} {'relL2':>10s}")
@@ -49,7 +49,7 @@ def main(which="mini3d"):
         with torch.no_grad():
             if isinstance(mod, (PoolGrapher, SwinGrapher)):
                 idx = mod.graph_conv.last_nn_idx.long().cpu()
-                rk = TO.ReplayKnn([idx], tol=1e-4)
+                rk = TO.ReplayKnn([idx], tol=1e-4, verify=precision == "fp32")
                 fn = TO.pool_grapher if isinstance(mod, PoolGrapher) else TO.swin_grapher
                 want = fn(xin, sd, name, dim, st, True, rk)
                 extra = f" knn excess {rk.worst:.2e}"
@@ -70,4 +70,4 @@ def main(which="mini3d"):
 
 
 if __name__ == "__main__":
-    main(sys.argv[1] if len(sys.argv) > 1 else "mini3d")
+    main(*(sys.argv[1:3] or ["mini3d"]))

@@ -238,6 +238,56 @@ def test_pool_unpool_forward_backward(dtype, spatial, pool):
 
 
 # ------------------------------------------------------------------------------------------------
+# batch / instance norm + LeakyReLU
+# ------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16], ids=["f32", "bf16"])
+@pytest.mark.parametrize("C,rows,instances,slope", [(33, 1000, 1, 0.01), (66, 777, 1, None), (132, 4099, 1, 0.01),
+                                                   (324, 168, 1, 0.01), (1296, 50, 1, 0.01), (264, 96, 2, 0.01),
+                                                   (40, 3, 1, 0.01), (33, 200003, 1, 0.01)])
+def test_norm_act_forward_backward(dtype, C, rows, instances, slope):
+    import torch.nn.functional as F
+    from nextou_b200 import ops
+    g = torch.Generator().manual_seed(C + rows)
+    x = (torch.randn(instances * rows, C, generator=g) * 2 + 0.5).to(dtype)
+    gamma = torch.rand(C, generator=g) + 0.5
+    beta = torch.randn(C, generator=g)
+    w = torch.randn(instances * rows, C, generator=g)
+    rm, rv = torch.zeros(C), torch.ones(C)
+    # oracle: torch CPU fp32 on the (possibly bf16-valued) input, reference layout (B, C, N)
+    xo = x.float().reshape(instances, rows, C).permute(0, 2, 1).clone().requires_grad_(True)
+    go, bo = gamma.clone().requires_grad_(True), beta.clone().requires_grad_(True)
+    if instances == 1:
+        rmo, rvo = rm.clone(), rv.clone()
+        yo = F.batch_norm(xo, rmo, rvo, go, bo, training=True, momentum=0.1, eps=1e-5)
+    else:
+        yo = F.instance_norm(xo, weight=go, bias=bo, eps=1e-5)
+    if slope is not None:
+        yo = F.leaky_relu(yo, slope)
+    wo = w.reshape(instances, rows, C).permute(0, 2, 1)
+    (yo * wo).sum().backward()
+    xg = x.to(DEV).requires_grad_(True)
+    gg, bg = gamma.to(DEV).requires_grad_(True), beta.to(DEV).requires_grad_(True)
+    rmg, rvg = (rm.to(DEV), rv.to(DEV)) if instances == 1 else (None, None)
+    y = ops.norm_act_tokens(xg, gg, bg, rmg, rvg, 0.1, 1e-5, 1.0 if slope is None else slope, instances)
+    assert y.dtype == dtype and y.shape == x.shape
+    (y.float() * w.to(DEV)).sum().backward()
+    want = yo.detach().permute(0, 2, 1).reshape(instances * rows, C)
+    gx = xo.grad.permute(0, 2, 1).reshape(instances * rows, C)
+    if dtype == torch.float32:
+        assert torch.allclose(y.cpu(), want, rtol=1e-5, atol=2e-5)
+        assert torch.allclose(xg.grad.cpu(), gx, rtol=1e-4, atol=1e-4 * max(1.0, gx.abs().max().item()))
+        assert torch.allclose(gg.grad.cpu(), go.grad, rtol=1e-4, atol=1e-3)
+        assert torch.allclose(bg.grad.cpu(), bo.grad, rtol=1e-4, atol=1e-3)
+        if instances == 1:
+            assert torch.allclose(rmg.cpu(), rmo, rtol=1e-5, atol=1e-6)
+            assert torch.allclose(rvg.cpu(), rvo, rtol=1e-5, atol=1e-6)
+    else:
+        assert torch.allclose(y.float().cpu(), want, rtol=1e-2, atol=2e-2)
+        assert ((xg.grad.float().cpu() - gx).norm() / gx.norm()).item() < 2e-2
+        assert ((gg.grad.cpu() - go.grad).norm() / go.grad.norm()).item() < 2e-2
+
+
+# ------------------------------------------------------------------------------------------------
 # BTI / TI loss
 # ------------------------------------------------------------------------------------------------
 @pytest.fixture(scope="module")
