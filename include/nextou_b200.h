@@ -165,6 +165,23 @@ int nextou_norm_bwd(const void* x, const void* dy, int dtype, int C, long long r
 int nextou_affine_act(const void* x, int dtype, int C, long long rows, const float* scale, const float* shift,
                       float slope, void* y, void* stream);
 
+/* ------------------------------------------------------------------------------------------
+ * tcgen05 / TMEM / TMA GEMM engine (csrc/gemm_tcgen05.cu): bf16 operands, fp32 accumulation in tensor memory.
+ * ------------------------------------------------------------------------------------------ */
+/* C[M][ldc] = A[M][K] * B[N][K]^T (+ bias[N]).  The 1x1 convolutions of the graphers / FFNs / segmentation heads
+ * (NexToU_Encoder_Decoder.py:305, 373-381, 710-720, 833-842) are exactly this with A = token rows, B = conv weight.
+ * A, B: bf16, K contiguous, row pitches lda / ldb (elements, multiples of 8), 16-byte aligned.  C: bf16 or fp32,
+ * ldc % 8 == 0; columns [N, ldc) are written as zeros (channel padding of the token-major format). */
+int nextou_gemm_bf16_tn(const void* A, long long lda, const void* B, long long ldb, void* C, long long ldc, int M,
+                        int N, int K, const float* bias, int out_dtype, void* stream);
+/* Stride-1 'same' convolution (odd kernel, zero padding (k-1)/2: the StackedConvBlocks convs, ED:125-141, 281-300)
+ * as implicit GEMM.  x: bf16 NDHWC [B][D][H][W][ldx]; wpack: bf16 [Cout][taps*cin_pad], cin_pad = ceil(Cin/64)*64,
+ * taps ordered (kd, kh, kw), zero padded; out: [B*D*H*W][ldo], columns [Cout, ldo) zero-filled.  2-D: D = kd = 1.
+ * The data-gradient of such a convolution is the same call on dY with the flipped / transposed weight pack. */
+int nextou_conv3d_ndhwc_fwd(const void* x, long long ldx, int B, int D, int H, int W, int Cin, const void* wpack,
+                            int Cout, int kd, int kh, int kw, const float* bias, void* out, long long ldo,
+                            int out_dtype, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -1,0 +1,462 @@
+// tcgen05 / TMEM / TMA GEMM engine for the dense contractions of the NexToU hot path (sm_100a only):
+//   * pointwise (1x1) convolutions  out[T][Cout] = tok[T][Cin] * W[Cout][Cin]^T + b     (ED:305, 373-381, 710-720, 833-842)
+//   * spatial convolutions as implicit GEMM over NDHWC activations (StackedConvBlocks, ED:125-141, 281-300):
+//       M = output voxels (a td x th x tw brick of <= 128 voxels per CTA), N = Cout, K = taps x Cin.
+//     The im2col gather never exists: for every tap a 5-D TMA box {64 ch, tw, th, td, 1} is fetched at the
+//     tap-shifted coordinate, out-of-range coordinates are zero-filled by the TMA unit (= the conv's zero padding),
+//     and the box lands in shared memory as 128-byte rows (one voxel x 64 channels) in the SWIZZLE_128B K-major
+//     layout that tcgen05.mma consumes directly.
+// Structure (one CTA = one 128 x BLOCK_N output tile, 192 threads):
+//   warp 0   : TMA producer (one elected lane), kStages-deep mbarrier ring
+//   warp 1   : MMA issuer (one elected lane): tcgen05.mma.cta_group::1.kind::f16, bf16 x bf16 -> fp32 in TMEM
+//   warps 2-5: epilogue: tcgen05.ld (32 lanes x 16 columns per instruction), + bias, -> bf16/fp32 global rows
+// Accumulators never touch registers until the epilogue; operands never touch registers at all.
+#include "common.cuh"
+#include <cuda.h>
+
+namespace nextou {
+
+// ------------------------------------------------------------------------------------------------------
+// raw PTX wrappers
+// ------------------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+// Bounded wait: a pipeline bug must trap (kernel error) instead of hanging the GPU.
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+  const uint32_t addr = smem_u32(bar);
+  uint32_t done = 0;
+  for (uint32_t spin = 0; !done; ++spin) {
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n"
+        "selp.u32 %0, 1, 0, p;\n"
+        "}\n"
+        : "=r"(done)
+        : "r"(addr), "r"(parity)
+        : "memory");
+    if (spin > (1u << 24)) __trap();
+  }
+}
+__device__ __forceinline__ void fence_barrier_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+
+__device__ __forceinline__ void tma_load_2d(void* dst, const CUtensorMap* map, uint64_t* bar, int c0, int c1) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+      ::"r"(smem_u32(dst)), "l"(map), "r"(smem_u32(bar)), "r"(c0), "r"(c1)
+      : "memory");
+}
+__device__ __forceinline__ void tma_load_5d(void* dst, const CUtensorMap* map, uint64_t* bar, int c0, int c1, int c2,
+                                            int c3, int c4) {
+  asm volatile(
+      "cp.async.bulk.tensor.5d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6, %7}], [%2];"
+      ::"r"(smem_u32(dst)), "l"(map), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2), "r"(c3), "r"(c4)
+      : "memory");
+}
+__device__ __forceinline__ void prefetch_tmap(const CUtensorMap* map) {
+  asm volatile("prefetch.tensormap [%0];" ::"l"(map) : "memory");
+}
+
+__device__ __forceinline__ void tmem_alloc(uint32_t* dst_smem, uint32_t ncols) {
+  asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(dst_smem)), "r"(ncols)
+               : "memory");
+  asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_dealloc(uint32_t taddr, uint32_t ncols) {
+  asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(ncols) : "memory");
+}
+__device__ __forceinline__ void umma_f16(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accum) {
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "setp.ne.b32 p, %4, 0;\n"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n"
+      "}\n" ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accum)
+      : "memory");
+}
+// arrives on the mbarrier once every previously issued tcgen05.mma of this thread has completed
+__device__ __forceinline__ void umma_commit(uint64_t* bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t (&r)[16]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+        "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+      : "r"(taddr)
+      : "memory");
+}
+__device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+
+// K-major, SWIZZLE_128B shared-memory matrix descriptor (cute::UMMA::SmemDescriptor, sm100 version field = 1):
+// rows are 128 B (64 bf16), 8-row groups are 1024 B apart (SBO); LBO is unused for swizzled K-major layouts.
+__device__ __forceinline__ uint64_t make_kmajor_sw128_desc(uint32_t smem_addr) {
+  uint64_t d = 0;
+  d |= (uint64_t)((smem_addr >> 4) & 0x3FFF);
+  d |= (uint64_t)1 << 16;            // leading byte offset (16 B units) — ignored
+  d |= (uint64_t)(1024 >> 4) << 32;  // stride byte offset
+  d |= (uint64_t)1 << 46;            // descriptor version (Blackwell)
+  d |= (uint64_t)2 << 61;            // SWIZZLE_128B
+  return d;
+}
+// cute::UMMA::InstrDescriptor for kind::f16: D = fp32, A = B = bf16, both K-major, dense
+__device__ __forceinline__ uint32_t make_idesc_bf16(int m, int n) {
+  return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(m >> 4) << 24);
+}
+
+// ------------------------------------------------------------------------------------------------------
+// kernel
+// ------------------------------------------------------------------------------------------------------
+constexpr int GEMM_BM = 128;
+constexpr int GEMM_BK = 64;   // one 128-byte swizzle row of bf16
+constexpr int GEMM_THREADS = 192;
+
+struct GemmParams {
+  // problem
+  int M, N;            // output rows (tokens / voxels) and columns (Cout)
+  int kblocks;         // 64-wide K blocks per tap (ceil(Cin / 64))
+  int taps;            // 1 for a plain GEMM
+  int block_n;         // UMMA N (multiple of 16, <= 256)
+  int tmem_cols;       // power of two >= block_n
+  int stages;
+  // output
+  void* C;
+  long long ldc;       // row pitch of C in elements; columns [N, ldc) are written as zeros
+  int out_dtype;
+  const float* bias;   // [N] or NULL
+  // implicit-GEMM geometry (is_conv)
+  int is_conv;
+  int D, H, W;         // output volume (== input volume for the stride-1 'same' convs served here)
+  int td, th, tw;      // output brick per CTA (td*th*tw <= 128)
+  int nd, nh, nw;      // bricks per axis
+  int kd, kh, kw, pd, ph, pw;
+};
+
+template <typename OutT>
+__device__ __forceinline__ void store_chunk16(OutT* row_ptr, int col0, const float (&v)[16], long long ldc) {
+  // col0 is a multiple of 16 and the row pitch a multiple of 8 elements -> 16-byte aligned halves
+#pragma unroll
+  for (int h = 0; h < 2; ++h) {
+    const int c = col0 + h * 8;
+    if (c + 8 <= ldc) {
+      if constexpr (sizeof(OutT) == 2) {
+        uint4 u;
+        __nv_bfloat162 p0 = __floats2bfloat162_rn(v[h * 8 + 0], v[h * 8 + 1]);
+        __nv_bfloat162 p1 = __floats2bfloat162_rn(v[h * 8 + 2], v[h * 8 + 3]);
+        __nv_bfloat162 p2 = __floats2bfloat162_rn(v[h * 8 + 4], v[h * 8 + 5]);
+        __nv_bfloat162 p3 = __floats2bfloat162_rn(v[h * 8 + 6], v[h * 8 + 7]);
+        u.x = *reinterpret_cast<unsigned*>(&p0);
+        u.y = *reinterpret_cast<unsigned*>(&p1);
+        u.z = *reinterpret_cast<unsigned*>(&p2);
+        u.w = *reinterpret_cast<unsigned*>(&p3);
+        *reinterpret_cast<uint4*>(row_ptr + c) = u;
+      } else {
+        *reinterpret_cast<float4*>(row_ptr + c) = make_float4(v[h * 8 + 0], v[h * 8 + 1], v[h * 8 + 2], v[h * 8 + 3]);
+        *reinterpret_cast<float4*>(row_ptr + c + 4) = make_float4(v[h * 8 + 4], v[h * 8 + 5], v[h * 8 + 6], v[h * 8 + 7]);
+      }
+    } else {
+#pragma unroll
+      for (int j = 0; j < 8; ++j)
+        if (c + j < ldc) row_ptr[c + j] = from_f<OutT>(v[h * 8 + j]);
+    }
+  }
+}
+
+__global__ void __launch_bounds__(GEMM_THREADS, 1)
+    gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
+                        const GemmParams p) {
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  // carve: [stages][A 16 KB] [stages][B block_n*128 B] [barriers]
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  const int a_bytes = GEMM_BM * GEMM_BK * 2;
+  const int b_bytes = p.block_n * GEMM_BK * 2;
+  uint8_t* smA = smem;
+  uint8_t* smB = smem + (size_t)p.stages * a_bytes;
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smB + (size_t)p.stages * b_bytes);
+  uint64_t* empty_bar = full_bar + p.stages;
+  uint64_t* tmem_full_bar = empty_bar + p.stages;
+  uint32_t* tmem_base_holder = reinterpret_cast<uint32_t*>(tmem_full_bar + 1);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int n0 = blockIdx.y * p.block_n;
+
+  // output brick of this CTA
+  int m0 = blockIdx.x * GEMM_BM;  // plain GEMM: first row
+  int bn = 0, d0 = 0, h0 = 0, w0 = 0;
+  if (p.is_conv) {
+    int t = blockIdx.x;
+    const int wt = t % p.nw; t /= p.nw;
+    const int ht = t % p.nh; t /= p.nh;
+    const int dt = t % p.nd; t /= p.nd;
+    bn = t;
+    d0 = dt * p.td; h0 = ht * p.th; w0 = wt * p.tw;
+  }
+
+  if (warp == 0 && lane == 0) {
+    prefetch_tmap(&tmA);
+    prefetch_tmap(&tmB);
+    for (int s = 0; s < p.stages; ++s) {
+      mbar_init(&full_bar[s], 1);
+      mbar_init(&empty_bar[s], 1);
+    }
+    mbar_init(tmem_full_bar, 1);
+    fence_barrier_init();
+  }
+  if (warp == 2) tmem_alloc(tmem_base_holder, (uint32_t)p.tmem_cols);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_base_holder;
+
+  const int total_kb = p.taps * p.kblocks;
+
+  if (warp == 0) {
+    // ===================== TMA producer =====================
+    if (lane == 0) {
+      const int a_tx = p.is_conv ? p.td * p.th * p.tw * GEMM_BK * 2 : a_bytes;
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int it = 0; it < total_kb; ++it) {
+        mbar_wait(&empty_bar[stage], phase ^ 1);
+        mbar_expect_tx(&full_bar[stage], (uint32_t)(a_tx + b_bytes));
+        const int tap = it / p.kblocks, cb = it - tap * p.kblocks;
+        if (p.is_conv) {
+          const int kw_ = tap % p.kw, kh_ = (tap / p.kw) % p.kh, kd_ = tap / (p.kw * p.kh);
+          tma_load_5d(smA + (size_t)stage * a_bytes, &tmA, &full_bar[stage], cb * GEMM_BK, w0 + kw_ - p.pw,
+                      h0 + kh_ - p.ph, d0 + kd_ - p.pd, bn);
+        } else {
+          tma_load_2d(smA + (size_t)stage * a_bytes, &tmA, &full_bar[stage], cb * GEMM_BK, m0);
+        }
+        tma_load_2d(smB + (size_t)stage * b_bytes, &tmB, &full_bar[stage], it * GEMM_BK, n0);
+        if (++stage == p.stages) { stage = 0; phase ^= 1; }
+      }
+    }
+  } else if (warp == 1) {
+    // ===================== MMA issuer =====================
+    if (lane == 0) {
+      const uint32_t idesc = make_idesc_bf16(GEMM_BM, p.block_n);
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int it = 0; it < total_kb; ++it) {
+        mbar_wait(&full_bar[stage], phase);
+        tc_fence_after();
+        const uint64_t adesc = make_kmajor_sw128_desc(smem_u32(smA + (size_t)stage * a_bytes));
+        const uint64_t bdesc = make_kmajor_sw128_desc(smem_u32(smB + (size_t)stage * b_bytes));
+#pragma unroll
+        for (int k = 0; k < GEMM_BK / 16; ++k) {
+          // advance 16 bf16 = 32 B along K inside the 128-byte swizzle row: +2 in the (>>4) start-address field
+          umma_f16(tmem_base, adesc + (uint64_t)(2 * k), bdesc + (uint64_t)(2 * k), idesc, (it | k) != 0 ? 1u : 0u);
+        }
+        umma_commit(&empty_bar[stage]);  // smem slot reusable once these MMAs have read it
+        if (++stage == p.stages) { stage = 0; phase ^= 1; }
+      }
+      umma_commit(tmem_full_bar);        // accumulator complete
+    }
+  } else {
+    // ===================== epilogue (warps 2..5 -> TMEM lane quarters warp%4) =====================
+    mbar_wait(tmem_full_bar, 0);
+    tc_fence_after();
+    const int q = warp & 3;
+    const int r = q * 32 + lane;  // row inside the tile == TMEM lane
+    long long out_row = -1;
+    if (p.is_conv) {
+      const int wx = r % p.tw, hy = (r / p.tw) % p.th, dz = r / (p.tw * p.th);
+      const int d = d0 + dz, h = h0 + hy, w = w0 + wx;
+      if (dz < p.td && d < p.D && h < p.H && w < p.W) out_row = (((long long)bn * p.D + d) * p.H + h) * p.W + w;
+    } else if (m0 + r < p.M) {
+      out_row = m0 + r;
+    }
+    for (int c = 0; c < p.block_n; c += 16) {
+      uint32_t raw[16];
+      tmem_ld16(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)c, raw);
+      tmem_ld_wait();
+      if (out_row >= 0) {
+        float v[16];
+#pragma unroll
+        for (int j = 0; j < 16; ++j) {
+          const int col = n0 + c + j;
+          float x = __uint_as_float(raw[j]);
+          if (p.bias != nullptr && col < p.N) x += p.bias[col];
+          v[j] = col < p.N ? x : 0.f;
+        }
+        if (n0 + c < p.ldc) {
+          if (p.out_dtype == NEXTOU_BF16)
+            store_chunk16(reinterpret_cast<__nv_bfloat16*>(p.C) + out_row * p.ldc, n0 + c, v, p.ldc);
+          else
+            store_chunk16(reinterpret_cast<float*>(p.C) + out_row * p.ldc, n0 + c, v, p.ldc);
+        }
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 2) tmem_dealloc(tmem_base, (uint32_t)p.tmem_cols);
+}
+
+// ------------------------------------------------------------------------------------------------------
+// host side
+// ------------------------------------------------------------------------------------------------------
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static EncodeTiledFn encode_fn() {
+  static EncodeTiledFn fn = nullptr;
+  if (!fn) {
+    void* ptr = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &ptr, cudaEnableDefault, &qres) == cudaSuccess &&
+        qres == cudaDriverEntryPointSuccess)
+      fn = reinterpret_cast<EncodeTiledFn>(ptr);
+  }
+  return fn;
+}
+
+static int encode_bf16_map(CUtensorMap* map, const void* base, int rank, const cuuint64_t* dims,
+                           const cuuint64_t* strides_bytes, const cuuint32_t* box, const char* what) {
+  EncodeTiledFn fn = encode_fn();
+  if (!fn) {
+    set_error("cuTensorMapEncodeTiled entry point unavailable");
+    return NEXTOU_ERR_CUDA;
+  }
+  cuuint32_t estr[5] = {1, 1, 1, 1, 1};
+  CUresult r = fn(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, (cuuint32_t)rank, const_cast<void*>(base), dims, strides_bytes,
+                  box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                  CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) {
+    set_error("cuTensorMapEncodeTiled(%s) failed with CUresult %d", what, (int)r);
+    return NEXTOU_ERR_CUDA;
+  }
+  return 0;
+}
+
+static int pick_block_n(int N) {
+  const int tiles = (N + 255) / 256;
+  int bn = (N + tiles - 1) / tiles;
+  bn = (bn + 15) / 16 * 16;
+  return bn < 16 ? 16 : bn;
+}
+static int pow2_cols(int n) {
+  int c = 32;
+  while (c < n) c <<= 1;
+  return c;
+}
+
+static int launch_gemm(const CUtensorMap& tmA, const CUtensorMap& tmB, GemmParams& p, long long m_tiles, cudaStream_t st) {
+  p.block_n = pick_block_n(p.N);
+  p.tmem_cols = pow2_cols(p.block_n);
+  const int per_stage = GEMM_BM * GEMM_BK * 2 + p.block_n * GEMM_BK * 2;
+  int stages = (200 * 1024) / per_stage;
+  if (stages > 4) stages = 4;
+  if (stages < 2) stages = 2;
+  const int total_kb = p.taps * p.kblocks;
+  if (stages > total_kb) stages = total_kb < 2 ? 2 : total_kb;
+  p.stages = stages;
+  const size_t smem = 1024 + (size_t)stages * per_stage + (2 * stages + 1) * sizeof(uint64_t) + 16;
+  int rc = ensure_smem(gemm_tcgen05_kernel, smem);
+  if (rc) return rc;
+  const int n_tiles = (p.N + p.block_n - 1) / p.block_n;
+  if (m_tiles > 2147483647LL || n_tiles > 65535) {
+    set_error("gemm: grid too large");
+    return NEXTOU_ERR_INVALID;
+  }
+  dim3 grid((unsigned)m_tiles, (unsigned)n_tiles);
+  gemm_tcgen05_kernel<<<grid, GEMM_THREADS, smem, st>>>(tmA, tmB, p);
+  return check_launch("gemm_tcgen05_kernel");
+}
+
+}  // namespace nextou
+
+using namespace nextou;
+
+// C[M][ldc] = A[M][K] * B[N][K]^T (+ bias): A, B bf16 with K contiguous (row pitches lda / ldb elements, multiples of 8,
+// 16-byte aligned bases); C bf16 or fp32 with ldc % 8 == 0; columns [N, ldc) of C are zero-filled.
+extern "C" int nextou_gemm_bf16_tn(const void* A, long long lda, const void* B, long long ldb, void* C, long long ldc,
+                                   int M, int N, int K, const float* bias, int out_dtype, void* stream) {
+  NEXTOU_REQUIRE(A && B && C, "gemm_bf16_tn: null pointer");
+  NEXTOU_REQUIRE(M > 0 && N > 0 && K > 0, "gemm_bf16_tn: bad shape M=%d N=%d K=%d", M, N, K);
+  NEXTOU_REQUIRE(lda % 8 == 0 && ldb % 8 == 0 && ldc % 8 == 0 && lda >= K && ldb >= K && ldc >= N,
+                 "gemm_bf16_tn: row pitches must be multiples of 8 elements and cover K / N (lda=%lld ldb=%lld ldc=%lld)", lda, ldb, ldc);
+  NEXTOU_REQUIRE(((uintptr_t)A & 15) == 0 && ((uintptr_t)B & 15) == 0 && ((uintptr_t)C & 15) == 0, "gemm_bf16_tn: 16-byte alignment");
+  NEXTOU_REQUIRE(out_dtype == NEXTOU_BF16 || out_dtype == NEXTOU_F32, "gemm_bf16_tn: bad out dtype");
+  GemmParams p = {};
+  p.M = M; p.N = N; p.kblocks = (K + GEMM_BK - 1) / GEMM_BK; p.taps = 1;
+  p.C = C; p.ldc = ldc; p.out_dtype = out_dtype; p.bias = bias; p.is_conv = 0;
+  const int bn = pick_block_n(N);
+  CUtensorMap tmA, tmB;
+  {
+    cuuint64_t dims[2] = {(cuuint64_t)K, (cuuint64_t)M};
+    cuuint64_t str[1] = {(cuuint64_t)lda * 2};
+    cuuint32_t box[2] = {GEMM_BK, GEMM_BM};
+    int rc = encode_bf16_map(&tmA, A, 2, dims, str, box, "A");
+    if (rc) return rc;
+  }
+  {
+    cuuint64_t dims[2] = {(cuuint64_t)K, (cuuint64_t)N};
+    cuuint64_t str[1] = {(cuuint64_t)ldb * 2};
+    cuuint32_t box[2] = {GEMM_BK, (cuuint32_t)bn};
+    int rc = encode_bf16_map(&tmB, B, 2, dims, str, box, "B");
+    if (rc) return rc;
+  }
+  return launch_gemm(tmA, tmB, p, (M + GEMM_BM - 1) / GEMM_BM, (cudaStream_t)stream);
+}
+
+// Stride-1 'same' convolution as implicit GEMM.  x: bf16 NDHWC [B][D][H][W][ldx] (ldx % 8 == 0, channels >= Cin are
+// ignored); wpack: bf16 [Cout][taps * cin_pad] with cin_pad = ceil(Cin/64)*64 and taps ordered (kd, kh, kw), zero padded;
+// out: [B*D*H*W][ldo] bf16/fp32, columns [Cout, ldo) zero-filled.  2-D convolutions use D = 1, kd = 1.
+extern "C" int nextou_conv3d_ndhwc_fwd(const void* x, long long ldx, int B, int D, int H, int W, int Cin,
+                                       const void* wpack, int Cout, int kd, int kh, int kw, const float* bias,
+                                       void* out, long long ldo, int out_dtype, void* stream) {
+  NEXTOU_REQUIRE(x && wpack && out, "conv3d_ndhwc_fwd: null pointer");
+  NEXTOU_REQUIRE(B > 0 && D > 0 && H > 0 && W > 0 && Cin > 0 && Cout > 0, "conv3d_ndhwc_fwd: bad shape");
+  NEXTOU_REQUIRE(kd % 2 == 1 && kh % 2 == 1 && kw % 2 == 1 && kd * kh * kw <= 343, "conv3d_ndhwc_fwd: odd kernel sizes only");
+  NEXTOU_REQUIRE(ldx % 8 == 0 && ldx >= Cin && ldo % 8 == 0 && ldo >= Cout, "conv3d_ndhwc_fwd: pitches must be multiples of 8");
+  NEXTOU_REQUIRE(((uintptr_t)x & 15) == 0 && ((uintptr_t)wpack & 15) == 0 && ((uintptr_t)out & 15) == 0, "conv3d_ndhwc_fwd: 16-byte alignment");
+  NEXTOU_REQUIRE(out_dtype == NEXTOU_BF16 || out_dtype == NEXTOU_F32, "conv3d_ndhwc_fwd: bad out dtype");
+  GemmParams p = {};
+  p.M = 0; p.N = Cout; p.kblocks = (Cin + GEMM_BK - 1) / GEMM_BK; p.taps = kd * kh * kw;
+  p.C = out; p.ldc = ldo; p.out_dtype = out_dtype; p.bias = bias; p.is_conv = 1;
+  p.D = D; p.H = H; p.W = W; p.kd = kd; p.kh = kh; p.kw = kw; p.pd = kd / 2; p.ph = kh / 2; p.pw = kw / 2;
+  // brick (td x th x tw <= 128 voxels) minimising the number of CTAs; ties -> the widest W extent (coalescing)
+  int tw = 1, th = 1, td = 1;
+  long long best = -1;
+  for (int a = 1; a <= (W < 128 ? W : 128); ++a)
+    for (int b = 1; a * b <= 128 && b <= H; ++b) {
+      int c = 128 / (a * b);
+      if (c > D) c = D;
+      const long long tiles = (long long)((W + a - 1) / a) * ((H + b - 1) / b) * ((D + c - 1) / c);
+      if (best < 0 || tiles < best || (tiles == best && a > tw && a <= 32)) {
+        best = tiles; tw = a; th = b; td = c;
+      }
+    }
+  p.tw = tw; p.th = th; p.td = td;
+  p.nw = (W + tw - 1) / tw; p.nh = (H + th - 1) / th; p.nd = (D + td - 1) / td;
+  const int bn = pick_block_n(Cout);
+  const int cin_pad = p.kblocks * GEMM_BK;
+  CUtensorMap tmA, tmB;
+  {
+    cuuint64_t dims[5] = {(cuuint64_t)Cin, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)D, (cuuint64_t)B};
+    cuuint64_t str[4] = {(cuuint64_t)ldx * 2, (cuuint64_t)ldx * 2 * W, (cuuint64_t)ldx * 2 * W * H,
+                         (cuuint64_t)ldx * 2 * W * H * D};
+    cuuint32_t box[5] = {GEMM_BK, (cuuint32_t)tw, (cuuint32_t)th, (cuuint32_t)td, 1};
+    int rc = encode_bf16_map(&tmA, x, 5, dims, str, box, "conv input");
+    if (rc) return rc;
+  }
+  {
+    cuuint64_t dims[2] = {(cuuint64_t)p.taps * cin_pad, (cuuint64_t)Cout};
+    cuuint64_t str[1] = {(cuuint64_t)p.taps * cin_pad * 2};
+    cuuint32_t box[2] = {GEMM_BK, (cuuint32_t)bn};
+    int rc = encode_bf16_map(&tmB, wpack, 2, dims, str, box, "conv weights");
+    if (rc) return rc;
+  }
+  return launch_gemm(tmA, tmB, p, (long long)B * p.nd * p.nh * p.nw, (cudaStream_t)stream);
+}

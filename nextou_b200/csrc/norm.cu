@@ -105,26 +105,55 @@ __global__ void norm_stats_kernel(const T* __restrict__ x, int C, int R, long lo
   block_channel_reduce(acc, C, R, smem, partial + ((long long)blockIdx.y * gridDim.x + blockIdx.x) * 2 * C);
 }
 
-// one thread per (instance, channel): fixed-order sum of the CTA partials in fp64, mean / invstd, running stats
-__global__ void norm_finalize_kernel(const float* __restrict__ partial, int nblk, int C, long long rows, int instances,
-                                     float eps, float* __restrict__ mean, float* __restrict__ invstd,
-                                     float* __restrict__ running_mean, float* __restrict__ running_var,
-                                     float momentum) {
-  const int t = blockIdx.x * blockDim.x + threadIdx.x;
-  if (t >= instances * C) return;
-  const int inst = t / C, c = t % C;
-  double s1 = 0.0, s2 = 0.0;
-  for (int b = 0; b < nblk; ++b) {
-    const float* p = partial + ((long long)inst * nblk + b) * 2 * C;
-    s1 += (double)p[c];
-    s2 += (double)p[C + c];
+// Fixed-order fp64 sum of the CTA partial rows: block = 32 columns x FIN_SLICES slices; slice s adds rows s, s+8, ...
+// (independent loads in flight), then the slices are combined in order.  `cols` = row length of `partial`.
+constexpr int FIN_SLICES = 8;
+__device__ __forceinline__ double sliced_column_sum(const float* __restrict__ rows_base, int nblk, int cols, int col,
+                                                    bool valid, double* sh) {
+  const int lane = threadIdx.x & 31, slice = threadIdx.x >> 5;
+  double s = 0.0;
+  if (valid) {
+    int b = slice;
+    for (; b + 3 * FIN_SLICES < nblk; b += 4 * FIN_SLICES) {
+      const float v0 = rows_base[(long long)b * cols + col];
+      const float v1 = rows_base[(long long)(b + FIN_SLICES) * cols + col];
+      const float v2 = rows_base[(long long)(b + 2 * FIN_SLICES) * cols + col];
+      const float v3 = rows_base[(long long)(b + 3 * FIN_SLICES) * cols + col];
+      s += (double)v0;
+      s += (double)v1;
+      s += (double)v2;
+      s += (double)v3;
+    }
+    for (; b < nblk; b += FIN_SLICES) s += (double)rows_base[(long long)b * cols + col];
   }
+  sh[slice * 32 + lane] = s;
+  __syncthreads();
+  double tot = 0.0;
+  if (slice == 0)
+    for (int i = 0; i < FIN_SLICES; ++i) tot += sh[i * 32 + lane];
+  __syncthreads();
+  return tot;  // meaningful in slice 0 only
+}
+
+// grid (ceil(C/32), instances), block 32 x FIN_SLICES: mean / invstd per (instance, channel), running stats
+__global__ void __launch_bounds__(32 * FIN_SLICES)
+    norm_finalize_kernel(const float* __restrict__ partial, int nblk, int C, long long rows, int instances, float eps,
+                         float* __restrict__ mean, float* __restrict__ invstd, float* __restrict__ running_mean,
+                         float* __restrict__ running_var, float momentum) {
+  __shared__ double sh[FIN_SLICES * 32];
+  const int inst = blockIdx.y;
+  const int c = blockIdx.x * 32 + (threadIdx.x & 31);
+  const bool valid = c < C;
+  const float* base = partial + (long long)inst * nblk * 2 * C;
+  const double s1 = sliced_column_sum(base, nblk, 2 * C, c, valid, sh);
+  const double s2 = sliced_column_sum(base, nblk, 2 * C, C + c, valid, sh);
+  if (!valid || threadIdx.x >= 32) return;
   const double n = (double)rows;
   const double m = s1 / n;
   double var = s2 / n - m * m;  // biased variance (what normalisation uses)
   if (var < 0.0) var = 0.0;
-  mean[t] = (float)m;
-  invstd[t] = (float)(1.0 / sqrt(var + (double)eps));
+  mean[inst * C + c] = (float)m;
+  invstd[inst * C + c] = (float)(1.0 / sqrt(var + (double)eps));
   if (running_mean != nullptr && inst == 0) {  // batch norm: a single instance spans the whole batch
     const double unbiased = rows > 1 ? var * n / (n - 1.0) : var;
     running_mean[c] = (float)((1.0 - momentum) * (double)running_mean[c] + momentum * m);
@@ -197,15 +226,16 @@ __global__ void norm_bwd_reduce_kernel(const T* __restrict__ x, const T* __restr
   block_channel_reduce(acc, C, R, smem, partial + ((long long)blockIdx.y * gridDim.x + blockIdx.x) * 2 * C);
 }
 
-// sums[inst][2][C] (fp32) from the CTA partials, fixed order, fp64 accumulation
-__global__ void norm_bwd_finalize_kernel(const float* __restrict__ partial, int nblk, int C, int instances,
-                                         float* __restrict__ sums) {
-  const int t = blockIdx.x * blockDim.x + threadIdx.x;
-  if (t >= instances * 2 * C) return;
-  const int inst = t / (2 * C), c = t % (2 * C);
-  double s = 0.0;
-  for (int b = 0; b < nblk; ++b) s += (double)partial[((long long)inst * nblk + b) * 2 * C + c];
-  sums[t] = (float)s;
+// sums[inst][2][C] (fp32) from the CTA partials, fixed order, fp64 accumulation; grid (ceil(2C/32), instances)
+__global__ void __launch_bounds__(32 * FIN_SLICES)
+    norm_bwd_finalize_kernel(const float* __restrict__ partial, int nblk, int C, int instances,
+                             float* __restrict__ sums) {
+  __shared__ double sh[FIN_SLICES * 32];
+  const int inst = blockIdx.y;
+  const int c = blockIdx.x * 32 + (threadIdx.x & 31);
+  const bool valid = c < 2 * C;
+  const double s = sliced_column_sum(partial + (long long)inst * nblk * 2 * C, nblk, 2 * C, c, valid, sh);
+  if (valid && threadIdx.x < 32) sums[(long long)inst * 2 * C + c] = (float)s;
 }
 
 // backward pass 2: dx = gamma * invstd * (dy' - s1/n - xhat * s2/n)
@@ -296,7 +326,7 @@ static int plan_sweep(int C, long long rows, int instances, SweepPlan& p) {
   p.R = R;
   p.threads = C * R / NV;
   const long long sweeps = (rows + R - 1) / R;
-  long long nblk = (4LL * num_sms() + instances - 1) / instances;
+  long long nblk = (2LL * num_sms() + instances - 1) / instances;
   if (nblk > sweeps) nblk = sweeps;
   if (nblk < 1) nblk = 1;
   p.nblk = (int)nblk;
@@ -332,9 +362,8 @@ extern "C" int nextou_norm_stats(const void* x, int dtype, int C, long long rows
   })
   rc = check_launch("norm_stats_kernel");
   if (rc) return rc;
-  const int n = instances * C;
-  norm_finalize_kernel<<<(n + 127) / 128, 128, 0, st>>>(partial, p.nblk, C, rows, instances, eps, mean, invstd,
-                                                       running_mean, running_var, momentum);
+  norm_finalize_kernel<<<dim3((C + 31) / 32, instances), 32 * FIN_SLICES, 0, st>>>(
+      partial, p.nblk, C, rows, instances, eps, mean, invstd, running_mean, running_var, momentum);
   return check_launch("norm_finalize_kernel");
 }
 
@@ -368,8 +397,8 @@ extern "C" int nextou_norm_bwd(const void* x, const void* dy, int dtype, int C, 
   })
   rc = check_launch("norm_bwd_reduce_kernel");
   if (rc) return rc;
-  const int n = instances * 2 * C;
-  norm_bwd_finalize_kernel<<<(n + 127) / 128, 128, 0, st>>>(partial, p.nblk, C, instances, sums);
+  norm_bwd_finalize_kernel<<<dim3((2 * C + 31) / 32, instances), 32 * FIN_SLICES, 0, st>>>(partial, p.nblk, C,
+                                                                                              instances, sums);
   rc = check_launch("norm_bwd_finalize_kernel");
   if (rc) return rc;
   DISPATCH_T(dtype, norm_bwd_apply_kernel<T><<<grid, p.threads, 0, st>>>((const T*)x, (const T*)dy, C, p.R, rows, mean,

@@ -363,6 +363,63 @@ def bti_loss(logits, target, mask_a, mask_c, inclusion, connectivity: int, min_t
 
 
 # ----------------------------------------------------------------------------------------------
+# tcgen05 GEMM engine (csrc/gemm_tcgen05.cu)
+# ----------------------------------------------------------------------------------------------
+def pad8(c: int) -> int:
+    return (c + 7) // 8 * 8
+
+
+def gemm_bf16_tn(a: torch.Tensor, b: torch.Tensor, bias: Optional[torch.Tensor] = None, n: Optional[int] = None,
+                 out_dtype=torch.bfloat16, out: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """out[M, ldc] = a[M, K] @ b[N, K]^T (+ bias); a, b bf16 with unit inner stride and row pitches that are multiples of
+    8 elements; returns the PADDED [M, pad8(N)] matrix (columns >= N are zero), or writes into `out`."""
+    _need_cuda(a, b)
+    assert a.dtype == torch.bfloat16 and b.dtype == torch.bfloat16 and a.stride(1) == 1 and b.stride(1) == 1
+    M, K = a.shape
+    N = b.shape[0] if n is None else n
+    if out is None:
+        out = torch.empty((M, pad8(N)), device=a.device, dtype=out_dtype)
+    bias32 = None if bias is None else bias.detach().float().contiguous()
+    check(_lib.lib().nextou_gemm_bf16_tn(ptr(a), ll(a.stride(0)), ptr(b), ll(b.stride(0)), ptr(out), ll(out.stride(0)), M, N,
+                                         K, ptr(bias32), dtype_code(out), cstream()), "nextou_gemm_bf16_tn")
+    return out
+
+
+def pack_conv_weight(w: torch.Tensor, transpose_flip: bool = False) -> torch.Tensor:
+    """(Cout, Cin, *k) conv weight -> bf16 [Cout, taps * cin_pad] (taps in (kd, kh, kw) order, Cin zero-padded to a
+    multiple of 64).  transpose_flip=True packs the data-gradient operator: [Cin, flipped taps * cout_pad]."""
+    nd = w.dim() - 2
+    if transpose_flip:
+        w = w.transpose(0, 1).flip(dims=tuple(range(2, 2 + nd)))
+    co, ci = w.shape[:2]
+    taps = 1
+    for s in w.shape[2:]:
+        taps *= s
+    ci_pad = (ci + 63) // 64 * 64
+    wp = w.reshape(co, ci, taps).permute(0, 2, 1)
+    wp = torch.nn.functional.pad(wp, (0, ci_pad - ci))
+    return wp.reshape(co, taps * ci_pad).to(torch.bfloat16).contiguous()
+
+
+def conv_ndhwc_bf16(x_tok: torch.Tensor, batch: int, spatial: Sequence[int], cin: int, wpack: torch.Tensor, cout: int,
+                    ksize: Sequence[int], bias: Optional[torch.Tensor] = None, out_dtype=torch.bfloat16) -> torch.Tensor:
+    """Stride-1 'same' convolution on a token-major bf16 volume [B*prod(spatial), ldx] -> padded [.., pad8(cout)]."""
+    _need_cuda(x_tok, wpack)
+    assert x_tok.dtype == torch.bfloat16 and x_tok.stride(1) == 1 and wpack.dtype == torch.bfloat16
+    sp = list(spatial)
+    ks = list(ksize)
+    if len(sp) == 2:
+        sp, ks = [1] + sp, [1] + ks
+    D, H, W = sp
+    out = torch.empty((batch * D * H * W, pad8(cout)), device=x_tok.device, dtype=out_dtype)
+    bias32 = None if bias is None else bias.detach().float().contiguous()
+    check(_lib.lib().nextou_conv3d_ndhwc_fwd(ptr(x_tok), ll(x_tok.stride(0)), batch, D, H, W, cin, ptr(wpack), cout, ks[0],
+                                             ks[1], ks[2], ptr(bias32), ptr(out), ll(out.stride(0)), dtype_code(out),
+                                             cstream()), "nextou_conv3d_ndhwc_fwd")
+    return out
+
+
+# ----------------------------------------------------------------------------------------------
 # batch / instance norm (+ LeakyReLU) on dense token-major matrices (TR:54-55, TN:32-51)
 # ----------------------------------------------------------------------------------------------
 def _dense_tokens(t: torch.Tensor) -> torch.Tensor:

@@ -1,0 +1,74 @@
+"""GPU parity of the tcgen05 GEMM engine (plain GEMM and implicit-GEMM convolution) against a CPU fp32 oracle
+evaluated on the same bf16-rounded operands (products of bf16 values are exact in fp32, so only the accumulation
+order and the final bf16 rounding differ)."""
+import pytest
+import torch
+import torch.nn.functional as F
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda"
+
+
+def _rel(a, b):
+    return ((a - b).norm() / b.norm().clamp_min(1e-12)).item()
+
+
+@pytest.mark.parametrize("M,N,K,ld_extra", [(128, 16, 64, 0), (300, 132, 132, 4), (1000, 33, 66, 6), (86016 // 8, 264, 132, 4),
+                                            (257, 528, 264, 0), (129, 1296, 324, 4), (64, 14, 33, 7), (5000, 324, 1296, 0),
+                                            (168, 648, 648, 0)])
+@pytest.mark.parametrize("out_dtype", [torch.bfloat16, torch.float32], ids=["obf16", "of32"])
+def test_gemm_bf16_tn(M, N, K, ld_extra, out_dtype):
+    from nextou_b200 import ops
+    g = torch.Generator().manual_seed(M + N + K)
+    lda = ops.pad8(K) + (8 if ld_extra else 0)
+    a_buf = torch.randn(M, lda, generator=g).bfloat16()
+    b_buf = (torch.randn(N, ops.pad8(K), generator=g) / K ** 0.5).bfloat16()
+    bias = torch.randn(N, generator=g)
+    a_buf[:, K:] = float("nan")                             # strided views: lanes beyond K must never be read
+    b_buf[:, K:] = float("nan")
+    a, b = a_buf[:, :K], b_buf[:, :K]
+    want = a.float() @ b.float().t() + bias
+    out = ops.gemm_bf16_tn(a_buf.to(DEV)[:, :K], b_buf.to(DEV)[:, :K], bias.to(DEV), out_dtype=out_dtype)
+    assert out.shape == (M, ops.pad8(N)) and out.dtype == out_dtype
+    got = out.float().cpu()
+    assert torch.count_nonzero(got[:, N:]) == 0             # channel padding is written as zeros
+    tol = 1e-2 if out_dtype == torch.bfloat16 else 2e-5
+    assert torch.allclose(got[:, :N], want, rtol=tol, atol=tol * want.abs().max().item()), _rel(got[:, :N], want)
+    if out_dtype == torch.float32:
+        assert _rel(got[:, :N], want) < 1e-6
+
+
+@pytest.mark.parametrize("B,spatial,cin,cout,ks", [
+    (1, (4, 16, 24), 33, 33, (1, 3, 3)), (1, (8, 12, 16), 66, 66, (3, 3, 3)), (2, (4, 7, 6), 324, 324, (3, 3, 3)),
+    (1, (6, 10, 20), 132, 66, (3, 3, 3)), (1, (1, 20, 36), 16, 40, (1, 3, 3)), (1, (16, 28, 24), 264, 132, (3, 3, 3)),
+    (1, (5, 9, 11), 8, 264, (3, 3, 3)), (2, (12, 20), 32, 48, (3, 3))])
+def test_conv_ndhwc_implicit_gemm(B, spatial, cin, cout, ks):
+    from nextou_b200 import ops
+    g = torch.Generator().manual_seed(cin * 7 + cout)
+    dim = len(spatial)
+    x = torch.randn(B, cin, *spatial, generator=g).bfloat16()
+    w = (torch.randn(cout, cin, *ks, generator=g) / (cin * 9) ** 0.5).bfloat16()
+    bias = torch.randn(cout, generator=g)
+    conv = F.conv3d if dim == 3 else F.conv2d
+    want = conv(x.float(), w.float(), bias, padding=[k // 2 for k in ks])
+    ldx = ops.pad8(cin)
+    tok = torch.zeros(B * x[0, 0].numel(), ldx, dtype=torch.bfloat16)
+    tok[:, :cin] = x.permute(0, *range(2, 2 + dim), 1).reshape(-1, cin)
+    if ldx > cin:
+        tok[:, cin:] = float("nan")                         # padding lanes must never be read
+    out = ops.conv_ndhwc_bf16(tok.to(DEV), B, spatial, cin, ops.pack_conv_weight(w).to(DEV), cout, ks, bias.to(DEV),
+                              out_dtype=torch.float32)
+    got = out.cpu()[:, :cout].reshape(B, *spatial, cout).permute(0, dim + 1, *range(1, dim + 1))
+    assert torch.count_nonzero(out.cpu()[:, cout:]) == 0
+    assert _rel(got, want) < 1e-5, _rel(got, want)
+    assert torch.allclose(got, want, rtol=1e-4, atol=1e-4 * want.abs().max().item())
+    # data gradient == the same kernel on dY with the flipped / transposed pack
+    dy = torch.randn(B, cout, *spatial, generator=g).bfloat16()
+    xg = x.float().requires_grad_(True)
+    conv(xg, w.float(), None, padding=[k // 2 for k in ks]).backward(dy.float())
+    dtok = torch.zeros(B * x[0, 0].numel(), ops.pad8(cout), dtype=torch.bfloat16)
+    dtok[:, :cout] = dy.permute(0, *range(2, 2 + dim), 1).reshape(-1, cout)
+    dx = ops.conv_ndhwc_bf16(dtok.to(DEV), B, spatial, cout, ops.pack_conv_weight(w, transpose_flip=True).to(DEV), cin, ks,
+                             None, out_dtype=torch.float32)
+    gotdx = dx.cpu()[:, :cin].reshape(B, *spatial, cin).permute(0, dim + 1, *range(1, dim + 1))
+    assert _rel(gotdx, xg.grad) < 1e-5, _rel(gotdx, xg.grad)
