@@ -72,6 +72,14 @@ class DropPath(nn.Module):
         return x * mask / keep
 
 
+def _residual(mod, out_tok, x, B, spatial):
+    """drop_path(out) + x (ED:389, 817, 932).  drop_path is the identity for NexToU (rate 0): then the add runs on the
+    physical token rows and keeps the channel-padded layout; a real DropPath goes through the logical view."""
+    if isinstance(mod.drop_path, nn.Identity):
+        return ops.from_tokens(ops.add_tokens(out_tok, ops.as_tokens(x)), B, spatial)
+    return mod.drop_path(ops.from_tokens(out_tok, B, spatial)) + x
+
+
 def _fc_bn(seq: nn.Sequential, tok: torch.Tensor, batch: int, act_slope=None) -> torch.Tensor:
     """nn.Sequential(1x1 conv, norm) as used for fc1 / fc2 everywhere (ED:373-381, 710-720, 833-842), on token rows:
     a GEMM followed by the fused norm (+ LeakyReLU) kernel."""
@@ -101,8 +109,7 @@ class FFN(nn.Module):
             h = _fc_bn(self.fc1, tok, B, self.act.negative_slope)
         else:
             h = self.act(_fc_bn(self.fc1, tok, B))
-        out = ops.from_tokens(_fc_bn(self.fc2, h, B), B, spatial)
-        return self.drop_path(out) + x
+        return _residual(self, _fc_bn(self.fc2, h, B), x, B, spatial)
 
 
 # ------------------------------------------------------------------------------------------------------
@@ -291,7 +298,7 @@ class Grapher(nn.Module):
         h = _fc_bn(self.fc1, ops.as_tokens(x), B)
         rp = _resized_relative_pos(self.relative_pos, _prod(spatial), self.n, self.r, self.ndim)
         h = _fc_bn(self.fc2, self.graph_conv.forward_tokens(h, B, spatial, rp), B)
-        return self.drop_path(ops.from_tokens(h, B, spatial)) + x
+        return _residual(self, h, x, B, spatial)
 
 
 # ------------------------------------------------------------------------------------------------------
@@ -386,7 +393,7 @@ class SwinGrapher(nn.Module):
         n_windows = B * _prod(spatial) // self.n
         g = self.graph_conv.forward_tokens(h, B, spatial, self.relative_pos, row_map=row_map, graphs=n_windows, n=self.n)
         g = _fc_bn(self.fc2, g, B)
-        return self.drop_path(ops.from_tokens(g, B, spatial)) + x
+        return _residual(self, g, x, B, spatial)
 
 
 class PoolGrapher(nn.Module):
@@ -421,7 +428,7 @@ class PoolGrapher(nn.Module):
         n_now = _prod([s // p for s, p in zip(spatial, self.pool_size)])
         rp = _resized_relative_pos(self.relative_pos, n_now, self.n, self.r, self.ndim)
         h = _fc_bn(self.fc2, self.graph_conv.forward_tokens(h, B, spatial, rp), B)
-        return self.drop_path(ops.from_tokens(h, B, spatial)) + x
+        return _residual(self, h, x, B, spatial)
 
 
 # ------------------------------------------------------------------------------------------------------
@@ -671,7 +678,9 @@ class NexToU_Decoder(nn.Module):
         for s in range(len(self.stages)):
             tc = self.transpconvs[s]
             up = dense.conv_transpose_nd(low, tc.weight, tc.bias, tuple(tc.stride))
-            x = self.stages[s](torch.cat((up, skips[-(s + 2)]), 1))
+            skip = skips[-(s + 2)]
+            cat = ops.cat_tokens(ops.as_tokens(up), ops.as_tokens(skip))      # torch.cat((up, skip), 1), ED:322
+            x = self.stages[s](ops.from_tokens(cat, up.shape[0], tuple(up.shape[2:])))
             if self.deep_supervision or s == last:
                 head = self.seg_layers[s if self.deep_supervision else -1]
                 B, spatial = x.shape[0], tuple(x.shape[2:])

@@ -91,22 +91,22 @@ class ConvDropoutNormReLU(nn.Module):
 
     def forward(self, x):
         mods = list(self.all_modules)
+        B, spatial = x.shape[0], tuple(x.shape[2:])
+        tok = ops.as_tokens(x)
         i = 0
         while i < len(mods):
             m = mods[i]
             nxt = mods[i + 1] if i + 1 < len(mods) else None
             if m is self.conv:
-                x = dense.conv_nd(x, m.weight, m.bias, tuple(m.stride), tuple(m.padding))
+                tok, spatial = dense.conv_tokens(tok, B, spatial, m)
             elif isinstance(m, (nn.modules.batchnorm._BatchNorm, nn.modules.instancenorm._InstanceNorm)):
                 fuse = isinstance(nxt, nn.LeakyReLU)
-                B, spatial = x.shape[0], tuple(x.shape[2:])
-                tok = dense.norm_tokens(ops.as_tokens(x), m, B, nxt.negative_slope if fuse else None)
-                x = ops.from_tokens(tok, B, spatial)
+                tok = dense.norm_tokens(tok, m, B, nxt.negative_slope if fuse else None)
                 i += 1 if fuse else 0
-            else:
-                x = m(x)
+            else:  # dropout / other activations: through the logical (N, C, *spatial) view
+                tok = ops.as_tokens(m(ops.from_tokens(tok, B, spatial)))
             i += 1
-        return x
+        return ops.from_tokens(tok, B, spatial)
 
     def compute_conv_feature_map_size(self, input_size):
         assert len(input_size) == len(self.stride)

@@ -4,24 +4,40 @@ grouped pointwise convolutions, spatial / transposed convolutions, batch / insta
 Every module in blocks.py / conv_blocks.py routes through this file, so it is the one place where a backend is
 chosen.  `stats` counts calls per backend (bench.py reports them):
 
-  * "native.*"  — hand-written sm_100a kernels behind the C-ABI (csrc/norm.cu; csrc/gemm_tcgen05.cu when enabled);
-  * "cublas.*"  — plain library GEMMs (1x1 convolutions are exactly `tokens @ W^T + b`);
-  * "cudnn.*"   — spatial / transposed convolutions that the native implicit-GEMM kernel does not cover yet.
+  * "tcgen05.*" — hand-written sm_100a tensor-core kernels (csrc/gemm_tcgen05.cu) for bf16 activations: every 1x1
+                  convolution (forward + data gradient) and every stride-1 spatial convolution (forward + data gradient);
+  * "native.*"  — hand-written normalisation kernels (csrc/norm.cu), all dtypes;
+  * "cublas.*"  — plain library GEMMs: fp32 (non-autocast) 1x1 convolutions and the weight gradients `dY^T X`;
+  * "cudnn.*"   — strided / transposed convolutions, fp32 convolutions and convolution weight gradients.
 
-Nothing here ever runs on the CPU.  Activations are logically (N, C, *spatial), physically channels-last; the
-token view [N*prod(spatial), C] of such a tensor is free (ops.as_tokens).
+Nothing here ever runs on the CPU.  Activations are logically (N, C, *spatial), physically token-major
+([voxels, C] rows at a pitch that is C or C rounded up to 8); ops.as_tokens / ops.from_tokens convert for free.
 """
 from __future__ import annotations
 
 from collections import Counter
-from typing import Optional
+from typing import Optional, Sequence, Tuple
 
 import torch
 import torch.nn.functional as F
 
-from . import ops
+from . import native, ops
 
 stats: Counter = Counter()
+# set to False to force the library path everywhere (A/B measurements)
+USE_TCGEN05 = True
+
+
+def _bf16_path(tok: torch.Tensor) -> bool:
+    """bf16 tensor-core path: the activations are bf16 already, or bf16 autocast is active (then, like autocast does
+    for conv / linear, fp32 inputs are rounded to bf16 on entry)."""
+    if not tok.is_cuda:
+        raise ops.NextouError("nextou_b200 needs CUDA tensors (there is no CPU fallback path)")
+    if not USE_TCGEN05:
+        return False
+    if tok.dtype == torch.bfloat16:
+        return True
+    return torch.is_autocast_enabled("cuda") and torch.get_autocast_dtype("cuda") == torch.bfloat16
 
 
 # ------------------------------------------------------------------------------------------------------
@@ -29,6 +45,9 @@ stats: Counter = Counter()
 # ------------------------------------------------------------------------------------------------------
 def linear_tokens(tok: torch.Tensor, conv: torch.nn.Module) -> torch.Tensor:
     """1x1 conv of `conv` (weight (Cout, Cin, 1, 1[, 1])) applied to token rows: [T, Cin] -> [T, Cout]."""
+    if _bf16_path(tok):
+        stats["tcgen05.linear"] += 1
+        return native.linear_tokens(tok, conv.weight, conv.bias)
     stats["cublas.linear"] += 1
     w = conv.weight.reshape(conv.weight.shape[0], -1)
     return F.linear(tok, w, conv.bias)
@@ -36,8 +55,10 @@ def linear_tokens(tok: torch.Tensor, conv: torch.nn.Module) -> torch.Tensor:
 
 def grouped_linear_tokens(tok: torch.Tensor, conv: torch.nn.Module) -> torch.Tensor:
     """Grouped 1x1 conv (groups = 6 in 3-D, 4 in 2-D; weight (Cout, Cin/g, 1, ...)): the groups are the diagonal
-    blocks of one dense GEMM.  The zero blocks cost (g-1)/g wasted FLOPs of a tiny GEMM (2C <= 648) but keep the
-    output token-major without a permute copy."""
+    blocks of one dense operand, which keeps the output token-major without a permute copy."""
+    if _bf16_path(tok):
+        stats["tcgen05.grouped_linear"] += 1
+        return native.grouped_linear_tokens(tok, conv.weight, conv.bias, conv.groups)
     stats["cublas.grouped_linear"] += 1
     g = conv.groups
     w = conv.weight.reshape(g, conv.weight.shape[0] // g, -1)
@@ -47,10 +68,21 @@ def grouped_linear_tokens(tok: torch.Tensor, conv: torch.nn.Module) -> torch.Ten
 # ------------------------------------------------------------------------------------------------------
 # spatial convolutions (ED:125-141, 281-300) and kernel == stride transposed convolutions (ED:273-276)
 # ------------------------------------------------------------------------------------------------------
-def conv_nd(x: torch.Tensor, weight: torch.Tensor, bias: Optional[torch.Tensor], stride, padding, groups: int = 1):
+def conv_tokens(tok: torch.Tensor, batch: int, spatial: Sequence[int], conv: torch.nn.Module
+                ) -> Tuple[torch.Tensor, Tuple[int, ...]]:
+    """k x k (x k) convolution of `conv` on a token-major volume; returns (token rows, output spatial shape)."""
+    stride, ks = tuple(conv.stride), tuple(conv.kernel_size)
+    same = all(s == 1 for s in stride) and all(k % 2 == 1 for k in ks) and tuple(conv.padding) == tuple(k // 2 for k in ks) \
+        and all(d == 1 for d in conv.dilation) and conv.groups == 1
+    if same and _bf16_path(tok):
+        stats["tcgen05.conv"] += 1
+        return native.conv_tokens(tok, conv.weight, conv.bias, batch, spatial), tuple(spatial)
     stats["cudnn.conv"] += 1
+    x = ops.from_tokens(tok, batch, spatial)
     f = F.conv3d if x.dim() == 5 else F.conv2d
-    return f(x, weight, bias, stride=stride, padding=padding, groups=groups)
+    y = f(x, conv.weight, conv.bias, stride=stride, padding=tuple(conv.padding), dilation=tuple(conv.dilation),
+          groups=conv.groups)
+    return ops.as_tokens(y), tuple(y.shape[2:])
 
 
 def conv_transpose_nd(x, weight, bias, stride):

@@ -1,0 +1,102 @@
+"""Autograd wrappers around the tcgen05 GEMM engine (csrc/gemm_tcgen05.cu) for bf16 token-major activations.
+
+forward  : hand-written tcgen05 kernels (TMA -> swizzled smem -> tcgen05.mma -> TMEM -> epilogue).
+backward : data gradients through the same kernels (a GEMM / convolution with the transposed / flipped weight
+           pack); weight gradients are plain library contractions for now (cuBLAS `dY^T X` for the 1x1 layers,
+           cuDNN wgrad for the spatial convolutions) — DESIGN.md tracks them as the next kernels to write.
+Token matrices are [rows, C] views with a row pitch that is a multiple of 8 elements (channel padding, don't-care).
+"""
+from __future__ import annotations
+
+from typing import Optional, Sequence
+
+import torch
+
+from . import ops
+
+
+def _f32(t):
+    return None if t is None else t.detach().float()
+
+
+class _LinearTokens(torch.autograd.Function):
+    """y[T, N] = x[T, K] @ w2d[N, K]^T + b  with w2d an fp32 / bf16 master weight."""
+
+    @staticmethod
+    def forward(ctx, x, w2d, bias):
+        xb = ops.tma_ready_bf16(x)
+        N, K = w2d.shape
+        wp = ops.tma_ready_bf16(w2d.detach())                   # [N, K] bf16 (padded pitch)
+        y = ops.gemm_bf16_tn(xb, wp, bias, n=N)[:, :N]
+        ctx.save_for_backward(xb, w2d)
+        ctx.has_bias = bias is not None
+        ctx.bias_dtype = None if bias is None else bias.dtype
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        xb, w2d = ctx.saved_tensors
+        N, K = w2d.shape
+        dyb = ops.tma_ready_bf16(dy)
+        dx = dw = db = None
+        if ctx.needs_input_grad[0]:
+            wt = ops.tma_ready_bf16(w2d.detach().t())            # [K, N] bf16: B operand of dX = dY W
+            dx = ops.gemm_bf16_tn(dyb, wt, None, n=K)[:, :K]
+        if ctx.needs_input_grad[1]:
+            dw = torch.matmul(dyb.t(), xb).to(w2d.dtype)         # library GEMM (cuBLAS), fp32 accumulate
+        if ctx.has_bias and ctx.needs_input_grad[2]:
+            db = dyb.float().sum(0).to(ctx.bias_dtype)
+        return dx, dw, db
+
+
+def linear_tokens(x_tok: torch.Tensor, weight: torch.Tensor, bias: Optional[torch.Tensor]) -> torch.Tensor:
+    """1x1 convolution on token rows through the tcgen05 GEMM; weight: (Cout, Cin, 1, ...)."""
+    return _LinearTokens.apply(x_tok, weight.reshape(weight.shape[0], -1), bias)
+
+
+def grouped_linear_tokens(x_tok: torch.Tensor, weight: torch.Tensor, bias: Optional[torch.Tensor], groups: int):
+    """Grouped 1x1 convolution: the groups are the diagonal blocks of one [Cout, Cin] operand (TN:85)."""
+    w = weight.reshape(groups, weight.shape[0] // groups, -1)
+    return _LinearTokens.apply(x_tok, torch.block_diag(*w.unbind(0)), bias)
+
+
+class _ConvTokens(torch.autograd.Function):
+    """Stride-1 'same' convolution on a token-major bf16 volume (implicit GEMM)."""
+
+    @staticmethod
+    def forward(ctx, x, weight, bias, batch, spatial):
+        xb = ops.tma_ready_bf16(x)
+        cout, cin = weight.shape[:2]
+        ks = tuple(weight.shape[2:])
+        y = ops.conv_ndhwc_bf16(xb, batch, spatial, cin, ops.pack_conv_weight(weight.detach()), cout, ks, bias)[:, :cout]
+        ctx.save_for_backward(xb, weight)
+        ctx.meta = (batch, tuple(spatial), bias is not None, None if bias is None else bias.dtype)
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        xb, weight = ctx.saved_tensors
+        batch, spatial, has_bias, bdt = ctx.meta
+        cout, cin = weight.shape[:2]
+        ks = tuple(weight.shape[2:])
+        dyb = ops.tma_ready_bf16(dy)
+        dx = dw = db = None
+        if ctx.needs_input_grad[0]:
+            wpack_t = ops.pack_conv_weight(weight.detach(), transpose_flip=True)
+            dx = ops.conv_ndhwc_bf16(dyb, batch, spatial, cout, wpack_t, cin, ks, None)[:, :cin]
+        if ctx.needs_input_grad[1]:
+            # library weight gradient (cuDNN wgrad) on the logical views
+            xin = ops.from_tokens(xb, batch, spatial)
+            gout = ops.from_tokens(dyb, batch, spatial)
+            pad = [k // 2 for k in ks]
+            one = [1] * len(ks)
+            _, dw, _ = torch.ops.aten.convolution_backward(gout, xin, weight.detach().to(torch.bfloat16), None, one, pad, one,
+                                                           False, [0] * len(ks), 1, [False, True, False])
+            dw = dw.to(weight.dtype)
+        if has_bias and ctx.needs_input_grad[2]:
+            db = dyb.float().sum(0).to(bdt)
+        return dx, dw, db, None, None
+
+
+def conv_tokens(x_tok, weight, bias, batch: int, spatial: Sequence[int]):
+    return _ConvTokens.apply(x_tok, weight, bias, batch, tuple(spatial))

@@ -31,19 +31,89 @@ def channels_last(x: torch.Tensor) -> torch.Tensor:
     return x.contiguous(memory_format=fmt)
 
 
+def pad8(c: int) -> int:
+    return (c + 7) // 8 * 8
+
+
+def _token_pitch(x: torch.Tensor):
+    """Row pitch (elements) if the logical (N, C, *spatial) tensor is physically token-major — channels unit-stride,
+    voxels in (n, *spatial) order at a constant pitch >= C (plain channels-last or channel-padded) — else None."""
+    C = x.shape[1]
+    if C > 1 and x.stride(1) != 1:
+        return None
+    pitch = x.stride(-1)
+    if pitch < C:
+        return None
+    expect = pitch
+    for n, st in zip(reversed(x.shape[2:]), reversed(x.stride()[2:])):
+        if n != 1 and st != expect:
+            return None
+        expect *= n
+    if x.shape[0] != 1 and x.stride(0) != expect:
+        return None
+    return pitch
+
+
 def as_tokens(x: torch.Tensor) -> torch.Tensor:
-    """(N, C, *spatial) -> [N*prod(spatial), C] token-major view (copies only if x is not channels-last)."""
-    x = channels_last(x)
-    perm = (0, *range(2, x.dim()), 1)
-    return x.permute(*perm).reshape(-1, x.shape[1])
+    """(N, C, *spatial) -> [N*prod(spatial), C] view with strides (pitch, 1); copies only if x is not token-major."""
+    C = x.shape[1]
+    T = x.numel() // C
+    pitch = _token_pitch(x)
+    if pitch is None:
+        x = channels_last(x)
+        pitch = _token_pitch(x)
+        if pitch is None:  # degenerate shapes where memory_format is ambiguous
+            return x.permute(0, *range(2, x.dim()), 1).reshape(T, C)
+    return x.as_strided((T, C), (pitch, 1), x.storage_offset())
 
 
 def from_tokens(tok: torch.Tensor, batch: int, spatial: Sequence[int]) -> torch.Tensor:
-    """[rows, C] token-major -> logical (N, C, *spatial) tensor that is physically channels-last (a view)."""
+    """[rows, C] token rows (strides (pitch, 1)) -> logical (N, C, *spatial) view, physically token-major."""
     C = tok.shape[1]
-    x = tok.reshape(batch, *spatial, C)
-    nd = len(spatial)
-    return x.permute(0, nd + 1, *range(1, nd + 1))
+    if tok.stride(1) != 1 and C > 1:
+        tok = tok.contiguous()
+    pitch = tok.stride(0)
+    strides = [1] * (2 + len(spatial))
+    acc = pitch
+    for i in range(len(spatial) - 1, -1, -1):
+        strides[2 + i] = acc
+        acc *= spatial[i]
+    strides[0] = acc
+    return tok.as_strided((batch, C, *spatial), tuple(strides), tok.storage_offset())
+
+
+def _rows_in_bounds(t: torch.Tensor, pitch: int) -> bool:
+    """True if the full [rows, pitch] rectangle under the [rows, C] view `t` lies inside its storage."""
+    need = t.storage_offset() + t.shape[0] * pitch
+    return need <= t.untyped_storage().nbytes() // t.element_size()
+
+
+def full_rows(t: torch.Tensor) -> torch.Tensor:
+    """The [rows, pitch] matrix (real + padding channels) under a [rows, C] token view, or None if unavailable."""
+    pitch = t.stride(0)
+    if t.dim() != 2 or t.stride(1) != 1 or pitch < t.shape[1]:
+        return None
+    if pitch == t.shape[1]:
+        return t
+    if not _rows_in_bounds(t, pitch):
+        return None
+    return t.as_strided((t.shape[0], pitch), (pitch, 1), t.storage_offset())
+
+
+def padded_like(rows: int, C: int, dtype, device) -> torch.Tensor:
+    """New [rows, C] view over a [rows, pad8(C)] buffer (padding channels are don't-care)."""
+    return torch.empty((rows, pad8(C)), device=device, dtype=dtype)[:, :C]
+
+
+def tma_ready_bf16(tok: torch.Tensor) -> torch.Tensor:
+    """[rows, C] bf16 view usable as a TMA operand (pitch % 8 == 0, 16-byte aligned); copies into a padded buffer
+    only when the given view is not."""
+    if (tok.dtype == torch.bfloat16 and tok.dim() == 2 and tok.stride(1) == 1 and tok.stride(0) % 8 == 0
+            and tok.data_ptr() % 16 == 0):
+        return tok
+    out = padded_like(tok.shape[0], tok.shape[1], torch.bfloat16, tok.device)
+    out.copy_(tok)
+    return out
 
 
 def _tok2d(t: torch.Tensor) -> torch.Tensor:
@@ -365,10 +435,6 @@ def bti_loss(logits, target, mask_a, mask_c, inclusion, connectivity: int, min_t
 # ----------------------------------------------------------------------------------------------
 # tcgen05 GEMM engine (csrc/gemm_tcgen05.cu)
 # ----------------------------------------------------------------------------------------------
-def pad8(c: int) -> int:
-    return (c + 7) // 8 * 8
-
-
 def gemm_bf16_tn(a: torch.Tensor, b: torch.Tensor, bias: Optional[torch.Tensor] = None, n: Optional[int] = None,
                  out_dtype=torch.bfloat16, out: Optional[torch.Tensor] = None) -> torch.Tensor:
     """out[M, ldc] = a[M, K] @ b[N, K]^T (+ bias); a, b bf16 with unit inner stride and row pitches that are multiples of
@@ -420,13 +486,36 @@ def conv_ndhwc_bf16(x_tok: torch.Tensor, batch: int, spatial: Sequence[int], cin
 
 
 # ----------------------------------------------------------------------------------------------
-# batch / instance norm (+ LeakyReLU) on dense token-major matrices (TR:54-55, TN:32-51)
+# batch / instance norm (+ LeakyReLU) on token-major matrices (TR:54-55, TN:32-51)
+# The kernels stream the physical [rows, pitch] matrix; padding channels (pitch > C) are extra don't-care lanes.
 # ----------------------------------------------------------------------------------------------
-def _dense_tokens(t: torch.Tensor) -> torch.Tensor:
+def _physical_rows(t: torch.Tensor):
+    """[rows, C] token view -> (physical [rows, pitch] matrix, C).  Copies only if the rows are not addressable."""
     t = _tok2d(_work_dtype(t))
-    if t.stride(0) != t.shape[1]:
+    full = full_rows(t)
+    if full is None:
         t = t.contiguous()
-    return t
+        full = t
+    return full, t.shape[1]
+
+
+def _rows_like(t: torch.Tensor, rows: int, C: int, pitch: int, dtype) -> torch.Tensor:
+    """Physical [rows, pitch] matrix whose first C columns equal `t` (a view when t already has that layout)."""
+    t = _tok2d(t)
+    if t.dtype == dtype and t.stride(0) == pitch:
+        full = full_rows(t)
+        if full is not None:
+            return full
+    buf = torch.empty((rows, pitch), device=t.device, dtype=dtype)
+    buf[:, :C].copy_(t)
+    return buf
+
+
+def _pad_vec(v: Optional[torch.Tensor], n: int, value: float):
+    if v is None:
+        return None
+    v = v.detach().float().contiguous()
+    return v if v.numel() == n else torch.nn.functional.pad(v, (0, n - v.numel()), value=value)
 
 
 def _norm_partial(C, rows, instances, device):
@@ -440,43 +529,48 @@ class _NormAct(torch.autograd.Function):
 
     @staticmethod
     def forward(ctx, x, gamma, beta, running_mean, running_var, momentum, eps, slope, instances):
-        x = _dense_tokens(x)
-        _need_cuda(x)
-        T, C = x.shape
+        xf, C = _physical_rows(x)
+        _need_cuda(xf)
+        T, P = xf.shape                      # P = physical row pitch >= C
         rows = T // instances
         assert rows * instances == T
         L = _lib.lib()
-        g32 = None if gamma is None else gamma.detach().float().contiguous()
-        b32 = None if beta is None else beta.detach().float().contiguous()
-        partial = _norm_partial(C, rows, instances, x.device)
-        mean = torch.empty(instances * C, device=x.device, dtype=torch.float32)
+        g32, b32 = _pad_vec(gamma, P, 1.0), _pad_vec(beta, P, 0.0)
+        rm = rv = None
+        if running_mean is not None:
+            rm, rv = (running_mean, running_var) if P == C else (_pad_vec(running_mean, P, 0.0), _pad_vec(running_var, P, 1.0))
+        partial = _norm_partial(P, rows, instances, xf.device)
+        mean = torch.empty(instances * P, device=xf.device, dtype=torch.float32)
         invstd = torch.empty_like(mean)
-        check(L.nextou_norm_stats(ptr(x), dtype_code(x), C, ll(rows), instances, cf(eps), ptr(partial), ptr(mean), ptr(invstd),
-                                  ptr(running_mean), ptr(running_var), cf(momentum if momentum is not None else 0.0),
-                                  cstream()), "nextou_norm_stats")
-        y = torch.empty_like(x)
-        check(L.nextou_norm_apply(ptr(x), dtype_code(x), C, ll(rows), instances, ptr(mean), ptr(invstd), ptr(g32), ptr(b32),
+        check(L.nextou_norm_stats(ptr(xf), dtype_code(xf), P, ll(rows), instances, cf(eps), ptr(partial), ptr(mean),
+                                  ptr(invstd), ptr(rm), ptr(rv), cf(momentum if momentum is not None else 0.0), cstream()),
+              "nextou_norm_stats")
+        if running_mean is not None and P != C:
+            running_mean.copy_(rm[:C])
+            running_var.copy_(rv[:C])
+        y = torch.empty_like(xf)
+        check(L.nextou_norm_apply(ptr(xf), dtype_code(xf), P, ll(rows), instances, ptr(mean), ptr(invstd), ptr(g32), ptr(b32),
                                   cf(slope), ptr(y), cstream()), "nextou_norm_apply")
-        ctx.save_for_backward(x, mean, invstd, g32, b32)
-        ctx.meta = (C, rows, instances, slope, gamma is not None, None if gamma is None else gamma.dtype)
-        return y
+        ctx.save_for_backward(xf, mean, invstd, g32, b32)
+        ctx.meta = (C, P, rows, instances, slope, gamma is not None, None if gamma is None else gamma.dtype)
+        return y[:, :C]
 
     @staticmethod
     def backward(ctx, dy):
-        x, mean, invstd, g32, b32 = ctx.saved_tensors
-        C, rows, instances, slope, affine, pdt = ctx.meta
-        dy = _dense_tokens(dy.to(x.dtype))
-        partial = _norm_partial(C, rows, instances, x.device)
-        sums = torch.empty(instances * 2 * C, device=x.device, dtype=torch.float32)
-        dx = torch.empty_like(x)
-        check(_lib.lib().nextou_norm_bwd(ptr(x), ptr(dy), dtype_code(x), C, ll(rows), instances, ptr(mean), ptr(invstd),
+        xf, mean, invstd, g32, b32 = ctx.saved_tensors
+        C, P, rows, instances, slope, affine, pdt = ctx.meta
+        dyf = _rows_like(dy, xf.shape[0], C, P, xf.dtype)
+        partial = _norm_partial(P, rows, instances, xf.device)
+        sums = torch.empty(instances * 2 * P, device=xf.device, dtype=torch.float32)
+        dx = torch.empty_like(xf)
+        check(_lib.lib().nextou_norm_bwd(ptr(xf), ptr(dyf), dtype_code(xf), P, ll(rows), instances, ptr(mean), ptr(invstd),
                                          ptr(g32), ptr(b32), cf(slope), ptr(partial), ptr(sums), ptr(dx), cstream()),
               "nextou_norm_bwd")
         dgamma = dbeta = None
         if affine:
-            s = sums.view(instances, 2, C).sum(0)
-            dbeta, dgamma = s[0].to(pdt), s[1].to(pdt)
-        return dx, dgamma, dbeta, None, None, None, None, None, None
+            s = sums.view(instances, 2, P).sum(0)
+            dbeta, dgamma = s[0, :C].to(pdt), s[1, :C].to(pdt)
+        return dx[:, :C], dgamma, dbeta, None, None, None, None, None, None
 
 
 def norm_act_tokens(x_tok, gamma, beta, running_mean=None, running_var=None, momentum=0.1, eps=1e-5, slope=1.0,
@@ -487,11 +581,54 @@ def norm_act_tokens(x_tok, gamma, beta, running_mean=None, running_var=None, mom
 
 def affine_act_tokens(x_tok, scale, shift, slope=1.0):
     """Eval-mode batch norm: y = lrelu(x * scale[c] + shift[c]) (no autograd: inference only)."""
-    x = _dense_tokens(x_tok)
-    _need_cuda(x)
     if torch.is_grad_enabled() and x_tok.requires_grad:
         raise NextouError("affine_act_tokens (eval-mode norm) does not implement a backward pass")
-    y = torch.empty_like(x)
-    check(_lib.lib().nextou_affine_act(ptr(x), dtype_code(x), x.shape[1], ll(x.shape[0]), ptr(scale.float().contiguous()),
-                                       ptr(shift.float().contiguous()), cf(slope), ptr(y), cstream()), "nextou_affine_act")
-    return y
+    xf, C = _physical_rows(x_tok)
+    _need_cuda(xf)
+    P = xf.shape[1]
+    y = torch.empty_like(xf)
+    check(_lib.lib().nextou_affine_act(ptr(xf), dtype_code(xf), P, ll(xf.shape[0]), ptr(_pad_vec(scale, P, 0.0)),
+                                       ptr(_pad_vec(shift, P, 0.0)), cf(slope), ptr(y), cstream()), "nextou_affine_act")
+    return y[:, :C]
+
+
+# ----------------------------------------------------------------------------------------------
+# residual add / channel concat that keep the channel-padded token layout (ED:322, 389, 817, 932)
+# ----------------------------------------------------------------------------------------------
+class _AddTokens(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, a, b):
+        fa, fb = full_rows(_tok2d(a)), full_rows(_tok2d(b))
+        if fa is not None and fb is not None and fa.shape == fb.shape and fa.dtype == fb.dtype:
+            return (fa + fb)[:, :a.shape[1]]                   # one pass over the physical rows, layout preserved
+        out = padded_like(a.shape[0], a.shape[1], torch.promote_types(a.dtype, b.dtype), a.device)
+        torch.add(a, b, out=out)
+        return out
+
+    @staticmethod
+    def backward(ctx, g):
+        return g, g
+
+
+def add_tokens(a, b):
+    return _AddTokens.apply(a, b)
+
+
+class _CatTokens(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, a, b):
+        ca, cb = a.shape[1], b.shape[1]
+        out = padded_like(a.shape[0], ca + cb, a.dtype, a.device)
+        out[:, :ca].copy_(a)
+        out[:, ca:].copy_(b)
+        ctx.split = ca
+        return out
+
+    @staticmethod
+    def backward(ctx, g):
+        return g[:, :ctx.split], g[:, ctx.split:]
+
+
+def cat_tokens(a, b):
+    """[rows, Ca], [rows, Cb] -> [rows, Ca + Cb] (torch.cat((up, skip), 1) of the decoder, ED:322), padded layout."""
+    return _CatTokens.apply(a, b.to(a.dtype))
