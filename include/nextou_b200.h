@@ -138,6 +138,13 @@ int nextou_bti_ce_bwd(const void* logits, int dtype, long long stride_b, long lo
                       const double* grad_out, void* dlogits, long long dstride_b, long long dstride_c,
                       long long dstride_v, void* stream);
 
+/* Weight gradient of the same convolutions (and, with kd = kh = kw = 1, of the 1x1 layers):
+ *   dW[co][tap][ci] += sum_v dy[v][co] * x[v + tap - pad][ci]     (fp32, the caller zero-fills dW[Cout][taps][cin_stride])
+ * dy / x: bf16 token-major volumes (pitches % 8 == 0).  Both operands are MN-major tcgen05 operands (the voxel axis is
+ * K), the voxel axis is split over CTAs and reduced with fp32 atomics. */
+int nextou_conv3d_ndhwc_wgrad(const void* dy, long long ldy, const void* x, long long ldx, int B, int D, int H, int W,
+                              int Cin, int Cout, int kd, int kh, int kw, float* dW, int cin_stride, void* stream);
+
 /* ------------------------------------------------------------------------------------------
  * Batch / instance normalisation (+ LeakyReLU) on a dense token-major matrix x[instances][rows][C]
  * (C = physical row pitch).  Replaces nn.BatchNorm{2,3}d in train mode (nnUNetTrainer_NexToU.py:54-55),
@@ -161,6 +168,9 @@ int nextou_norm_apply(const void* x, int dtype, int C, long long rows, int insta
 int nextou_norm_bwd(const void* x, const void* dy, int dtype, int C, long long rows, int instances,
                     const float* mean, const float* invstd, const float* gamma, const float* beta, float slope,
                     float* partial, float* sums, void* dx, void* stream);
+/* column sums of a dense [rows][C] matrix: sums[0][C] = sum_r x, sums[1][C] = sum_r x^2 (fp32); `partial` as for
+ * nextou_norm_stats with instances = 1.  Bias gradients of the 1x1 / spatial convolutions (d bias = colsum(dY)). */
+int nextou_colsum(const void* x, int dtype, int C, long long rows, float* partial, float* sums, void* stream);
 /* eval-mode batch norm: y = lrelu(x*scale[c] + shift[c]) with the running statistics folded by the caller */
 int nextou_affine_act(const void* x, int dtype, int C, long long rows, const float* scale, const float* shift,
                       float slope, void* y, void* stream);

@@ -460,3 +460,230 @@ extern "C" int nextou_conv3d_ndhwc_fwd(const void* x, long long ldx, int B, int 
   }
   return launch_gemm(tmA, tmB, p, (long long)B * p.nd * p.nh * p.nw, (cudaStream_t)stream);
 }
+
+// ======================================================================================================
+// Weight gradient:  dW[co][tap][ci] += sum_v dY[v][co] * X[v + tap - pad][ci]
+// GEMM view: M = Cout (128 per CTA), N = Cin tile (<= 256), K = voxels.  The voxel axis is the row axis of both
+// token-major operands, so both are MN-MAJOR tcgen05 operands: a TMA box {64 channels, 64-voxel brick} lands as
+// 64 rows (K) of 128 B (64 channels of M or N) — the canonical SWIZZLE_128B MN-major atom.  Per 64-voxel K block the
+// dY brick is fetched once and multiplied with the tap-shifted X bricks of a whole tap group, each tap owning its
+// own fp32 accumulator slab in tensor memory; the K axis is split over CTAs and the partial dW tiles are reduced
+// with fp32 global atomics (dW is zero-filled by the caller).
+// ======================================================================================================
+namespace nextou {
+
+constexpr int WG_BRICK = 64;               // voxels per K block
+constexpr int WG_BOX_BYTES = WG_BRICK * 128;  // one {64 ch x 64 voxel} box
+constexpr int WG_THREADS = 192;
+
+struct WgradParams {
+  int Cout, Cin;
+  int D, H, W, B;
+  int td, th, tw, nd, nh, nw;     // 64-voxel brick and bricks per axis
+  int kd, kh, kw, pd, ph, pw, taps;
+  int n_tile;                     // N per CTA (multiple of 16, <= 256)
+  int n_boxes;                    // ceil(n_tile / 64)
+  int tap_group;                  // taps per CTA (tap_group * n_tile <= 512 TMEM columns)
+  int n_groups, n_mtiles, n_ntiles, ksplit;
+  int tmem_cols, stages;
+  long long total_bricks;
+  float* dW;                      // [Cout][taps][cin_stride]
+  int cin_stride;
+};
+
+// MN-major SWIZZLE_128B descriptor: 64-element (128 B) MN blocks `lbo` bytes apart, 8-row K groups 1024 B apart
+__device__ __forceinline__ uint64_t make_mnmajor_sw128_desc(uint32_t smem_addr, uint32_t lbo_bytes) {
+  uint64_t d = 0;
+  d |= (uint64_t)((smem_addr >> 4) & 0x3FFF);
+  d |= (uint64_t)((lbo_bytes >> 4) & 0x3FFF) << 16;
+  d |= (uint64_t)(1024 >> 4) << 32;
+  d |= (uint64_t)1 << 46;
+  d |= (uint64_t)2 << 61;
+  return d;
+}
+
+__global__ void __launch_bounds__(WG_THREADS, 1)
+    wgrad_tcgen05_kernel(const __grid_constant__ CUtensorMap tmDY, const __grid_constant__ CUtensorMap tmX,
+                         const WgradParams p) {
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  const int stage_bytes = (2 + p.tap_group * p.n_boxes) * WG_BOX_BYTES;
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + (size_t)p.stages * stage_bytes);
+  uint64_t* empty_bar = full_bar + p.stages;
+  uint64_t* tmem_full_bar = empty_bar + p.stages;
+  uint32_t* tmem_base_holder = reinterpret_cast<uint32_t*>(tmem_full_bar + 1);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  int t = blockIdx.y;
+  const int nt = t % p.n_ntiles; t /= p.n_ntiles;
+  const int mt = t % p.n_mtiles; t /= p.n_mtiles;
+  const int grp = t;
+  const int m0 = mt * 128, n0 = nt * p.n_tile;
+  const int tap0 = grp * p.tap_group;
+  const int ntaps = min(p.tap_group, p.taps - tap0);
+  const int ks = blockIdx.x;
+
+  if (warp == 0 && lane == 0) {
+    prefetch_tmap(&tmDY);
+    prefetch_tmap(&tmX);
+    for (int s = 0; s < p.stages; ++s) {
+      mbar_init(&full_bar[s], 1);
+      mbar_init(&empty_bar[s], 1);
+    }
+    mbar_init(tmem_full_bar, 1);
+    fence_barrier_init();
+  }
+  if (warp == 2) tmem_alloc(tmem_base_holder, (uint32_t)p.tmem_cols);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_base_holder;
+
+  // bricks of this K split: ks, ks + ksplit, ...
+  const long long nb = p.total_bricks > ks ? (p.total_bricks - ks + p.ksplit - 1) / p.ksplit : 0;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      int stage = 0;
+      uint32_t phase = 0;
+      for (long long i = 0; i < nb; ++i) {
+        long long b = ks + i * p.ksplit;
+        const int wt = (int)(b % p.nw); b /= p.nw;
+        const int ht = (int)(b % p.nh); b /= p.nh;
+        const int dt = (int)(b % p.nd); b /= p.nd;
+        const int bn = (int)b;
+        const int w0 = wt * p.tw, h0 = ht * p.th, d0 = dt * p.td;
+        mbar_wait(&empty_bar[stage], phase ^ 1);
+        mbar_expect_tx(&full_bar[stage], (uint32_t)((2 + ntaps * p.n_boxes) * WG_BOX_BYTES));
+        uint8_t* st = smem + (size_t)stage * stage_bytes;
+        tma_load_5d(st, &tmDY, &full_bar[stage], m0, w0, h0, d0, bn);
+        tma_load_5d(st + WG_BOX_BYTES, &tmDY, &full_bar[stage], m0 + 64, w0, h0, d0, bn);
+        for (int tp = 0; tp < ntaps; ++tp) {
+          const int tap = tap0 + tp;
+          const int kw_ = tap % p.kw, kh_ = (tap / p.kw) % p.kh, kd_ = tap / (p.kw * p.kh);
+          for (int j = 0; j < p.n_boxes; ++j)
+            tma_load_5d(st + (size_t)(2 + tp * p.n_boxes + j) * WG_BOX_BYTES, &tmX, &full_bar[stage], n0 + 64 * j,
+                        w0 + kw_ - p.pw, h0 + kh_ - p.ph, d0 + kd_ - p.pd, bn);
+        }
+        if (++stage == p.stages) { stage = 0; phase ^= 1; }
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0 && nb > 0) {
+      // D fp32, A/B bf16, both MN-major (bits 15, 16)
+      const uint32_t idesc = make_idesc_bf16(128, p.n_tile) | (1u << 15) | (1u << 16);
+      int stage = 0;
+      uint32_t phase = 0;
+      for (long long i = 0; i < nb; ++i) {
+        mbar_wait(&full_bar[stage], phase);
+        tc_fence_after();
+        const uint32_t st = smem_u32(smem + (size_t)stage * stage_bytes);
+        for (int tp = 0; tp < ntaps; ++tp) {
+          const uint32_t xb = st + (uint32_t)(2 + tp * p.n_boxes) * WG_BOX_BYTES;
+#pragma unroll
+          for (int k = 0; k < WG_BRICK / 16; ++k) {
+            // 16 voxels = 16 rows of 128 B = 2048 B along K
+            const uint64_t adesc = make_mnmajor_sw128_desc(st + k * 2048, WG_BOX_BYTES);
+            const uint64_t bdesc = make_mnmajor_sw128_desc(xb + k * 2048, WG_BOX_BYTES);
+            umma_f16(tmem_base + (uint32_t)(tp * p.n_tile), adesc, bdesc, idesc, (i | k) != 0 ? 1u : 0u);
+          }
+        }
+        umma_commit(&empty_bar[stage]);
+        if (++stage == p.stages) { stage = 0; phase ^= 1; }
+      }
+      umma_commit(tmem_full_bar);
+    }
+  } else if (nb > 0) {
+    mbar_wait(tmem_full_bar, 0);
+    tc_fence_after();
+    const int q = warp & 3;
+    const int co = m0 + q * 32 + lane;
+    for (int tp = 0; tp < ntaps; ++tp) {
+      for (int c = 0; c < p.n_tile; c += 16) {
+        uint32_t raw[16];
+        tmem_ld16(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(tp * p.n_tile + c), raw);
+        tmem_ld_wait();
+        if (co < p.Cout) {
+          float* dst = p.dW + ((long long)co * p.taps + (tap0 + tp)) * p.cin_stride + n0 + c;
+#pragma unroll
+          for (int j = 0; j < 16; ++j)
+            if (n0 + c + j < p.Cin) atomicAdd(dst + j, __uint_as_float(raw[j]));
+        }
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 2) tmem_dealloc(tmem_base, (uint32_t)p.tmem_cols);
+}
+
+}  // namespace nextou
+
+// dW[Cout][taps][cin_stride] (fp32, caller zero-fills) += wgrad of a stride-1 'same' convolution.  dy: bf16 tokens
+// [B*D*H*W][ldy] (Cout channels), x: bf16 tokens [..][ldx] (Cin channels).  A 1x1 layer is kd = kh = kw = 1.
+extern "C" int nextou_conv3d_ndhwc_wgrad(const void* dy, long long ldy, const void* x, long long ldx, int B, int D, int H,
+                                         int W, int Cin, int Cout, int kd, int kh, int kw, float* dW, int cin_stride,
+                                         void* stream) {
+  NEXTOU_REQUIRE(dy && x && dW, "conv3d_ndhwc_wgrad: null pointer");
+  NEXTOU_REQUIRE(B > 0 && D > 0 && H > 0 && W > 0 && Cin > 0 && Cout > 0 && cin_stride >= Cin, "conv3d_ndhwc_wgrad: bad shape");
+  NEXTOU_REQUIRE(kd % 2 == 1 && kh % 2 == 1 && kw % 2 == 1, "conv3d_ndhwc_wgrad: odd kernel sizes only");
+  NEXTOU_REQUIRE(ldy % 8 == 0 && ldy >= Cout && ldx % 8 == 0 && ldx >= Cin, "conv3d_ndhwc_wgrad: pitches must be multiples of 8");
+  NEXTOU_REQUIRE(((uintptr_t)dy & 15) == 0 && ((uintptr_t)x & 15) == 0, "conv3d_ndhwc_wgrad: 16-byte alignment");
+  WgradParams p = {};
+  p.Cout = Cout; p.Cin = Cin; p.D = D; p.H = H; p.W = W; p.B = B;
+  p.kd = kd; p.kh = kh; p.kw = kw; p.pd = kd / 2; p.ph = kh / 2; p.pw = kw / 2; p.taps = kd * kh * kw;
+  p.dW = dW; p.cin_stride = cin_stride;
+  // 64-voxel brick with power-of-two edges minimising the brick count (ties: widest along W)
+  long long best = -1;
+  for (int a = 64; a >= 1; a >>= 1)
+    for (int b = 64 / a; b >= 1; b >>= 1) {
+      const int c = 64 / (a * b);
+      const long long bricks = (long long)((W + a - 1) / a) * ((H + b - 1) / b) * ((D + c - 1) / c);
+      if (best < 0 || bricks < best) { best = bricks; p.tw = a; p.th = b; p.td = c; }
+    }
+  p.nw = (W + p.tw - 1) / p.tw; p.nh = (H + p.th - 1) / p.th; p.nd = (D + p.td - 1) / p.td;
+  p.total_bricks = (long long)B * p.nd * p.nh * p.nw;
+  p.n_ntiles = (Cin + 255) / 256;
+  p.n_tile = ((Cin + p.n_ntiles - 1) / p.n_ntiles + 15) / 16 * 16;
+  p.n_boxes = (p.n_tile + 63) / 64;
+  p.n_mtiles = (Cout + 127) / 128;
+  // taps per CTA: TMEM (512 columns) and shared memory (2 stages) limits
+  int tg = 512 / p.n_tile;
+  const int smem_budget = 200 * 1024;
+  while (tg > 1 && 2 * (2 + tg * p.n_boxes) * WG_BOX_BYTES > smem_budget) --tg;
+  if (tg > p.taps) tg = p.taps;
+  NEXTOU_REQUIRE(tg >= 1 && 2 * (2 + tg * p.n_boxes) * WG_BOX_BYTES <= smem_budget, "conv3d_ndhwc_wgrad: tile does not fit");
+  p.tap_group = tg;
+  p.n_groups = (p.taps + tg - 1) / tg;
+  p.tmem_cols = pow2_cols(tg * p.n_tile);
+  p.stages = 2;
+  const long long tiles = (long long)p.n_groups * p.n_mtiles * p.n_ntiles;
+  long long ksplit = (2LL * num_sms() + tiles - 1) / tiles;
+  if (ksplit > p.total_bricks) ksplit = p.total_bricks;
+  if (ksplit < 1) ksplit = 1;
+  p.ksplit = (int)ksplit;
+  CUtensorMap tmDY, tmX;
+  {
+    cuuint64_t dims[5] = {(cuuint64_t)Cout, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)D, (cuuint64_t)B};
+    cuuint64_t str[4] = {(cuuint64_t)ldy * 2, (cuuint64_t)ldy * 2 * W, (cuuint64_t)ldy * 2 * W * H,
+                         (cuuint64_t)ldy * 2 * W * H * D};
+    cuuint32_t box[5] = {64, (cuuint32_t)p.tw, (cuuint32_t)p.th, (cuuint32_t)p.td, 1};
+    int rc = encode_bf16_map(&tmDY, dy, 5, dims, str, box, "wgrad dY");
+    if (rc) return rc;
+  }
+  {
+    cuuint64_t dims[5] = {(cuuint64_t)Cin, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)D, (cuuint64_t)B};
+    cuuint64_t str[4] = {(cuuint64_t)ldx * 2, (cuuint64_t)ldx * 2 * W, (cuuint64_t)ldx * 2 * W * H,
+                         (cuuint64_t)ldx * 2 * W * H * D};
+    cuuint32_t box[5] = {64, (cuuint32_t)p.tw, (cuuint32_t)p.th, (cuuint32_t)p.td, 1};
+    int rc = encode_bf16_map(&tmX, x, 5, dims, str, box, "wgrad X");
+    if (rc) return rc;
+  }
+  const size_t smem = 1024 + (size_t)p.stages * (2 + tg * p.n_boxes) * WG_BOX_BYTES + (2 * p.stages + 1) * sizeof(uint64_t) + 16;
+  int rc = ensure_smem(wgrad_tcgen05_kernel, smem);
+  if (rc) return rc;
+  NEXTOU_REQUIRE(tiles <= 65535, "conv3d_ndhwc_wgrad: too many tiles");
+  dim3 grid((unsigned)p.ksplit, (unsigned)tiles);
+  wgrad_tcgen05_kernel<<<grid, WG_THREADS, smem, (cudaStream_t)stream>>>(tmDY, tmX, p);
+  return check_launch("wgrad_tcgen05_kernel");
+}

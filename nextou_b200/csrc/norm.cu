@@ -416,3 +416,23 @@ extern "C" int nextou_affine_act(const void* x, int dtype, int C, long long rows
                                                                                         scale, shift, slope, (T*)y);)
   return check_launch("affine_act_kernel");
 }
+
+// Per-channel column sums of a [rows][C] matrix: sums[0][C] = sum_r x, sums[1][C] = sum_r x^2 (fp32).  Used for the
+// bias gradients of the GEMM / convolution layers (d bias = column sum of dY).
+extern "C" int nextou_colsum(const void* x, int dtype, int C, long long rows, float* partial, float* sums,
+                             void* stream) {
+  NEXTOU_REQUIRE(x && partial && sums, "colsum: null pointer");
+  SweepPlan p;
+  int rc = plan_sweep(C, rows, 1, p);
+  if (rc) return rc;
+  cudaStream_t st = (cudaStream_t)stream;
+  DISPATCH_T(dtype, {
+    rc = ensure_smem(norm_stats_kernel<T>, p.smem);
+    if (rc) return rc;
+    norm_stats_kernel<T><<<dim3(p.nblk, 1), p.threads, p.smem, st>>>((const T*)x, C, p.R, rows, partial);
+  })
+  rc = check_launch("norm_stats_kernel");
+  if (rc) return rc;
+  norm_bwd_finalize_kernel<<<dim3((2 * C + 31) / 32, 1), 32 * FIN_SLICES, 0, st>>>(partial, p.nblk, C, 1, sums);
+  return check_launch("norm_bwd_finalize_kernel");
+}

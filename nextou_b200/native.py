@@ -2,8 +2,7 @@
 
 forward  : hand-written tcgen05 kernels (TMA -> swizzled smem -> tcgen05.mma -> TMEM -> epilogue).
 backward : data gradients through the same kernels (a GEMM / convolution with the transposed / flipped weight
-           pack); weight gradients are plain library contractions for now (cuBLAS `dY^T X` for the 1x1 layers,
-           cuDNN wgrad for the spatial convolutions) — DESIGN.md tracks them as the next kernels to write.
+           pack); weight gradients through the MN-major tcgen05 kernel (voxel axis = K, split over CTAs).
 Token matrices are [rows, C] views with a row pitch that is a multiple of 8 elements (channel padding, don't-care).
 """
 from __future__ import annotations
@@ -43,9 +42,10 @@ class _LinearTokens(torch.autograd.Function):
             wt = ops.tma_ready_bf16(w2d.detach().t())            # [K, N] bf16: B operand of dX = dY W
             dx = ops.gemm_bf16_tn(dyb, wt, None, n=K)[:, :K]
         if ctx.needs_input_grad[1]:
-            dw = torch.matmul(dyb.t(), xb).to(w2d.dtype)         # library GEMM (cuBLAS), fp32 accumulate
+            # dW = dY^T X through the MN-major tcgen05 weight-gradient kernel (a 1x1 "convolution" over T voxels)
+            dw = ops.conv_wgrad_bf16(dyb, xb, 1, (xb.shape[0],), K, N, (1,)).reshape(N, K).to(w2d.dtype)
         if ctx.has_bias and ctx.needs_input_grad[2]:
-            db = dyb.float().sum(0).to(ctx.bias_dtype)
+            db = ops.colsum_tokens(dyb).to(ctx.bias_dtype)
         return dx, dw, db
 
 
@@ -85,16 +85,10 @@ class _ConvTokens(torch.autograd.Function):
             wpack_t = ops.pack_conv_weight(weight.detach(), transpose_flip=True)
             dx = ops.conv_ndhwc_bf16(dyb, batch, spatial, cout, wpack_t, cin, ks, None)[:, :cin]
         if ctx.needs_input_grad[1]:
-            # library weight gradient (cuDNN wgrad) on the logical views
-            xin = ops.from_tokens(xb, batch, spatial)
-            gout = ops.from_tokens(dyb, batch, spatial)
-            pad = [k // 2 for k in ks]
-            one = [1] * len(ks)
-            _, dw, _ = torch.ops.aten.convolution_backward(gout, xin, weight.detach().to(torch.bfloat16), None, one, pad, one,
-                                                           False, [0] * len(ks), 1, [False, True, False])
+            dw = ops.conv_wgrad_bf16(dyb, xb, batch, spatial, cin, cout, ks)
             dw = dw.to(weight.dtype)
         if has_bias and ctx.needs_input_grad[2]:
-            db = dyb.float().sum(0).to(bdt)
+            db = ops.colsum_tokens(dyb).to(bdt)
         return dx, dw, db, None, None
 
 

@@ -54,8 +54,7 @@ def _token_pitch(x: torch.Tensor):
     return pitch
 
 
-def as_tokens(x: torch.Tensor) -> torch.Tensor:
-    """(N, C, *spatial) -> [N*prod(spatial), C] view with strides (pitch, 1); copies only if x is not token-major."""
+def _as_tokens_view(x: torch.Tensor) -> torch.Tensor:
     C = x.shape[1]
     T = x.numel() // C
     pitch = _token_pitch(x)
@@ -67,8 +66,7 @@ def as_tokens(x: torch.Tensor) -> torch.Tensor:
     return x.as_strided((T, C), (pitch, 1), x.storage_offset())
 
 
-def from_tokens(tok: torch.Tensor, batch: int, spatial: Sequence[int]) -> torch.Tensor:
-    """[rows, C] token rows (strides (pitch, 1)) -> logical (N, C, *spatial) view, physically token-major."""
+def _from_tokens_view(tok: torch.Tensor, batch: int, spatial: Sequence[int]) -> torch.Tensor:
     C = tok.shape[1]
     if tok.stride(1) != 1 and C > 1:
         tok = tok.contiguous()
@@ -80,6 +78,44 @@ def from_tokens(tok: torch.Tensor, batch: int, spatial: Sequence[int]) -> torch.
         acc *= spatial[i]
     strides[0] = acc
     return tok.as_strided((batch, C, *spatial), tuple(strides), tok.storage_offset())
+
+
+class _AsTokens(torch.autograd.Function):
+    """Re-view only: the backward is the inverse re-view (never torch's generic as_strided backward, which
+    zero-fills the whole base buffer and scatters into it)."""
+
+    @staticmethod
+    def forward(ctx, x):
+        ctx.meta = (x.shape[0], tuple(x.shape[2:]))
+        return _as_tokens_view(x)
+
+    @staticmethod
+    def backward(ctx, g):
+        return _from_tokens_view(g, *ctx.meta)
+
+
+class _FromTokens(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, tok, batch, spatial):
+        return _from_tokens_view(tok, batch, spatial)
+
+    @staticmethod
+    def backward(ctx, g):
+        return _as_tokens_view(g), None, None
+
+
+def as_tokens(x: torch.Tensor) -> torch.Tensor:
+    """(N, C, *spatial) -> [N*prod(spatial), C] view with strides (pitch, 1); copies only if x is not token-major."""
+    if x.requires_grad and torch.is_grad_enabled():
+        return _AsTokens.apply(x)
+    return _as_tokens_view(x)
+
+
+def from_tokens(tok: torch.Tensor, batch: int, spatial: Sequence[int]) -> torch.Tensor:
+    """[rows, C] token rows (strides (pitch, 1)) -> logical (N, C, *spatial) view, physically token-major."""
+    if tok.requires_grad and torch.is_grad_enabled():
+        return _FromTokens.apply(tok, batch, tuple(spatial))
+    return _from_tokens_view(tok, batch, spatial)
 
 
 def _rows_in_bounds(t: torch.Tensor, pitch: int) -> bool:
@@ -485,6 +521,25 @@ def conv_ndhwc_bf16(x_tok: torch.Tensor, batch: int, spatial: Sequence[int], cin
     return out
 
 
+def conv_wgrad_bf16(dy_tok: torch.Tensor, x_tok: torch.Tensor, batch: int, spatial: Sequence[int], cin: int, cout: int,
+                    ksize: Sequence[int]) -> torch.Tensor:
+    """fp32 weight gradient (Cout, Cin, *ksize) of a stride-1 'same' convolution (1x1: ksize of ones) from bf16
+    token-major dY [rows, Cout] and X [rows, Cin] (csrc/gemm_tcgen05.cu, MN-major tcgen05 operands)."""
+    _need_cuda(dy_tok, x_tok)
+    assert dy_tok.dtype == torch.bfloat16 and x_tok.dtype == torch.bfloat16
+    sp = list(spatial)
+    ks = list(ksize)
+    while len(sp) < 3:
+        sp, ks = [1] + sp, [1] + ks
+    D, H, W = sp
+    taps = ks[0] * ks[1] * ks[2]
+    dw = torch.zeros((cout, taps, cin), device=x_tok.device, dtype=torch.float32)
+    check(_lib.lib().nextou_conv3d_ndhwc_wgrad(ptr(dy_tok), ll(dy_tok.stride(0)), ptr(x_tok), ll(x_tok.stride(0)), batch, D, H,
+                                               W, cin, cout, ks[0], ks[1], ks[2], ptr(dw), cin, cstream()),
+          "nextou_conv3d_ndhwc_wgrad")
+    return dw.permute(0, 2, 1).reshape(cout, cin, *ksize)
+
+
 # ----------------------------------------------------------------------------------------------
 # batch / instance norm (+ LeakyReLU) on token-major matrices (TR:54-55, TN:32-51)
 # The kernels stream the physical [rows, pitch] matrix; padding channels (pitch > C) are extra don't-care lanes.
@@ -632,3 +687,14 @@ class _CatTokens(torch.autograd.Function):
 def cat_tokens(a, b):
     """[rows, Ca], [rows, Cb] -> [rows, Ca + Cb] (torch.cat((up, skip), 1) of the decoder, ED:322), padded layout."""
     return _CatTokens.apply(a, b.to(a.dtype))
+
+
+def colsum_tokens(tok: torch.Tensor) -> torch.Tensor:
+    """fp32 [C] column sums of a [rows, C] token view (bias gradients), one streaming pass (csrc/norm.cu)."""
+    xf, C = _physical_rows(tok)
+    _need_cuda(xf)
+    T, P = xf.shape
+    partial = _norm_partial(P, T, 1, xf.device)
+    sums = torch.empty(2 * P, device=xf.device, dtype=torch.float32)
+    check(_lib.lib().nextou_colsum(ptr(xf), dtype_code(xf), P, ll(T), ptr(partial), ptr(sums), cstream()), "nextou_colsum")
+    return sums[:C]

@@ -72,3 +72,28 @@ def test_conv_ndhwc_implicit_gemm(B, spatial, cin, cout, ks):
                              None, out_dtype=torch.float32)
     gotdx = dx.cpu()[:, :cin].reshape(B, *spatial, cin).permute(0, dim + 1, *range(1, dim + 1))
     assert _rel(gotdx, xg.grad) < 1e-5, _rel(gotdx, xg.grad)
+
+
+@pytest.mark.parametrize("B,spatial,cin,cout,ks", [
+    (1, (4, 16, 24), 33, 33, (1, 3, 3)), (1, (8, 12, 16), 66, 66, (3, 3, 3)), (2, (4, 7, 6), 324, 324, (3, 3, 3)),
+    (1, (6, 10, 20), 132, 66, (3, 3, 3)), (1, (16, 28, 24), 264, 132, (3, 3, 3)), (1, (5, 9, 11), 8, 264, (3, 3, 3)),
+    (2, (12, 20), 32, 48, (3, 3)), (1, (32, 56, 48), 132, 132, (1, 1, 1)), (1, (2, 7, 12), 648, 324, (1, 1, 1)),
+    (1, (8, 64, 96), 1, 33, (1, 3, 3))])
+def test_conv_wgrad_mn_major(B, spatial, cin, cout, ks):
+    """Weight gradient through the MN-major tcgen05 path vs autograd of F.conv on the same bf16-valued operands."""
+    from nextou_b200 import ops
+    g = torch.Generator().manual_seed(cin * 3 + cout)
+    dim = len(spatial)
+    x = torch.randn(B, cin, *spatial, generator=g).bfloat16()
+    dy = torch.randn(B, cout, *spatial, generator=g).bfloat16()
+    w = torch.zeros(cout, cin, *ks, requires_grad=True)
+    conv = F.conv3d if dim == 3 else F.conv2d
+    conv(x.float(), w, None, padding=[k // 2 for k in ks]).backward(dy.float())
+    V = B * x[0, 0].numel()
+    xt = torch.full((V, ops.pad8(cin)), float("nan"), dtype=torch.bfloat16)
+    xt[:, :cin] = x.permute(0, *range(2, 2 + dim), 1).reshape(-1, cin)
+    dt = torch.full((V, ops.pad8(cout)), float("nan"), dtype=torch.bfloat16)
+    dt[:, :cout] = dy.permute(0, *range(2, 2 + dim), 1).reshape(-1, cout)
+    dw = ops.conv_wgrad_bf16(dt.to(DEV)[:, :cout], xt.to(DEV)[:, :cin], B, spatial, cin, cout, ks)
+    assert dw.shape == w.shape and dw.dtype == torch.float32
+    assert _rel(dw.cpu(), w.grad) < 1e-5, _rel(dw.cpu(), w.grad)

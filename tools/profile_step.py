@@ -31,6 +31,8 @@ def main():
             outs = model(x); loss = loss_fn(outs, t)
         loss.backward()
         torch.nn.utils.clip_grad_norm_(params, 12); opt.step()
+    global _step_fn
+    _step_fn = step
     for _ in range(3): step()
     torch.cuda.synchronize()
     with profile(activities=[ProfilerActivity.CUDA, ProfilerActivity.CPU]) as prof:
@@ -43,4 +45,26 @@ def main():
     print(f"total CUDA kernel time per step: {tot:.1f} ms")
     for k, ms, n in rows[:45]:
         print(f"{ms:9.2f} ms {100*ms/tot:5.1f}% n={n:6.1f}  {k[:130]}")
+
+
+def copy_breakdown(steps=1):
+    """Which aten::copy_ / contiguous / fill calls cost GPU time, by shape and Python call site."""
+    import torch
+    from torch.profiler import profile, ProfilerActivity
+    global _step_fn
+    dev = torch.device("cuda", 0)
+    with profile(activities=[ProfilerActivity.CUDA, ProfilerActivity.CPU], record_shapes=True, with_stack=True) as prof:
+        for _ in range(steps):
+            _step_fn()
+        torch.cuda.synchronize()
+    ka = prof.key_averages(group_by_input_shape=True, group_by_stack_n=6)
+    rows = [e for e in ka if e.key in ("aten::copy_", "aten::fill_", "aten::add", "aten::sum", "aten::add_", "aten::zero_", "aten::mul")]
+    rows.sort(key=lambda e: -e.device_time_total)
+    for e in rows[:40]:
+        stack = [s for s in e.stack if "nextou_b200" in s or "bench" in s or "tools" in s][:3]
+        print(f"{e.device_time_total/1e3/steps:8.2f} ms n={e.count/steps:5.0f} {e.key:12s} {str(e.input_shapes)[:70]:70s} {' <- '.join(x.split('/')[-1][:60] for x in stack)}")
+
+
 main()
+if len(sys.argv) > 2 and sys.argv[2] == 'copies':
+    copy_breakdown()
