@@ -138,6 +138,12 @@ int nextou_bti_ce_bwd(const void* logits, int dtype, long long stride_b, long lo
                       const double* grad_out, void* dlogits, long long dstride_b, long long dstride_c,
                       long long dstride_v, void* stream);
 
+/* Same contract, restricted to kh, kw in {1, 3} (all non-down-sampling NexToU convolutions): halo-reuse variant
+ * (csrc/conv_tcgen05.cu) — one haloed activation box per depth tap feeds all in-plane taps through row-shifted
+ * UMMA descriptors, cutting the L2 -> SM activation traffic 6.4x. */
+int nextou_conv3d_ndhwc_halo_fwd(const void* x, long long ldx, int B, int D, int H, int W, int Cin, const void* wpack,
+                                 int Cout, int kd, int kh, int kw, const float* bias, void* out, long long ldo,
+                                 int out_dtype, void* stream);
 /* Weight gradient of the same convolutions (and, with kd = kh = kw = 1, of the 1x1 layers):
  *   dW[co][tap][ci] += sum_v dy[v][co] * x[v + tap - pad][ci]     (fp32, the caller zero-fills dW[Cout][taps][cin_stride])
  * dy / x: bf16 token-major volumes (pitches % 8 == 0).  Both operands are MN-major tcgen05 operands (the voxel axis is

@@ -503,8 +503,12 @@ def pack_conv_weight(w: torch.Tensor, transpose_flip: bool = False) -> torch.Ten
     return wp.reshape(co, taps * ci_pad).to(torch.bfloat16).contiguous()
 
 
+CONV_HALO = True  # use the halo-reuse kernel (csrc/conv_tcgen05.cu) whenever kh, kw are 1 or 3
+
+
 def conv_ndhwc_bf16(x_tok: torch.Tensor, batch: int, spatial: Sequence[int], cin: int, wpack: torch.Tensor, cout: int,
-                    ksize: Sequence[int], bias: Optional[torch.Tensor] = None, out_dtype=torch.bfloat16) -> torch.Tensor:
+                    ksize: Sequence[int], bias: Optional[torch.Tensor] = None, out_dtype=torch.bfloat16,
+                    halo: Optional[bool] = None) -> torch.Tensor:
     """Stride-1 'same' convolution on a token-major bf16 volume [B*prod(spatial), ldx] -> padded [.., pad8(cout)]."""
     _need_cuda(x_tok, wpack)
     assert x_tok.dtype == torch.bfloat16 and x_tok.stride(1) == 1 and wpack.dtype == torch.bfloat16
@@ -515,9 +519,10 @@ def conv_ndhwc_bf16(x_tok: torch.Tensor, batch: int, spatial: Sequence[int], cin
     D, H, W = sp
     out = torch.empty((batch * D * H * W, pad8(cout)), device=x_tok.device, dtype=out_dtype)
     bias32 = None if bias is None else bias.detach().float().contiguous()
-    check(_lib.lib().nextou_conv3d_ndhwc_fwd(ptr(x_tok), ll(x_tok.stride(0)), batch, D, H, W, cin, ptr(wpack), cout, ks[0],
-                                             ks[1], ks[2], ptr(bias32), ptr(out), ll(out.stride(0)), dtype_code(out),
-                                             cstream()), "nextou_conv3d_ndhwc_fwd")
+    use_halo = (CONV_HALO if halo is None else halo) and ks[1] in (1, 3) and ks[2] in (1, 3)
+    fn = _lib.lib().nextou_conv3d_ndhwc_halo_fwd if use_halo else _lib.lib().nextou_conv3d_ndhwc_fwd
+    check(fn(ptr(x_tok), ll(x_tok.stride(0)), batch, D, H, W, cin, ptr(wpack), cout, ks[0], ks[1], ks[2], ptr(bias32),
+             ptr(out), ll(out.stride(0)), dtype_code(out), cstream()), "nextou_conv3d_ndhwc_fwd")
     return out
 
 

@@ -41,8 +41,10 @@ def test_gemm_bf16_tn(M, N, K, ld_extra, out_dtype):
 @pytest.mark.parametrize("B,spatial,cin,cout,ks", [
     (1, (4, 16, 24), 33, 33, (1, 3, 3)), (1, (8, 12, 16), 66, 66, (3, 3, 3)), (2, (4, 7, 6), 324, 324, (3, 3, 3)),
     (1, (6, 10, 20), 132, 66, (3, 3, 3)), (1, (1, 20, 36), 16, 40, (1, 3, 3)), (1, (16, 28, 24), 264, 132, (3, 3, 3)),
-    (1, (5, 9, 11), 8, 264, (3, 3, 3)), (2, (12, 20), 32, 48, (3, 3))])
-def test_conv_ndhwc_implicit_gemm(B, spatial, cin, cout, ks):
+    (1, (5, 9, 11), 8, 264, (3, 3, 3)), (2, (12, 20), 32, 48, (3, 3)), (1, (3, 18, 10), 64, 32, (1, 3, 1)),
+    (1, (3, 18, 10), 64, 32, (1, 1, 3)), (1, (5, 18, 10), 64, 32, (3, 1, 1))])
+@pytest.mark.parametrize("halo", [False, True], ids=["pertap", "halo"])
+def test_conv_ndhwc_implicit_gemm(B, spatial, cin, cout, ks, halo):
     from nextou_b200 import ops
     g = torch.Generator().manual_seed(cin * 7 + cout)
     dim = len(spatial)
@@ -57,7 +59,7 @@ def test_conv_ndhwc_implicit_gemm(B, spatial, cin, cout, ks):
     if ldx > cin:
         tok[:, cin:] = float("nan")                         # padding lanes must never be read
     out = ops.conv_ndhwc_bf16(tok.to(DEV), B, spatial, cin, ops.pack_conv_weight(w).to(DEV), cout, ks, bias.to(DEV),
-                              out_dtype=torch.float32)
+                              out_dtype=torch.float32, halo=halo)
     got = out.cpu()[:, :cout].reshape(B, *spatial, cout).permute(0, dim + 1, *range(1, dim + 1))
     assert torch.count_nonzero(out.cpu()[:, cout:]) == 0
     assert _rel(got, want) < 1e-5, _rel(got, want)
@@ -69,7 +71,7 @@ def test_conv_ndhwc_implicit_gemm(B, spatial, cin, cout, ks):
     dtok = torch.zeros(B * x[0, 0].numel(), ops.pad8(cout), dtype=torch.bfloat16)
     dtok[:, :cout] = dy.permute(0, *range(2, 2 + dim), 1).reshape(-1, cout)
     dx = ops.conv_ndhwc_bf16(dtok.to(DEV), B, spatial, cout, ops.pack_conv_weight(w, transpose_flip=True).to(DEV), cin, ks,
-                             None, out_dtype=torch.float32)
+                             None, out_dtype=torch.float32, halo=halo)
     gotdx = dx.cpu()[:, :cin].reshape(B, *spatial, cin).permute(0, dim + 1, *range(1, dim + 1))
     assert _rel(gotdx, xg.grad) < 1e-5, _rel(gotdx, xg.grad)
 
