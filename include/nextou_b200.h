@@ -151,6 +151,11 @@ int nextou_conv3d_ndhwc_halo_fwd(const void* x, long long ldx, int B, int D, int
 int nextou_conv3d_ndhwc_wgrad(const void* dy, long long ldy, const void* x, long long ldx, int B, int D, int H, int W,
                               int Cin, int Cout, int kd, int kh, int kw, float* dW, int cin_stride, void* stream);
 
+/* Same contract, kh, kw in {1, 3}: halo-reuse variant (one haloed X box per 8x8 voxel brick feeds all in-plane taps). */
+int nextou_conv3d_ndhwc_halo_wgrad(const void* dy, long long ldy, const void* x, long long ldx, int B, int D, int H,
+                                   int W, int Cin, int Cout, int kd, int kh, int kw, float* dW, int cin_stride,
+                                   void* stream);
+
 /* ------------------------------------------------------------------------------------------
  * Batch / instance normalisation (+ LeakyReLU) on a dense token-major matrix x[instances][rows][C]
  * (C = physical row pitch).  Replaces nn.BatchNorm{2,3}d in train mode (nnUNetTrainer_NexToU.py:54-55),

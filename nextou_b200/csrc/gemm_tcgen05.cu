@@ -114,7 +114,7 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1)
     }
   } else if (warp == 1) {
     // ===================== MMA issuer =====================
-    if (lane == 0) {
+    {  // whole warp: warp-uniform control flow (descriptors stay in uniform registers), one elected lane issues
       const uint32_t idesc = make_idesc_bf16(GEMM_BM, p.block_n);
       int stage = 0;
       uint32_t phase = 0;
@@ -123,15 +123,19 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1)
         tc_fence_after();
         const uint64_t adesc = make_kmajor_sw128_desc(smem_u32(smA + (size_t)stage * a_bytes));
         const uint64_t bdesc = make_kmajor_sw128_desc(smem_u32(smB + (size_t)stage * b_bytes));
+        if (elect_one()) {
 #pragma unroll
-        for (int k = 0; k < GEMM_BK / 16; ++k) {
-          // advance 16 bf16 = 32 B along K inside the 128-byte swizzle row: +2 in the (>>4) start-address field
-          umma_f16(tmem_base, adesc + (uint64_t)(2 * k), bdesc + (uint64_t)(2 * k), idesc, (it | k) != 0 ? 1u : 0u);
+          for (int k = 0; k < GEMM_BK / 16; ++k) {
+            // advance 16 bf16 = 32 B along K inside the 128-byte swizzle row: +2 in the (>>4) start-address field
+            umma_f16(tmem_base, adesc + (uint64_t)(2 * k), bdesc + (uint64_t)(2 * k), idesc, (it | k) != 0 ? 1u : 0u);
+          }
+          umma_commit(&empty_bar[stage]);  // smem slot reusable once these MMAs have read it
         }
-        umma_commit(&empty_bar[stage]);  // smem slot reusable once these MMAs have read it
+        __syncwarp();
         if (++stage == p.stages) { stage = 0; phase ^= 1; }
       }
-      umma_commit(tmem_full_bar);        // accumulator complete
+      if (elect_one()) umma_commit(tmem_full_bar);        // accumulator complete
+      __syncwarp();
     }
   } else {
     // ===================== epilogue (warps 2..5 -> TMEM lane quarters warp%4) =====================

@@ -20,6 +20,7 @@ __device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
 __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
   const uint32_t addr = smem_u32(bar);
   uint32_t done = 0;
+  const long long t_start = clock64();
   for (uint32_t spin = 0; !done; ++spin) {
     asm volatile(
         "{\n"
@@ -30,7 +31,7 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
         : "=r"(done)
         : "r"(addr), "r"(parity)
         : "memory");
-    if (spin > (1u << 24)) __trap();
+    if ((spin & 1023u) == 1023u && clock64() - t_start > 4000000000LL) __trap();  // ~2 s: never hang the GPU
   }
 }
 __device__ __forceinline__ void fence_barrier_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
@@ -53,6 +54,19 @@ __device__ __forceinline__ void tma_load_5d(void* dst, const CUtensorMap* map, u
 }
 __device__ __forceinline__ void prefetch_tmap(const CUtensorMap* map) {
   asm volatile("prefetch.tensormap [%0];" ::"l"(map) : "memory");
+}
+
+// one lane of a fully converged warp (warp-uniform control flow around it keeps descriptors in uniform registers)
+__device__ __forceinline__ bool elect_one() {
+  uint32_t pred = 0;
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "elect.sync _|p, 0xffffffff;\n"
+      "selp.u32 %0, 1, 0, p;\n"
+      "}\n"
+      : "=r"(pred));
+  return pred != 0;
 }
 
 __device__ __forceinline__ void tmem_alloc(uint32_t* dst_smem, uint32_t ncols) {

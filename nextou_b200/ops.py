@@ -527,7 +527,7 @@ def conv_ndhwc_bf16(x_tok: torch.Tensor, batch: int, spatial: Sequence[int], cin
 
 
 def conv_wgrad_bf16(dy_tok: torch.Tensor, x_tok: torch.Tensor, batch: int, spatial: Sequence[int], cin: int, cout: int,
-                    ksize: Sequence[int]) -> torch.Tensor:
+                    ksize: Sequence[int], halo: Optional[bool] = None) -> torch.Tensor:
     """fp32 weight gradient (Cout, Cin, *ksize) of a stride-1 'same' convolution (1x1: ksize of ones) from bf16
     token-major dY [rows, Cout] and X [rows, Cin] (csrc/gemm_tcgen05.cu, MN-major tcgen05 operands)."""
     _need_cuda(dy_tok, x_tok)
@@ -539,9 +539,10 @@ def conv_wgrad_bf16(dy_tok: torch.Tensor, x_tok: torch.Tensor, batch: int, spati
     D, H, W = sp
     taps = ks[0] * ks[1] * ks[2]
     dw = torch.zeros((cout, taps, cin), device=x_tok.device, dtype=torch.float32)
-    check(_lib.lib().nextou_conv3d_ndhwc_wgrad(ptr(dy_tok), ll(dy_tok.stride(0)), ptr(x_tok), ll(x_tok.stride(0)), batch, D, H,
-                                               W, cin, cout, ks[0], ks[1], ks[2], ptr(dw), cin, cstream()),
-          "nextou_conv3d_ndhwc_wgrad")
+    use_halo = (CONV_HALO if halo is None else halo) and ks[1] in (1, 3) and ks[2] in (1, 3) and taps > 1
+    fn = _lib.lib().nextou_conv3d_ndhwc_halo_wgrad if use_halo else _lib.lib().nextou_conv3d_ndhwc_wgrad
+    check(fn(ptr(dy_tok), ll(dy_tok.stride(0)), ptr(x_tok), ll(x_tok.stride(0)), batch, D, H, W, cin, cout, ks[0], ks[1],
+             ks[2], ptr(dw), cin, cstream()), "nextou_conv3d_ndhwc_wgrad")
     return dw.permute(0, 2, 1).reshape(cout, cin, *ksize)
 
 

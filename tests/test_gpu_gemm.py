@@ -81,7 +81,8 @@ def test_conv_ndhwc_implicit_gemm(B, spatial, cin, cout, ks, halo):
     (1, (6, 10, 20), 132, 66, (3, 3, 3)), (1, (16, 28, 24), 264, 132, (3, 3, 3)), (1, (5, 9, 11), 8, 264, (3, 3, 3)),
     (2, (12, 20), 32, 48, (3, 3)), (1, (32, 56, 48), 132, 132, (1, 1, 1)), (1, (2, 7, 12), 648, 324, (1, 1, 1)),
     (1, (8, 64, 96), 1, 33, (1, 3, 3))])
-def test_conv_wgrad_mn_major(B, spatial, cin, cout, ks):
+@pytest.mark.parametrize("halo", [False, True], ids=["pertap", "halo"])
+def test_conv_wgrad_mn_major(B, spatial, cin, cout, ks, halo):
     """Weight gradient through the MN-major tcgen05 path vs autograd of F.conv on the same bf16-valued operands."""
     from nextou_b200 import ops
     g = torch.Generator().manual_seed(cin * 3 + cout)
@@ -96,6 +97,6 @@ def test_conv_wgrad_mn_major(B, spatial, cin, cout, ks):
     xt[:, :cin] = x.permute(0, *range(2, 2 + dim), 1).reshape(-1, cin)
     dt = torch.full((V, ops.pad8(cout)), float("nan"), dtype=torch.bfloat16)
     dt[:, :cout] = dy.permute(0, *range(2, 2 + dim), 1).reshape(-1, cout)
-    dw = ops.conv_wgrad_bf16(dt.to(DEV)[:, :cout], xt.to(DEV)[:, :cin], B, spatial, cin, cout, ks)
+    dw = ops.conv_wgrad_bf16(dt.to(DEV)[:, :cout], xt.to(DEV)[:, :cin], B, spatial, cin, cout, ks, halo=halo)
     assert dw.shape == w.shape and dw.dtype == torch.float32
     assert _rel(dw.cpu(), w.grad) < 1e-5, _rel(dw.cpu(), w.grad)
