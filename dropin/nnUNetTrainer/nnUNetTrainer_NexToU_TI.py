@@ -1,0 +1,2 @@
+"""Drop-in for nnunetv2/training/nnUNetTrainer/nnUNetTrainer_NexToU_TI.py."""
+from nextou_b200.trainers import nnUNetTrainer_NexToU_TI  # noqa: F401

@@ -482,8 +482,9 @@ def gemm_bf16_tn(a: torch.Tensor, b: torch.Tensor, bias: Optional[torch.Tensor] 
     if out is None:
         out = torch.empty((M, pad8(N)), device=a.device, dtype=out_dtype)
     bias32 = None if bias is None else bias.detach().float().contiguous()
-    check(_lib.lib().nextou_gemm_bf16_tn(ptr(a), ll(a.stride(0)), ptr(b), ll(b.stride(0)), ptr(out), ll(out.stride(0)), M, N,
-                                         K, ptr(bias32), dtype_code(out), cstream()), "nextou_gemm_bf16_tn")
+    with _lib.timed("gemm_tcgen05", 2 * M * (K + N) + 2 * N * K, 2 * M * N * K):
+        check(_lib.lib().nextou_gemm_bf16_tn(ptr(a), ll(a.stride(0)), ptr(b), ll(b.stride(0)), ptr(out), ll(out.stride(0)), M,
+                                             N, K, ptr(bias32), dtype_code(out), cstream()), "nextou_gemm_bf16_tn")
     return out
 
 
@@ -521,8 +522,13 @@ def conv_ndhwc_bf16(x_tok: torch.Tensor, batch: int, spatial: Sequence[int], cin
     bias32 = None if bias is None else bias.detach().float().contiguous()
     use_halo = (CONV_HALO if halo is None else halo) and ks[1] in (1, 3) and ks[2] in (1, 3)
     fn = _lib.lib().nextou_conv3d_ndhwc_halo_fwd if use_halo else _lib.lib().nextou_conv3d_ndhwc_fwd
-    check(fn(ptr(x_tok), ll(x_tok.stride(0)), batch, D, H, W, cin, ptr(wpack), cout, ks[0], ks[1], ks[2], ptr(bias32),
-             ptr(out), ll(out.stride(0)), dtype_code(out), cstream()), "nextou_conv3d_ndhwc_fwd")
+    V = batch * D * H * W
+    # algorithmic work / traffic: 2*V*Cin*Cout*taps flops; input + output + weights once, bf16
+    flops = 2 * V * cin * cout * ks[0] * ks[1] * ks[2]
+    nbytes = 2 * V * (cin + cout) + 2 * cin * cout * ks[0] * ks[1] * ks[2]
+    with _lib.timed("conv_halo_tcgen05" if use_halo else "conv_pertap_tcgen05", nbytes, flops):
+        check(fn(ptr(x_tok), ll(x_tok.stride(0)), batch, D, H, W, cin, ptr(wpack), cout, ks[0], ks[1], ks[2], ptr(bias32),
+                 ptr(out), ll(out.stride(0)), dtype_code(out), cstream()), "nextou_conv3d_ndhwc_fwd")
     return out
 
 
@@ -541,8 +547,11 @@ def conv_wgrad_bf16(dy_tok: torch.Tensor, x_tok: torch.Tensor, batch: int, spati
     dw = torch.zeros((cout, taps, cin), device=x_tok.device, dtype=torch.float32)
     use_halo = (CONV_HALO if halo is None else halo) and ks[1] in (1, 3) and ks[2] in (1, 3) and taps > 1
     fn = _lib.lib().nextou_conv3d_ndhwc_halo_wgrad if use_halo else _lib.lib().nextou_conv3d_ndhwc_wgrad
-    check(fn(ptr(dy_tok), ll(dy_tok.stride(0)), ptr(x_tok), ll(x_tok.stride(0)), batch, D, H, W, cin, cout, ks[0], ks[1],
-             ks[2], ptr(dw), cin, cstream()), "nextou_conv3d_ndhwc_wgrad")
+    V = batch * D * H * W
+    with _lib.timed("wgrad_halo_tcgen05" if use_halo else "wgrad_tcgen05", 2 * V * (cin + cout) + 4 * cin * cout * taps,
+                    2 * V * cin * cout * taps):
+        check(fn(ptr(dy_tok), ll(dy_tok.stride(0)), ptr(x_tok), ll(x_tok.stride(0)), batch, D, H, W, cin, cout, ks[0], ks[1],
+                 ks[2], ptr(dw), cin, cstream()), "nextou_conv3d_ndhwc_wgrad")
     return dw.permute(0, 2, 1).reshape(cout, cin, *ksize)
 
 
