@@ -138,6 +138,25 @@ int nextou_bti_ce_bwd(const void* logits, int dtype, long long stride_b, long lo
                       const double* grad_out, void* dlogits, long long dstride_b, long long dstride_c,
                       long long dstride_v, void* stream);
 
+/* ---- fused per-scale training loss:  w_ce * CE + w_dice * SoftDice + w_ti * (B)TI -------------------------------
+ * Replaces the three softmax evaluations and ~20 element-wise passes of DC_and_CE_and_BTI_Loss.forward
+ * (loss/compound_bti_loss.py:33-61; Dice and CE are upstream nnU-Net's MemoryEfficientSoftDiceLoss /
+ * RobustCrossEntropyLoss) with two passes over the logits.  NC in {2..8, 14, 16, 19}.
+ * nextou_dsloss_plan: number of CTAs per batch item (= rows of `partial`).
+ * nextou_dsloss_stats: labels[B][V] = argmax (first maximum), ce[B][V] = -log softmax[target] (fp64 storage, fp32 math),
+ *   sums[B][3*NC+1] = sum_v p_c | sum_v p_c*y_c | sum_v y_c | sum_v ce, reduced in fixed order from
+ *   partial[B][nblk][3*NC+1].
+ * nextou_dsloss_bwd: dlogit_c = p_c (g_c - sum_k p_k g_k) + (scal[0] + scal[1]*crit) (p_c - y_c) with
+ *   g_c = coef_a[b][c]*y_c + coef_b[b][c] (the Dice derivative); crit may be NULL. */
+int nextou_dsloss_plan(long long V, int B, int* nblk_out);
+int nextou_dsloss_stats(const void* logits, int dtype, long long stride_b, long long stride_c, long long stride_v, int B,
+                        int NC, long long V, const void* target, int target_code, uint8_t* labels, double* ce,
+                        double* partial, double* sums, void* stream);
+int nextou_dsloss_bwd(const void* logits, int dtype, long long stride_b, long long stride_c, long long stride_v, int B,
+                      int NC, long long V, const void* target, int target_code, const uint8_t* crit, const float* coef_a,
+                      const float* coef_b, const float* scal, void* dlogits, long long dstride_b, long long dstride_c,
+                      long long dstride_v, void* stream);
+
 /* Same contract, restricted to kh, kw in {1, 3} (all non-down-sampling NexToU convolutions): halo-reuse variant
  * (csrc/conv_tcgen05.cu) — one haloed activation box per depth tap feeds all in-plane taps through row-shifted
  * UMMA descriptors, cutting the L2 -> SM activation traffic 6.4x. */

@@ -540,7 +540,7 @@ extern "C" int nextou_conv3d_ndhwc_halo_wgrad(const void* dy, long long ldy, con
   p.tmem_cols = pow2_cols(inplane * p.n_tile);
   const long long tiles = (long long)kd * p.n_mtiles * p.n_ntiles;
   long long ksplit = (3LL * num_sms() + tiles - 1) / tiles;
-  if (ksplit > p.total_bricks) ksplit = p.total_bricks;
+  if (ksplit > p.total_bricks / 16) ksplit = p.total_bricks / 16;   // >= 16 K blocks per CTA amortise prologue + atomics
   if (ksplit < 1) ksplit = 1;
   p.ksplit = (int)ksplit;
   CUtensorMap tmDY, tmX;

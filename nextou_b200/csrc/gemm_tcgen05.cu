@@ -208,6 +208,155 @@ static int launch_gemm(const CUtensorMap& tmA, const CUtensorMap& tmB, GemmParam
 
 using namespace nextou;
 
+// ======================================================================================================
+// Persistent plain GEMM for the 1x1 layers: C[M][ldc] = A[M][K] * B[N][K]^T (+ bias).
+// The 1x1 convolutions of NexToU have tiny K (132..1296) and N (14..1296): one 128-row tile is only 3..21 K blocks of MMA
+// work, so a one-tile-per-CTA kernel is dominated by launch / TMEM-allocation / barrier-init / pipeline-fill overhead
+// (measured 8.7x off the HBM roofline).  Here a CTA keeps its [block_n x K] weight slice RESIDENT in shared memory
+// (loaded once), walks the row tiles m = blockIdx.x, blockIdx.x + gridDim.x, ..., streams only the activation tiles
+// through a TMA ring and double-buffers the accumulator in tensor memory so the epilogue of tile i overlaps tile i+1.
+// 192 threads: warp 0 TMA producer, warp 1 MMA issuer (warp-uniform, elected lane), warps 2-5 epilogue.
+// ======================================================================================================
+namespace nextou {
+
+constexpr int PG_MAX_STAGES = 8;
+
+struct PGemmParams {
+  int M, N, K;
+  int kblocks, last_ksteps;
+  int block_n, tmem_cols, a_stages;
+  int b_resident;          // weights of this Cout tile stay in smem; else they share the ring stage with A
+  long long m_tiles;
+  void* C;
+  long long ldc;
+  int out_dtype;
+  const float* bias;
+};
+
+__device__ __forceinline__ void mbar_arrive_cta(uint64_t* bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+
+__global__ void __launch_bounds__(GEMM_THREADS, 1)
+    gemm_pers_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
+                             const PGemmParams p) {
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  const int a_bytes = GEMM_BM * GEMM_BK * 2;
+  const int b_bytes = p.block_n * GEMM_BK * 2;
+  const int stage_bytes = p.b_resident ? a_bytes : a_bytes + b_bytes;
+  uint8_t* ring = smem;
+  uint8_t* smBres = smem + (size_t)p.a_stages * stage_bytes;                       // [kblocks][block_n x 64] when resident
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smBres + (p.b_resident ? (size_t)p.kblocks * b_bytes : 0));
+  uint64_t* empty_bar = full_bar + p.a_stages;
+  uint64_t* bres_bar = empty_bar + p.a_stages;
+  uint64_t* tmem_full = bres_bar + 1;     // [2]
+  uint64_t* tmem_empty = tmem_full + 2;   // [2]
+  uint32_t* tmem_holder = reinterpret_cast<uint32_t*>(tmem_empty + 2);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int n0 = blockIdx.y * p.block_n;
+
+  if (warp == 0 && lane == 0) {
+    prefetch_tmap(&tmA);
+    prefetch_tmap(&tmB);
+    for (int s = 0; s < p.a_stages; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1); }
+    mbar_init(bres_bar, 1);
+    for (int a = 0; a < 2; ++a) { mbar_init(&tmem_full[a], 1); mbar_init(&tmem_empty[a], 4); }
+    fence_barrier_init();
+  }
+  if (warp == 2) tmem_alloc(tmem_holder, (uint32_t)p.tmem_cols);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_holder;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      if (p.b_resident) {
+        mbar_expect_tx(bres_bar, (uint32_t)(p.kblocks * b_bytes));
+        for (int kb = 0; kb < p.kblocks; ++kb) tma_load_2d(smBres + (size_t)kb * b_bytes, &tmB, bres_bar, kb * GEMM_BK, n0);
+      }
+      int st = 0;
+      uint32_t ph = 0;
+      for (long long mt = blockIdx.x; mt < p.m_tiles; mt += gridDim.x) {
+        const int m0 = (int)(mt * GEMM_BM);
+        for (int kb = 0; kb < p.kblocks; ++kb) {
+          mbar_wait(&empty_bar[st], ph ^ 1);
+          mbar_expect_tx(&full_bar[st], (uint32_t)stage_bytes);
+          tma_load_2d(ring + (size_t)st * stage_bytes, &tmA, &full_bar[st], kb * GEMM_BK, m0);
+          if (!p.b_resident) tma_load_2d(ring + (size_t)st * stage_bytes + a_bytes, &tmB, &full_bar[st], kb * GEMM_BK, n0);
+          if (++st == p.a_stages) { st = 0; ph ^= 1; }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    const uint32_t idesc = make_idesc_bf16(GEMM_BM, p.block_n);
+    if (p.b_resident) mbar_wait(bres_bar, 0);
+    int st = 0, it = 0;
+    uint32_t ph = 0;
+    for (long long mt = blockIdx.x; mt < p.m_tiles; mt += gridDim.x, ++it) {
+      const int acc = it & 1;
+      mbar_wait(&tmem_empty[acc], ((it >> 1) & 1) ^ 1);
+      tc_fence_after();
+      const uint32_t tacc = tmem_base + (uint32_t)(acc * p.block_n);
+      for (int kb = 0; kb < p.kblocks; ++kb) {
+        mbar_wait(&full_bar[st], ph);
+        tc_fence_after();
+        const uint32_t sa = smem_u32(ring + (size_t)st * stage_bytes);
+        const uint64_t adesc = make_kmajor_sw128_desc(sa);
+        const uint64_t bdesc = make_kmajor_sw128_desc(p.b_resident ? smem_u32(smBres + (size_t)kb * b_bytes) : sa + a_bytes);
+        const int ksteps = (kb == p.kblocks - 1) ? p.last_ksteps : 4;
+        if (elect_one()) {
+          for (int k = 0; k < ksteps; ++k)
+            umma_f16(tacc, adesc + (uint64_t)(2 * k), bdesc + (uint64_t)(2 * k), idesc, (kb | k) != 0 ? 1u : 0u);
+          umma_commit(&empty_bar[st]);
+        }
+        __syncwarp();
+        if (++st == p.a_stages) { st = 0; ph ^= 1; }
+      }
+      if (elect_one()) umma_commit(&tmem_full[acc]);
+      __syncwarp();
+    }
+  } else {
+    const int q = warp & 3;
+    int it = 0;
+    for (long long mt = blockIdx.x; mt < p.m_tiles; mt += gridDim.x, ++it) {
+      const long long row = mt * GEMM_BM + q * 32 + lane;
+      const int acc = it & 1;
+      mbar_wait(&tmem_full[acc], (it >> 1) & 1);
+      tc_fence_after();
+      for (int c = 0; c < p.block_n; c += 16) {
+        uint32_t raw[16];
+        tmem_ld16(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * p.block_n + c), raw);
+        tmem_ld_wait();
+        if (row < p.M && n0 + c < p.ldc) {
+          float v[16];
+#pragma unroll
+          for (int j = 0; j < 16; ++j) {
+            const int col = n0 + c + j;
+            float x = __uint_as_float(raw[j]);
+            if (p.bias != nullptr && col < p.N) x += p.bias[col];
+            v[j] = col < p.N ? x : 0.f;
+          }
+          if (p.out_dtype == NEXTOU_BF16)
+            store_chunk16(reinterpret_cast<__nv_bfloat16*>(p.C) + row * p.ldc, n0 + c, v, p.ldc);
+          else
+            store_chunk16(reinterpret_cast<float*>(p.C) + row * p.ldc, n0 + c, v, p.ldc);
+        }
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive_cta(&tmem_empty[acc]);
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 2) tmem_dealloc(tmem_base, (uint32_t)p.tmem_cols);
+}
+
+}  // namespace nextou
+
 // C[M][ldc] = A[M][K] * B[N][K]^T (+ bias): A, B bf16 with K contiguous (row pitches lda / ldb elements, multiples of 8,
 // 16-byte aligned bases); C bf16 or fp32 with ldc % 8 == 0; columns [N, ldc) of C are zero-filled.
 extern "C" int nextou_gemm_bf16_tn(const void* A, long long lda, const void* B, long long ldb, void* C, long long ldc,
@@ -218,10 +367,25 @@ extern "C" int nextou_gemm_bf16_tn(const void* A, long long lda, const void* B, 
                  "gemm_bf16_tn: row pitches must be multiples of 8 elements and cover K / N (lda=%lld ldb=%lld ldc=%lld)", lda, ldb, ldc);
   NEXTOU_REQUIRE(((uintptr_t)A & 15) == 0 && ((uintptr_t)B & 15) == 0 && ((uintptr_t)C & 15) == 0, "gemm_bf16_tn: 16-byte alignment");
   NEXTOU_REQUIRE(out_dtype == NEXTOU_BF16 || out_dtype == NEXTOU_F32, "gemm_bf16_tn: bad out dtype");
-  GemmParams p = {};
-  p.M = M; p.N = N; p.kblocks = (K + GEMM_BK - 1) / GEMM_BK; p.taps = 1;
-  p.C = C; p.ldc = ldc; p.out_dtype = out_dtype; p.bias = bias; p.is_conv = 0;
-  const int bn = pick_block_n(N);
+  PGemmParams p = {};
+  p.M = M; p.N = N; p.K = K;
+  p.kblocks = (K + GEMM_BK - 1) / GEMM_BK;
+  p.last_ksteps = (K - (p.kblocks - 1) * GEMM_BK + 15) / 16;
+  p.block_n = pick_block_n(N);
+  p.tmem_cols = pow2_cols(2 * p.block_n);
+  p.m_tiles = (M + GEMM_BM - 1) / GEMM_BM;
+  p.C = C; p.ldc = ldc; p.out_dtype = out_dtype; p.bias = bias;
+  const int a_bytes = GEMM_BM * GEMM_BK * 2, b_bytes = p.block_n * GEMM_BK * 2;
+  const int budget = 200 * 1024;
+  const long long bres = (long long)p.kblocks * b_bytes;
+  p.b_resident = bres <= budget - 3 * a_bytes ? 1 : 0;
+  {
+    const int per_stage = p.b_resident ? a_bytes : a_bytes + b_bytes;
+    int st = (int)((budget - (p.b_resident ? bres : 0)) / per_stage);
+    if (st > PG_MAX_STAGES) st = PG_MAX_STAGES;
+    NEXTOU_REQUIRE(st >= 2, "gemm_bf16_tn: tile does not fit in shared memory (N tile %d, K %d)", p.block_n, K);
+    p.a_stages = st;
+  }
   CUtensorMap tmA, tmB;
   {
     cuuint64_t dims[2] = {(cuuint64_t)K, (cuuint64_t)M};
@@ -233,11 +397,25 @@ extern "C" int nextou_gemm_bf16_tn(const void* A, long long lda, const void* B, 
   {
     cuuint64_t dims[2] = {(cuuint64_t)K, (cuuint64_t)N};
     cuuint64_t str[1] = {(cuuint64_t)ldb * 2};
-    cuuint32_t box[2] = {GEMM_BK, (cuuint32_t)bn};
+    cuuint32_t box[2] = {GEMM_BK, (cuuint32_t)p.block_n};
     int rc = encode_bf16_map(&tmB, B, 2, dims, str, box, "B");
     if (rc) return rc;
   }
-  return launch_gemm(tmA, tmB, p, (M + GEMM_BM - 1) / GEMM_BM, (cudaStream_t)stream);
+  const size_t smem = 1024 + (size_t)p.a_stages * (p.b_resident ? a_bytes : a_bytes + b_bytes) + (p.b_resident ? (size_t)bres : 0) +
+                      (2 * p.a_stages + 5) * sizeof(uint64_t) + 16;
+  int rc = ensure_smem(gemm_pers_tcgen05_kernel, smem);
+  if (rc) return rc;
+  const int n_tiles = (N + p.block_n - 1) / p.block_n;
+  int per_sm = (int)((220 * 1024) / smem);
+  if (per_sm > 512 / p.tmem_cols) per_sm = 512 / p.tmem_cols;
+  if (per_sm < 1) per_sm = 1;
+  long long ctas = ((long long)num_sms() * per_sm + n_tiles - 1) / n_tiles;
+  if (ctas > p.m_tiles) ctas = p.m_tiles;
+  if (ctas < 1) ctas = 1;
+  NEXTOU_REQUIRE(n_tiles <= 65535, "gemm_bf16_tn: grid too large");
+  dim3 grid((unsigned)ctas, (unsigned)n_tiles);
+  gemm_pers_tcgen05_kernel<<<grid, GEMM_THREADS, smem, (cudaStream_t)stream>>>(tmA, tmB, p);
+  return check_launch("gemm_pers_tcgen05_kernel");
 }
 
 // Stride-1 'same' convolution as implicit GEMM.  x: bf16 NDHWC [B][D][H][W][ldx] (ldx % 8 == 0, channels >= Cin are
@@ -399,7 +577,8 @@ __global__ void __launch_bounds__(WG_THREADS, 1)
       }
     }
   } else if (warp == 1) {
-    if (lane == 0 && nb > 0) {
+    // warp-uniform control flow, one elected lane issues (descriptors stay in uniform registers)
+    if (nb > 0) {
       // D fp32, A/B bf16, both MN-major (bits 15, 16)
       const uint32_t idesc = make_idesc_bf16(128, p.n_tile) | (1u << 15) | (1u << 16);
       int stage = 0;
@@ -408,20 +587,24 @@ __global__ void __launch_bounds__(WG_THREADS, 1)
         mbar_wait(&full_bar[stage], phase);
         tc_fence_after();
         const uint32_t st = smem_u32(smem + (size_t)stage * stage_bytes);
-        for (int tp = 0; tp < ntaps; ++tp) {
-          const uint32_t xb = st + (uint32_t)(2 + tp * p.n_boxes) * WG_BOX_BYTES;
+        if (elect_one()) {
+          for (int tp = 0; tp < ntaps; ++tp) {
+            const uint32_t xb = st + (uint32_t)(2 + tp * p.n_boxes) * WG_BOX_BYTES;
 #pragma unroll
-          for (int k = 0; k < WG_BRICK / 16; ++k) {
-            // 16 voxels = 16 rows of 128 B = 2048 B along K
-            const uint64_t adesc = make_mnmajor_sw128_desc(st + k * 2048, WG_BOX_BYTES);
-            const uint64_t bdesc = make_mnmajor_sw128_desc(xb + k * 2048, WG_BOX_BYTES);
-            umma_f16(tmem_base + (uint32_t)(tp * p.n_tile), adesc, bdesc, idesc, (i | k) != 0 ? 1u : 0u);
+            for (int k = 0; k < WG_BRICK / 16; ++k) {
+              // 16 voxels = 16 rows of 128 B = 2048 B along K
+              const uint64_t adesc = make_mnmajor_sw128_desc(st + k * 2048, WG_BOX_BYTES);
+              const uint64_t bdesc = make_mnmajor_sw128_desc(xb + k * 2048, WG_BOX_BYTES);
+              umma_f16(tmem_base + (uint32_t)(tp * p.n_tile), adesc, bdesc, idesc, (i | k) != 0 ? 1u : 0u);
+            }
           }
+          umma_commit(&empty_bar[stage]);
         }
-        umma_commit(&empty_bar[stage]);
+        __syncwarp();
         if (++stage == p.stages) { stage = 0; phase ^= 1; }
       }
-      umma_commit(tmem_full_bar);
+      if (elect_one()) umma_commit(tmem_full_bar);
+      __syncwarp();
     }
   } else if (nb > 0) {
     mbar_wait(tmem_full_bar, 0);
@@ -486,12 +669,12 @@ extern "C" int nextou_conv3d_ndhwc_wgrad(const void* dy, long long ldy, const vo
   p.tap_group = tg;
   p.n_groups = (p.taps + tg - 1) / tg;
   p.tmem_cols = pow2_cols(tg * p.n_tile);
-  p.stages = 2;
   const long long tiles = (long long)p.n_groups * p.n_mtiles * p.n_ntiles;
   long long ksplit = (2LL * num_sms() + tiles - 1) / tiles;
   if (ksplit > p.total_bricks) ksplit = p.total_bricks;
   if (ksplit < 1) ksplit = 1;
   p.ksplit = (int)ksplit;
+  p.stages = 2;   // small stages keep several CTAs resident per SM (measured better than a deeper ring here)
   CUtensorMap tmDY, tmX;
   {
     cuuint64_t dims[5] = {(cuuint64_t)Cout, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)D, (cuuint64_t)B};

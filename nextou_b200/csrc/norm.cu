@@ -93,6 +93,7 @@ __global__ void norm_stats_kernel(const T* __restrict__ x, int C, int R, long lo
   const T* base = x + (long long)blockIdx.y * total;
   const long long S = (long long)C * R;
   float acc[NV][2] = {};
+#pragma unroll 2
   for (long long off = (long long)blockIdx.x * S + NV * threadIdx.x; off < total; off += (long long)gridDim.x * S) {
     float v[NV];
     load_guard(base, off, total, v);
@@ -178,6 +179,7 @@ __global__ void norm_apply_kernel(const T* __restrict__ x, int C, int R, long lo
     sc[e] = invstd[blockIdx.y * C + ch] * g;
     sh[e] = b - mean[blockIdx.y * C + ch] * sc[e];
   }
+#pragma unroll 2
   for (long long off = (long long)blockIdx.x * S + NV * threadIdx.x; off < total; off += (long long)gridDim.x * S) {
     float v[NV];
     load_guard(base, off, total, v);
@@ -211,6 +213,7 @@ __global__ void norm_bwd_reduce_kernel(const T* __restrict__ x, const T* __restr
     b[e] = beta ? beta[ch] : 0.f;
   }
   float acc[NV][2] = {};
+#pragma unroll 2
   for (long long off = (long long)blockIdx.x * S + NV * threadIdx.x; off < total; off += (long long)gridDim.x * S) {
     float v[NV], d[NV];
     load_guard(xb, off, total, v);
@@ -261,6 +264,7 @@ __global__ void norm_bwd_apply_kernel(const T* __restrict__ x, const T* __restri
     m1[e] = sums[(long long)blockIdx.y * 2 * C + ch] * inv_n;
     m2[e] = sums[(long long)blockIdx.y * 2 * C + C + ch] * inv_n;
   }
+#pragma unroll 2
   for (long long off = (long long)blockIdx.x * S + NV * threadIdx.x; off < total; off += (long long)gridDim.x * S) {
     float v[NV], d[NV];
     load_guard(xb, off, total, v);
@@ -288,6 +292,7 @@ __global__ void affine_act_kernel(const T* __restrict__ x, int C, int R, long lo
     sc[e] = scale[ch];
     sh[e] = shift[ch];
   }
+#pragma unroll 2
   for (long long off = (long long)blockIdx.x * S + NV * threadIdx.x; off < total; off += (long long)gridDim.x * S) {
     float v[NV];
     load_guard(x, off, total, v);
@@ -326,7 +331,7 @@ static int plan_sweep(int C, long long rows, int instances, SweepPlan& p) {
   p.R = R;
   p.threads = C * R / NV;
   const long long sweeps = (rows + R - 1) / R;
-  long long nblk = (2LL * num_sms() + instances - 1) / instances;
+  long long nblk = (8LL * num_sms() + instances - 1) / instances;   // 4 resident CTAs / SM x 2 waves
   if (nblk > sweeps) nblk = sweeps;
   if (nblk < 1) nblk = 1;
   p.nblk = (int)nblk;

@@ -118,23 +118,48 @@ __device__ __forceinline__ uint32_t make_idesc_bf16(int m, int n) {
 
 
 // ---- epilogue store: 16 consecutive columns of one output row ---------------------------------------
+__device__ __forceinline__ void st_global_256(void* p, const uint32_t (&w)[8]) {
+  asm volatile("st.global.v8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};" ::"l"(p), "r"(w[0]), "r"(w[1]), "r"(w[2]), "r"(w[3]),
+               "r"(w[4]), "r"(w[5]), "r"(w[6]), "r"(w[7])
+               : "memory");
+}
+__device__ __forceinline__ uint32_t pack_bf16x2(float a, float b) {
+  __nv_bfloat162 t = __floats2bfloat162_rn(a, b);
+  return *reinterpret_cast<uint32_t*>(&t);
+}
+
 template <typename OutT>
 __device__ __forceinline__ void store_chunk16(OutT* row_ptr, int col0, const float (&v)[16], long long ldc) {
-  // col0 is a multiple of 16 and the row pitch a multiple of 8 elements -> 16-byte aligned halves
+  // col0 is a multiple of 16 and the row pitch a multiple of 8 elements.  Full chunks whose address is 32-byte aligned
+  // go out as 256-bit stores (one full sector per lane instead of two half-sector stores); else 16-byte halves.
+  OutT* dst = row_ptr + col0;
+  if (col0 + 16 <= ldc && (reinterpret_cast<uintptr_t>(dst) & 31) == 0) {
+    if constexpr (sizeof(OutT) == 2) {
+      uint32_t w[8];
+#pragma unroll
+      for (int j = 0; j < 8; ++j) w[j] = pack_bf16x2(v[2 * j], v[2 * j + 1]);
+      st_global_256(dst, w);
+    } else {
+      uint32_t w[8];
+#pragma unroll
+      for (int j = 0; j < 8; ++j) w[j] = __float_as_uint(v[j]);
+      st_global_256(dst, w);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) w[j] = __float_as_uint(v[8 + j]);
+      st_global_256(dst + 8, w);
+    }
+    return;
+  }
 #pragma unroll
   for (int h = 0; h < 2; ++h) {
     const int c = col0 + h * 8;
     if (c + 8 <= ldc) {
       if constexpr (sizeof(OutT) == 2) {
         uint4 u;
-        __nv_bfloat162 p0 = __floats2bfloat162_rn(v[h * 8 + 0], v[h * 8 + 1]);
-        __nv_bfloat162 p1 = __floats2bfloat162_rn(v[h * 8 + 2], v[h * 8 + 3]);
-        __nv_bfloat162 p2 = __floats2bfloat162_rn(v[h * 8 + 4], v[h * 8 + 5]);
-        __nv_bfloat162 p3 = __floats2bfloat162_rn(v[h * 8 + 6], v[h * 8 + 7]);
-        u.x = *reinterpret_cast<unsigned*>(&p0);
-        u.y = *reinterpret_cast<unsigned*>(&p1);
-        u.z = *reinterpret_cast<unsigned*>(&p2);
-        u.w = *reinterpret_cast<unsigned*>(&p3);
+        u.x = pack_bf16x2(v[h * 8 + 0], v[h * 8 + 1]);
+        u.y = pack_bf16x2(v[h * 8 + 2], v[h * 8 + 3]);
+        u.z = pack_bf16x2(v[h * 8 + 4], v[h * 8 + 5]);
+        u.w = pack_bf16x2(v[h * 8 + 6], v[h * 8 + 7]);
         *reinterpret_cast<uint4*>(row_ptr + c) = u;
       } else {
         *reinterpret_cast<float4*>(row_ptr + c) = make_float4(v[h * 8 + 0], v[h * 8 + 1], v[h * 8 + 2], v[h * 8 + 3]);

@@ -195,9 +195,26 @@ class _CompoundInteractionLoss(nn.Module):
         self.ce = RobustCrossEntropyLoss(**ce_kwargs)
         self.dc = dice_class(apply_nonlin=softmax_helper_dim1, **soft_dice_kwargs)
         self.ti = self._ti_class(**ti_kwargs)
+        self.fused = True   # False: compose the three terms from separate ops like the reference does
+
+    def _fusable(self, net_output, target) -> bool:
+        """The one-kernel path covers the configuration every reference trainer builds (…_BTI_Synapse.py:50-58):
+        hard labels, no ignore label, default CE arguments, softmax Dice without tp clipping."""
+        ce, dc = self.ce, self.dc
+        return (self.fused and net_output.is_cuda and self.ignore_label is None and target.shape[1] == 1
+                and target.ndim == net_output.ndim and net_output.shape[1] in ops.SEG_LOSS_CLASSES
+                and ce.weight is None and ce.reduction == "mean" and ce.label_smoothing == 0.0 and ce.ignore_index == -100
+                and type(dc).__name__ in ("SoftDiceLoss", "MemoryEfficientSoftDiceLoss")
+                and getattr(dc, "clip_tp", None) is None and dc.apply_nonlin is softmax_helper_dim1
+                and (self.weight_ti == 0 or bool(self.ti.interaction_list)))
 
     def forward(self, net_output: torch.Tensor, target: torch.Tensor):
         """target must be (b, 1, *spatial)."""
+        if self._fusable(net_output, target):
+            ti = self.ti
+            return ops.seg_loss(net_output, target, self.weight_ce, self.weight_dice, self.weight_ti, self.dc.batch_dice,
+                                self.dc.do_bg, self.dc.smooth, getattr(self.dc, "ddp", False),
+                                ti.interaction_table() if self.weight_ti != 0 else None, ti.connectivity, ti.min_thick)
         if self.ignore_label is not None:
             assert target.shape[1] == 1, 'ignore label is not implemented for one hot encoded target variables ' \
                                          '(DC_and_CE_loss)'

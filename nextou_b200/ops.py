@@ -468,6 +468,85 @@ def bti_loss(logits, target, mask_a, mask_c, inclusion, connectivity: int, min_t
     return _BTILoss.apply(logits, target, (list(mask_a), list(mask_c), list(inclusion)), connectivity, min_thick)
 
 
+SEG_LOSS_CLASSES = (2, 3, 4, 5, 6, 7, 8, 14, 16, 19)   # instantiated class counts of csrc/dsloss.cu
+
+
+class _SegLoss(torch.autograd.Function):
+    """w_ce * CE + w_dice * SoftDice + w_ti * (B)TI of one deep-supervision scale from two passes over the logits
+    (csrc/dsloss.cu).  cfg = (w_ce, w_dice, w_ti, batch_dice, do_bg, smooth, ddp, table | None, connectivity, min_thick)."""
+
+    @staticmethod
+    def forward(ctx, logits, target, cfg):
+        _need_cuda(logits, target)
+        w_ce, w_dice, w_ti, batch_dice, do_bg, smooth, ddp, table, connectivity, min_thick = cfg
+        x, (sb, sc, sv) = _prep_logits(logits)
+        y = _prep_target(target)
+        B, NC = x.shape[:2]
+        V = x[0, 0].numel()
+        L = _lib.lib()
+        dev = x.device
+        nblk = ctypes.c_int(0)
+        check(L.nextou_dsloss_plan(ll(V), B, ctypes.byref(nblk)), "nextou_dsloss_plan")
+        width = 3 * NC + 1
+        labels = torch.empty((B, *x.shape[2:]), device=dev, dtype=torch.uint8)
+        ce = torch.empty((B, V), device=dev, dtype=torch.float64)
+        partial = torch.empty((B, nblk.value, width), device=dev, dtype=torch.float64)
+        sums = torch.empty((B, width), device=dev, dtype=torch.float64)
+        check(L.nextou_dsloss_stats(ptr(x), dtype_code(x), ll(sb), ll(sc), ll(sv), B, NC, ll(V), ptr(y), _TGT_CODE[y.dtype],
+                                    ptr(labels), ptr(ce), ptr(partial), ptr(sums), cstream()), "nextou_dsloss_stats")
+        crit = None
+        ti = None
+        if w_ti != 0:
+            crit = bti_critical_map(labels, *table, connectivity, min_thick)
+            L.nextou_bti_masked_sum_workspace_bytes.restype = ctypes.c_size_t
+            ws = torch.empty(L.nextou_bti_masked_sum_workspace_bytes(B) // 8, device=dev, dtype=torch.float64)
+            ti = torch.empty((), device=dev, dtype=torch.float64)
+            check(L.nextou_bti_masked_sum(ptr(ce), ptr(crit), B, ll(V), ptr(ws), ptr(ti), cstream()), "nextou_bti_masked_sum")
+        # per-class algebra on [B, NC] doubles (MemoryEfficientSoftDiceLoss.forward; CrossEntropyLoss mean reduction)
+        P, I, G = sums[:, :NC], sums[:, NC:2 * NC], sums[:, 2 * NC:3 * NC]
+        if batch_dice:
+            if ddp and torch.distributed.is_available() and torch.distributed.is_initialized():
+                pig = sums[:, :3 * NC].sum(0, keepdim=True)
+                torch.distributed.all_reduce(pig)  # AllGatherGrad + sum: gradients stay with the local voxels
+                P, I, G = pig[:, :NC], pig[:, NC:2 * NC], pig[:, 2 * NC:]
+            else:
+                P, I, G = P.sum(0, keepdim=True), I.sum(0, keepdim=True), G.sum(0, keepdim=True)
+        first = 0 if do_bg else 1
+        raw = G + P + smooth
+        den = torch.clip(raw, 1e-8)
+        num = 2 * I + smooth
+        n_terms = den[:, first:].numel()
+        total = sums[:, 3 * NC].sum() * (w_ce / (B * V)) - (num / den)[:, first:].sum() * (w_dice / n_terms)
+        if ti is not None:
+            total = total + w_ti * ti
+        dI = -2.0 * w_dice / n_terms / den
+        dP = torch.where(raw >= 1e-8, w_dice / n_terms * num / (den * den), torch.zeros_like(den))
+        coef = torch.stack([dI, dP]).expand(2, B, NC).clone()
+        coef[:, :, :first] = 0
+        ctx.save_for_backward(x, y, crit if crit is not None else labels, coef)
+        ctx.meta = (sb, sc, sv, B, NC, V, logits.dtype, crit is not None, w_ce, w_ti)
+        return total
+
+    @staticmethod
+    def backward(ctx, gout):
+        x, y, crit, coef = ctx.saved_tensors
+        sb, sc, sv, B, NC, V, in_dtype, has_crit, w_ce, w_ti = ctx.meta
+        g = gout.to(torch.float64)
+        coef32 = (coef * g).float().contiguous()
+        scal = (torch.stack([g * (w_ce / (B * V)), g * (w_ti / B)])).float().contiguous()
+        dx = torch.empty_strided(x.shape, x.stride(), device=x.device, dtype=x.dtype)
+        check(_lib.lib().nextou_dsloss_bwd(ptr(x), dtype_code(x), ll(sb), ll(sc), ll(sv), B, NC, ll(V), ptr(y),
+                                           _TGT_CODE[y.dtype], ptr(crit if has_crit else None), ptr(coef32[0]), ptr(coef32[1]),
+                                           ptr(scal), ptr(dx), ll(sb), ll(sc), ll(sv), cstream()), "nextou_dsloss_bwd")
+        return dx.to(in_dtype), None, None
+
+
+def seg_loss(logits, target, w_ce, w_dice, w_ti, batch_dice, do_bg, smooth, ddp, table, connectivity, min_thick):
+    """Fused CE + soft Dice + (B)TI for one output scale -> fp64 scalar (compound_bti_loss.py:33-61)."""
+    return _SegLoss.apply(logits, target, (float(w_ce), float(w_dice), float(w_ti), bool(batch_dice), bool(do_bg), float(smooth),
+                                           bool(ddp), table, connectivity, min_thick))
+
+
 # ----------------------------------------------------------------------------------------------
 # tcgen05 GEMM engine (csrc/gemm_tcgen05.cu)
 # ----------------------------------------------------------------------------------------------

@@ -356,3 +356,90 @@ def test_bti_full_size_properties():
     assert torch.equal(swapped, crit)
     const = ops.bti_critical_map(torch.full_like(labels, 3), ma, mc, flags, 26, 1)
     assert int(const.sum()) == 0
+
+
+# ------------------------------------------------------------------------------------------------
+# fused CE + soft Dice + BTI (csrc/dsloss.cu) vs the oracle's three-term composition
+# ------------------------------------------------------------------------------------------------
+def _oracle_compound(logits, target, exc, dim, conn, w_ti, batch_dice, do_bg, smooth=1e-5):
+    import torch.nn.functional as F
+    lg = logits.double().requires_grad_(True)
+    p = torch.softmax(lg, 1)
+    axes = tuple(range(2, p.ndim))
+    onehot = torch.zeros_like(p).scatter_(1, target.long(), 1)
+    first = 0 if do_bg else 1
+    inter, pred, gt = (p * onehot).sum(axes)[:, first:], p.sum(axes)[:, first:], onehot.sum(axes)[:, first:]
+    if batch_dice:
+        inter, pred, gt = inter.sum(0), pred.sum(0), gt.sum(0)
+    dc = -((2 * inter + smooth) / torch.clip(gt + pred + smooth, 1e-8)).mean()
+    ce = F.cross_entropy(lg, target[:, 0].long())
+    ti = TO.bti_loss(lg, target, [], exc, dim, conn, 1) if w_ti else 0.0
+    total = ce + dc + w_ti * ti
+    total.backward()
+    return total.item(), lg.grad
+
+
+@pytest.mark.parametrize("shape,nc,kind,batch_dice,do_bg,w_ti,dtype", [
+    ((2, 10, 20, 24), 14, "synapse", True, False, 1e-6, torch.float32),
+    ((2, 10, 20, 24), 14, "synapse", False, True, 1e-2, torch.float32),
+    ((3, 33, 47), 5, "pairs", True, False, 1e-4, torch.float32),
+    ((1, 9, 31, 30), 3, "pairs", False, False, 0.0, torch.float32),
+    ((2, 12, 24, 20), 14, "synapse", True, False, 1e-2, torch.bfloat16),
+])
+@pytest.mark.parametrize("layout", ["ncdhw", "channels_last"])
+def test_fused_seg_loss_matches_oracle_and_unfused(shape, nc, kind, batch_dice, do_bg, w_ti, dtype, layout):
+    from nextou_b200 import ops
+    from nextou_b200.losses import DC_and_CE_and_BTI_Loss
+    logits, target = bti_case(shape, nc, 5)
+    logits = logits.to(dtype)
+    _, exc = bti_interactions(kind, nc)
+    dim = len(shape) - 1
+    conn = 26 if dim == 3 else 8
+    mod = DC_and_CE_and_BTI_Loss({"batch_dice": batch_dice, "smooth": 1e-5, "do_bg": do_bg, "ddp": False}, {},
+                                 {"dim": dim, "connectivity": conn, "inclusion": [], "exclusion": exc, "min_thick": 1},
+                                 weight_ce=1, weight_dice=1, weight_ti=w_ti)
+    lg = logits.to(DEV)
+    if layout == "channels_last":
+        lg = ops.channels_last(lg)
+    lg.requires_grad_(True)
+    assert mod._fusable(lg, target.to(DEV))
+    n0 = ops._lib.lib().nextou_launch_count()
+    val = mod(lg, target.to(DEV))
+    (val * 2.0).backward()
+    assert ops._lib.lib().nextou_launch_count() - n0 in (3, 6)       # stats + reduce + bwd (+ critical map + 2-stage sum)
+    ref, ref_grad = _oracle_compound(logits.float(), target, exc, dim, conn, w_ti, batch_dice, do_bg)
+    assert abs(val.item() - ref) <= 1e-5 * max(1.0, abs(ref))          # fp32 softmax / log, fp64 accumulation
+    g = lg.grad.double().cpu() / 2.0
+    scale = ref_grad.abs().max().item()
+    tol = 1e-5 if dtype == torch.float32 else 8e-3                      # bf16 gradient storage: 2^-8 relative
+    assert (g - ref_grad).abs().max().item() <= tol * scale
+    if dtype != torch.float32:
+        return
+    # the unfused composition of the product (reference structure) agrees too
+    mod.fused = False
+    lg2 = lg.detach().clone().requires_grad_(True)
+    val2 = mod(lg2, target.to(DEV))
+    val2.backward()
+    assert abs(val2.item() - val.item()) <= 1e-5 * max(1.0, abs(ref))
+    assert (lg2.grad.double().cpu() - g).abs().max().item() <= max(tol, 2e-5) * scale
+
+
+def test_fused_seg_loss_full_size_properties():
+    """BASELINE patch (14 x 64 x 224 x 192): value vs the oracle, and gradient properties that hold at any size —
+    every voxel's gradient sums to zero over classes (softmax Jacobian), and the loss is invariant to a per-voxel
+    shift of all logits."""
+    from nextou_b200.losses import DC_and_CE_and_BTI_Loss
+    from oracle.ref_shims import SYNAPSE_EXCLUSION, make_tensors
+    exc = make_tensors(SYNAPSE_EXCLUSION)
+    logits, target = bti_case((1, 64, 224, 192), 14, 21)
+    mod = DC_and_CE_and_BTI_Loss({"batch_dice": True, "smooth": 1e-5, "do_bg": False, "ddp": False}, {},
+                                 {"dim": 3, "connectivity": 26, "inclusion": [], "exclusion": exc, "min_thick": 1},
+                                 weight_ce=1, weight_dice=1, weight_ti=1e-6)
+    lg = logits.to(DEV).requires_grad_(True)
+    val = mod(lg, target.to(DEV))
+    val.backward()
+    ref = TO.training_loss([logits, logits], [target, target], exc)     # weights (1, 0): one active scale
+    assert abs(val.item() - ref.item()) <= 1e-5 * abs(ref.item())
+    assert lg.grad.sum(1).abs().max().item() <= 1e-9
+    shifted = mod(lg.detach() + torch.randn(1, 1, 64, 224, 192, device=DEV), target.to(DEV))
+    assert abs(shifted.item() - val.item()) <= 1e-5 * abs(val.item())
