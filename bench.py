@@ -213,28 +213,37 @@ def run_own(args):
     for _ in range(max(args.warmup, 3)):
         step(x_dev, t_dev)
     barrier()
+    gstep = None
+    if not args.no_graph:
+        # the product's whole-step CUDA graph (nextou_b200/graphed.py): same step() body, captured once
+        from nextou_b200.graphed import GraphedTrainStep
+        gstep = GraphedTrainStep(model, loss_fn, opt, x_dev, t_dev, clip_grad_norm=12, reducer=reducer, warmup=1)
+        for _ in range(max(args.warmup, 3)):
+            gstep(gstep.static_x, gstep.static_t)
+        barrier()
 
     # ---- device-resident timing (value) -------------------------------------------------------------
     sampler = ClockSampler(local)
     if rank == 0:
         sampler.start()
-    _lib.KernelTimers.enabled = {"knn_topk", "gemm_tcgen05", "conv_halo_tcgen05", "conv_pertap_tcgen05",
-                                 "wgrad_halo_tcgen05", "wgrad_tcgen05"}
-    _lib.KernelTimers.reset()
+    timed = {"knn_topk", "gemm_tcgen05", "conv_halo_tcgen05", "conv_pertap_tcgen05", "wgrad_halo_tcgen05", "wgrad_tcgen05"}
+    if gstep is None:
+        _lib.KernelTimers.enabled = timed
+        _lib.KernelTimers.reset()
     dense.stats.clear()
     launches0 = _lib.launch_count()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     barrier()
     e0.record()
     for _ in range(args.steps):
-        step(x_dev, t_dev)
+        if gstep is None:
+            step(x_dev, t_dev)
+        else:
+            gstep(gstep.static_x, gstep.static_t)       # inputs resident: no copy
     e1.record()
     barrier()
     ms = e0.elapsed_time(e1)
-    launches = _lib.launch_count() - launches0
-    lib_calls = dict(dense.stats)
-    ktimes = _lib.KernelTimers.summary()
-    _lib.KernelTimers.enabled = set()
+    launches = (_lib.launch_count() - launches0) if gstep is None else gstep.launches_per_step * args.steps
     clocks = sampler.stop() if rank == 0 else None
 
     # ---- end-to-end timing (host buffers, H2D + D2H inside the timed region) -------------------------
@@ -243,12 +252,33 @@ def run_own(args):
     f0.record()
     last = 0.0
     for _ in range(args.steps):
-        xd = x_host.to(dev, non_blocking=True)
-        td = [t.to(dev, non_blocking=True) for t in t_host]
-        last = step(xd, td).item()          # D2H read of the loss
+        if gstep is None:
+            xd = x_host.to(dev, non_blocking=True)
+            td = [t.to(dev, non_blocking=True) for t in t_host]
+            last = step(xd, td).item()          # D2H read of the loss
+        else:
+            last = gstep(x_host, t_host).item()  # pinned host -> static device buffers, replay, D2H read of the loss
     f1.record()
     barrier()
     ms_e2e = f0.elapsed_time(f1)
+
+    # ---- per-kernel CUDA-event pass (roofline): kernels inside a graph replay cannot be bracketed by events, so the
+    # same step runs eagerly right after the timed region with an event pair around every tcgen05 / kNN launch --------
+    roof_steps = args.steps
+    if gstep is not None:
+        roof_steps = min(args.steps, 5)
+        _lib.KernelTimers.enabled = timed
+        _lib.KernelTimers.reset()
+        dense.stats.clear()
+        for _ in range(roof_steps):
+            step(x_dev, t_dev)
+        barrier()
+    lib_calls = {k: v * args.steps / roof_steps for k, v in dense.stats.items()}
+    ktimes = _lib.KernelTimers.summary()
+    for kt in ktimes.values():          # normalise to the timed region's step count
+        for key in ("launches", "ms", "bytes", "flops"):
+            kt[key] = kt[key] * args.steps / roof_steps
+    _lib.KernelTimers.enabled = set()
 
     if world > 1:
         t = torch.tensor([ms, ms_e2e], device=dev, dtype=torch.float64)
@@ -290,7 +320,7 @@ def run_own(args):
                     "launches_per_step": top["launches_per_step"], "avg_launch_ms": top["avg_launch_ms"],
                     "share_of_step": top["share_of_step"],
                     "definition": "achieved = algorithmic FLOPs (2*voxels*Cin*Cout*taps per launch, no padding) / CUDA-event time "
-                                  "of the launches inside the timed region; traffic = ncu dram bytes per launch (profiles/)",
+                                  "of the launches (eager pass of the same step right after the graph-replay timed region when graphs are on); traffic = ncu dram bytes per launch (profiles/)",
                     "all_kernels": fams}
         line = {"metric": METRIC, "value": world * args.steps / (ms * 1e-3), "unit": "patches/s", "n_gpus": world,
                 "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": ms / args.steps,
@@ -298,6 +328,7 @@ def run_own(args):
                 "config": {"workload": WORKLOAD, "global_batch": world, "parallelism": f"dp{world}",
                            "loss": "DeepSupervision(Dice+CE+1e-6*BTI, Synapse interactions)",
                            "optimizer": "SGD nesterov 0.99, clip 12",
+                           "execution": "eager" if gstep is None else "whole-step CUDA graph replay (fwd+loss+bwd+clip+SGD)",
                            "l2": "no flush needed: per-step working set (activations, several GB) >> 126 MB L2",
                            "library_calls_per_step": {k: v / args.steps for k, v in lib_calls.items()}},
                 "clocks": clocks,
@@ -327,6 +358,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="own", choices=["own", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-graph", action="store_true", help="issue every kernel from Python instead of replaying the step graph")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)

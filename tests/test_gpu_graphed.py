@@ -1,0 +1,90 @@
+"""Whole-step CUDA graph (nextou_b200/graphed.py): replay must reproduce the eager step."""
+import copy
+
+import numpy as np
+import pytest
+import torch
+
+from tests import helpers as H
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda"
+
+
+def _setup(seed=0):
+    from nextou_b200.losses import DC_and_CE_and_BTI_Loss, DeepSupervisionWrapper
+    from oracle.ref_shims import SYNAPSE_EXCLUSION, make_tensors
+    cfg = dict(H.MINI3D)
+    model = H.build_product(cfg, seed=seed).to(DEV).train()
+    exc = make_tensors(SYNAPSE_EXCLUSION)
+    exc = [[e.to(DEV) for e in p] if isinstance(p, list) else p.to(DEV) for p in exc]
+    inner = DC_and_CE_and_BTI_Loss({"batch_dice": True, "smooth": 1e-5, "do_bg": False, "ddp": False}, {},
+                                   {"dim": 3, "connectivity": 26, "inclusion": [], "exclusion": exc, "min_thick": 1},
+                                   weight_ce=1, weight_dice=1, weight_ti=1e-6)
+    g = torch.Generator().manual_seed(3)
+    x = torch.randn(1, 1, *cfg["patch"], generator=g)
+    with torch.no_grad(), torch.autocast("cuda", dtype=torch.bfloat16):
+        outs = model(x.to(DEV))
+    n_cls = outs[0].shape[1]
+    targets = [torch.randint(0, n_cls, (1, 1, *o.shape[2:]), generator=g).float() for o in outs]
+    w = np.array([1 / 2 ** i for i in range(len(outs))])
+    w[-1] = 0
+    loss_fn = DeepSupervisionWrapper(inner, (w / w.sum()).tolist())
+    return model, loss_fn, x, targets
+
+
+def test_graph_replay_matches_eager_steps():
+    from nextou_b200.graphed import GraphedTrainStep, graph_safe
+    model, loss_fn, x, targets = _setup()
+    assert graph_safe(model) is None
+    state0 = copy.deepcopy(model.state_dict())
+    xd, td = x.to(DEV), [t.to(DEV) for t in targets]
+
+    def make_opt(m):
+        return torch.optim.SGD([p for p in m.parameters() if p.requires_grad], lr=1e-2, momentum=0.99, nesterov=True,
+                               weight_decay=3e-5)
+
+    # eager: 2 steps from state0 with a fresh optimizer
+    opt = make_opt(model)
+    eager = []
+    for _ in range(2):
+        opt.zero_grad(set_to_none=True)
+        with torch.autocast("cuda", dtype=torch.bfloat16):
+            loss = loss_fn(model(xd), td)
+        loss.backward()
+        torch.nn.utils.clip_grad_norm_(opt.param_groups[0]["params"], 12)
+        opt.step()
+        eager.append(loss.item())
+    w_eager = {k: v.clone() for k, v in model.state_dict().items()}
+    del loss    # a live autograd graph pins AccumulateGrad nodes to the eager stream, which would invalidate the capture
+
+    # graphed: build (its warm-up steps move the weights), rewind to state0 and a clean momentum, replay 2 steps
+    opt2 = make_opt(model)
+    step = GraphedTrainStep(model, loss_fn, opt2, xd, td, clip_grad_norm=12, warmup=1)
+    assert step.launches_per_step > 100
+    with torch.no_grad():
+        model.load_state_dict(state0)
+        for st in opt2.state.values():
+            st["momentum_buffer"].zero_()
+    got = [step(x.pin_memory(), [t.pin_memory() for t in targets]).item() for _ in range(2)]
+    # first step: identical kernels on identical data (atomics in gather / pooling backward reorder fp32 sums, hence
+    # not bit-exact); momentum buffer zero == "first step" semantics of SGD since buf = grad either way up to dampening 0
+    assert abs(got[0] - eager[0]) <= 1e-6 * abs(eager[0])
+    assert abs(got[1] - eager[1]) <= 5e-2 * abs(eager[1])      # second step sees chaotic kNN flips of the updated net
+    num = sum((model.state_dict()[k].float() - w_eager[k].float()).pow(2).sum().item() for k in w_eager
+              if w_eager[k].dtype.is_floating_point)
+    den = sum(w_eager[k].float().pow(2).sum().item() for k in w_eager if w_eager[k].dtype.is_floating_point)
+    assert (num / den) ** 0.5 < 1e-2
+
+
+def test_graph_refuses_host_random_dilation():
+    from nextou_b200._lib import NextouError
+    from nextou_b200.blocks import DyGraphConv
+    from nextou_b200.graphed import GraphedTrainStep, graph_safe
+    model, loss_fn, x, targets = _setup()
+    first = next(m for m in model.modules() if isinstance(m, DyGraphConv))
+    first.d = 2
+    assert "dilation" in graph_safe(model)
+    opt = torch.optim.SGD(model.parameters(), lr=1e-2)
+    with pytest.raises(NextouError):
+        GraphedTrainStep(model, loss_fn, opt, x.to(DEV), [t.to(DEV) for t in targets])
