@@ -222,6 +222,32 @@ int nextou_conv3d_ndhwc_fwd(const void* x, long long ldx, int B, int D, int H, i
                             int Cout, int kd, int kh, int kw, const float* bias, void* out, long long ldo,
                             int out_dtype, void* stream);
 
+
+/* Strided convolution forward — the down-sampling first convolution of encoder stages 1..5 (StackedConvBlocks call sites
+ * NexToU_Encoder_Decoder.py:125-141; conv(k, stride, pad=(k-1)//2)):  out[o] = bias + sum_k x[o*s + k - p] . W[k].
+ * x: bf16 NDHWC [B][Di][Hi][Wi][ldx]; wpack as for nextou_conv3d_ndhwc_fwd; out: [B*Do*Ho*Wo][ldo] with
+ * Do = (Di + 2 pd - kd) / sd + 1 (likewise H, W).  The strided gather is done by the TMA unit (element strides). */
+int nextou_conv3d_ndhwc_strided_fwd(const void* x, long long ldx, int B, int Di, int Hi, int Wi, int Cin,
+                                    const void* wpack, int Cout, int kd, int kh, int kw, int sd, int sh, int sw, int pd,
+                                    int ph, int pw, const float* bias, void* out, long long ldo, int out_dtype,
+                                    void* stream);
+/* Data gradient of that convolution, and — with pd = ph = pw = 0 and kernel == stride — the FORWARD of the decoder's
+ * transposed convolutions (ConvTranspose(k = s = stride), NexToU_Encoder_Decoder.py:273-276, 321):
+ *   dx[u][ci] = bias[ci] + sum_{(v,k): v*s + k - p == u} dy[v][:] . wpack_t[ci][k][:]
+ * dy: bf16 NDHWC [B][Do][Ho][Wo][ldy] (Cout channels); wpack_t: bf16 [Cin][taps*cout_pad], taps in (kd,kh,kw) order (not
+ * flipped), cout_pad = ceil(Cout/64)*64; dx: [B*Di*Hi*Wi][ldx].  One launch per output parity class (u mod s). */
+int nextou_conv3d_ndhwc_strided_dgrad(const void* dy, long long ldy, int B, int Do, int Ho, int Wo, int Cout,
+                                      const void* wpack_t, int Cin, int kd, int kh, int kw, int sd, int sh, int sw, int pd,
+                                      int ph, int pw, const float* bias, void* dx, long long ldx, int Di, int Hi, int Wi,
+                                      int out_dtype, void* stream);
+/* Weight gradient with a strided read:  dW[m][tap][n] += sum_i dy[i][m] * x[i*s + tap - pad][n]  (fp32, caller zero-fills
+ * dW[Cout][taps][cin_stride]).  dy: bf16 tokens of the dense grid [B][D][H][W][ldy] (Cout = M channels); x: bf16 tokens of
+ * the strided-read volume [B][Dx][Hx][Wx][ldx] (Cin = N channels).  Strided convolution: dy = output gradient, x = input.
+ * Transposed convolution (kernel == stride, pad 0): dy := the layer input, x := the output gradient. */
+int nextou_conv3d_ndhwc_strided_wgrad(const void* dy, long long ldy, const void* x, long long ldx, int B, int D, int H,
+                                      int W, int Dx, int Hx, int Wx, int Cin, int Cout, int kd, int kh, int kw, int sd,
+                                      int sh, int sw, int pd, int ph, int pw, float* dW, int cin_stride, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -21,6 +21,7 @@ namespace nextou {
 constexpr int GEMM_BM = 128;
 constexpr int GEMM_BK = 64;   // one 128-byte swizzle row of bf16
 constexpr int GEMM_THREADS = 192;
+constexpr int MAX_TAPS = 64;
 
 struct GemmParams {
   // problem
@@ -37,10 +38,18 @@ struct GemmParams {
   const float* bias;   // [N] or NULL
   // implicit-GEMM geometry (is_conv)
   int is_conv;
-  int D, H, W;         // output volume (== input volume for the stride-1 'same' convs served here)
-  int td, th, tw;      // output brick per CTA (td*th*tw <= 128)
+  int D, H, W;         // the i-grid the CTAs tile (output volume of a forward conv; per-class sub-grid of a data gradient)
+  int td, th, tw;      // brick of the i-grid per CTA (td*th*tw <= 128)
   int nd, nh, nw;      // bricks per axis
-  int kd, kh, kw, pd, ph, pw;
+  // generalised tap geometry: tap t reads the input at coordinate i*es + tap_off[t] (es = element stride of the input
+  // tensor map) and uses weight block tap_wi[t]; grid point i is written to output voxel i*os + oo of a [Do][Ho][Wo] volume
+  int es_d, es_h, es_w;
+  int os_d, os_h, os_w, oo_d, oo_h, oo_w;
+  int Do, Ho, Wo;
+  int last_ksteps;     // K16 steps of the last (ragged) 64-channel block
+  int zero_fill;       // no taps at all: write bias / zeros
+  signed char tap_dd[MAX_TAPS], tap_dh[MAX_TAPS], tap_dw[MAX_TAPS];
+  short tap_wi[MAX_TAPS];
 };
 
 __global__ void __launch_bounds__(GEMM_THREADS, 1)
@@ -102,13 +111,13 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1)
         mbar_expect_tx(&full_bar[stage], (uint32_t)(a_tx + b_bytes));
         const int tap = it / p.kblocks, cb = it - tap * p.kblocks;
         if (p.is_conv) {
-          const int kw_ = tap % p.kw, kh_ = (tap / p.kw) % p.kh, kd_ = tap / (p.kw * p.kh);
-          tma_load_5d(smA + (size_t)stage * a_bytes, &tmA, &full_bar[stage], cb * GEMM_BK, w0 + kw_ - p.pw,
-                      h0 + kh_ - p.ph, d0 + kd_ - p.pd, bn);
+          tma_load_5d(smA + (size_t)stage * a_bytes, &tmA, &full_bar[stage], cb * GEMM_BK, w0 * p.es_w + p.tap_dw[tap],
+                      h0 * p.es_h + p.tap_dh[tap], d0 * p.es_d + p.tap_dd[tap], bn);
+          tma_load_2d(smB + (size_t)stage * b_bytes, &tmB, &full_bar[stage], (p.tap_wi[tap] * p.kblocks + cb) * GEMM_BK, n0);
         } else {
           tma_load_2d(smA + (size_t)stage * a_bytes, &tmA, &full_bar[stage], cb * GEMM_BK, m0);
+          tma_load_2d(smB + (size_t)stage * b_bytes, &tmB, &full_bar[stage], it * GEMM_BK, n0);
         }
-        tma_load_2d(smB + (size_t)stage * b_bytes, &tmB, &full_bar[stage], it * GEMM_BK, n0);
         if (++stage == p.stages) { stage = 0; phase ^= 1; }
       }
     }
@@ -116,16 +125,17 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1)
     // ===================== MMA issuer =====================
     {  // whole warp: warp-uniform control flow (descriptors stay in uniform registers), one elected lane issues
       const uint32_t idesc = make_idesc_bf16(GEMM_BM, p.block_n);
-      int stage = 0;
+      int stage = 0, cb = 0;
       uint32_t phase = 0;
       for (int it = 0; it < total_kb; ++it) {
         mbar_wait(&full_bar[stage], phase);
         tc_fence_after();
         const uint64_t adesc = make_kmajor_sw128_desc(smem_u32(smA + (size_t)stage * a_bytes));
         const uint64_t bdesc = make_kmajor_sw128_desc(smem_u32(smB + (size_t)stage * b_bytes));
+        const int ksteps = (cb == p.kblocks - 1) ? p.last_ksteps : GEMM_BK / 16;   // skip all-zero K16 steps of the padding
+        if (++cb == p.kblocks) cb = 0;
         if (elect_one()) {
-#pragma unroll
-          for (int k = 0; k < GEMM_BK / 16; ++k) {
+          for (int k = 0; k < ksteps; ++k) {
             // advance 16 bf16 = 32 B along K inside the 128-byte swizzle row: +2 in the (>>4) start-address field
             umma_f16(tmem_base, adesc + (uint64_t)(2 * k), bdesc + (uint64_t)(2 * k), idesc, (it | k) != 0 ? 1u : 0u);
           }
@@ -134,12 +144,12 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1)
         __syncwarp();
         if (++stage == p.stages) { stage = 0; phase ^= 1; }
       }
-      if (elect_one()) umma_commit(tmem_full_bar);        // accumulator complete
+      if (total_kb > 0 && elect_one()) umma_commit(tmem_full_bar);        // accumulator complete
       __syncwarp();
     }
   } else {
     // ===================== epilogue (warps 2..5 -> TMEM lane quarters warp%4) =====================
-    mbar_wait(tmem_full_bar, 0);
+    if (!p.zero_fill) mbar_wait(tmem_full_bar, 0);
     tc_fence_after();
     const int q = warp & 3;
     const int r = q * 32 + lane;  // row inside the tile == TMEM lane
@@ -147,14 +157,20 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1)
     if (p.is_conv) {
       const int wx = r % p.tw, hy = (r / p.tw) % p.th, dz = r / (p.tw * p.th);
       const int d = d0 + dz, h = h0 + hy, w = w0 + wx;
-      if (dz < p.td && d < p.D && h < p.H && w < p.W) out_row = (((long long)bn * p.D + d) * p.H + h) * p.W + w;
+      if (dz < p.td && d < p.D && h < p.H && w < p.W)
+        out_row = (((long long)bn * p.Do + d * p.os_d + p.oo_d) * p.Ho + h * p.os_h + p.oo_h) * p.Wo + w * p.os_w + p.oo_w;
     } else if (m0 + r < p.M) {
       out_row = m0 + r;
     }
     for (int c = 0; c < p.block_n; c += 16) {
       uint32_t raw[16];
-      tmem_ld16(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)c, raw);
-      tmem_ld_wait();
+      if (!p.zero_fill) {
+        tmem_ld16(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)c, raw);
+        tmem_ld_wait();
+      } else {
+#pragma unroll
+        for (int j = 0; j < 16; ++j) raw[j] = 0u;
+      }
       if (out_row >= 0) {
         float v[16];
 #pragma unroll
@@ -418,55 +434,161 @@ extern "C" int nextou_gemm_bf16_tn(const void* A, long long lda, const void* B, 
   return check_launch("gemm_pers_tcgen05_kernel");
 }
 
-// Stride-1 'same' convolution as implicit GEMM.  x: bf16 NDHWC [B][D][H][W][ldx] (ldx % 8 == 0, channels >= Cin are
-// ignored); wpack: bf16 [Cout][taps * cin_pad] with cin_pad = ceil(Cin/64)*64 and taps ordered (kd, kh, kw), zero padded;
-// out: [B*D*H*W][ldo] bf16/fp32, columns [Cout, ldo) zero-filled.  2-D convolutions use D = 1, kd = 1.
-extern "C" int nextou_conv3d_ndhwc_fwd(const void* x, long long ldx, int B, int D, int H, int W, int Cin,
-                                       const void* wpack, int Cout, int kd, int kh, int kw, const float* bias,
-                                       void* out, long long ldo, int out_dtype, void* stream) {
-  NEXTOU_REQUIRE(x && wpack && out, "conv3d_ndhwc_fwd: null pointer");
-  NEXTOU_REQUIRE(B > 0 && D > 0 && H > 0 && W > 0 && Cin > 0 && Cout > 0, "conv3d_ndhwc_fwd: bad shape");
-  NEXTOU_REQUIRE(kd % 2 == 1 && kh % 2 == 1 && kw % 2 == 1 && kd * kh * kw <= 343, "conv3d_ndhwc_fwd: odd kernel sizes only");
-  NEXTOU_REQUIRE(ldx % 8 == 0 && ldx >= Cin && ldo % 8 == 0 && ldo >= Cout, "conv3d_ndhwc_fwd: pitches must be multiples of 8");
-  NEXTOU_REQUIRE(((uintptr_t)x & 15) == 0 && ((uintptr_t)wpack & 15) == 0 && ((uintptr_t)out & 15) == 0, "conv3d_ndhwc_fwd: 16-byte alignment");
-  NEXTOU_REQUIRE(out_dtype == NEXTOU_BF16 || out_dtype == NEXTOU_F32, "conv3d_ndhwc_fwd: bad out dtype");
+// ------------------------------------------------------------------------------------------------------
+// General per-tap implicit GEMM: out[i*os + oo][:] = bias + sum_t  x[i*es + off_t][:] * Wblock[wi_t]^T   for i in an i-grid.
+// Serves (a) strided forward convolutions (es = stride, os = 1), (b) the data gradient of a strided convolution and the
+// forward of a kernel == stride transposed convolution, one launch per output parity class (es = 1, os = stride, oo = class).
+// ------------------------------------------------------------------------------------------------------
+namespace nextou {
+struct TapList {
+  int n = 0;
+  int dd[MAX_TAPS], dh[MAX_TAPS], dw[MAX_TAPS], wi[MAX_TAPS];
+};
+
+static int launch_conv_general(const void* x, long long ldx, int B, int Di, int Hi, int Wi, int Cin, const void* wpack,
+                               int w_taps_total, int Cout, const TapList& taps, int gd, int gh, int gw,   // i-grid
+                               int es_d, int es_h, int es_w, int os_d, int os_h, int os_w, int oo_d, int oo_h, int oo_w,
+                               int Do, int Ho, int Wo, const float* bias, void* out, long long ldo, int out_dtype,
+                               cudaStream_t stream) {
   GemmParams p = {};
-  p.M = 0; p.N = Cout; p.kblocks = (Cin + GEMM_BK - 1) / GEMM_BK; p.taps = kd * kh * kw;
+  p.M = 0; p.N = Cout; p.kblocks = (Cin + GEMM_BK - 1) / GEMM_BK; p.taps = taps.n;
+  p.last_ksteps = (Cin - (p.kblocks - 1) * GEMM_BK + 15) / 16;
+  p.zero_fill = taps.n == 0 ? 1 : 0;
   p.C = out; p.ldc = ldo; p.out_dtype = out_dtype; p.bias = bias; p.is_conv = 1;
-  p.D = D; p.H = H; p.W = W; p.kd = kd; p.kh = kh; p.kw = kw; p.pd = kd / 2; p.ph = kh / 2; p.pw = kw / 2;
-  // brick (td x th x tw <= 128 voxels) minimising the number of CTAs; ties -> the widest W extent (coalescing)
+  p.D = gd; p.H = gh; p.W = gw;
+  p.es_d = es_d; p.es_h = es_h; p.es_w = es_w;
+  p.os_d = os_d; p.os_h = os_h; p.os_w = os_w; p.oo_d = oo_d; p.oo_h = oo_h; p.oo_w = oo_w;
+  p.Do = Do; p.Ho = Ho; p.Wo = Wo;
+  for (int t = 0; t < taps.n; ++t) {
+    p.tap_dd[t] = (signed char)taps.dd[t]; p.tap_dh[t] = (signed char)taps.dh[t]; p.tap_dw[t] = (signed char)taps.dw[t];
+    p.tap_wi[t] = (short)taps.wi[t];
+  }
+  // brick (td x th x tw <= 128 grid points) minimising the number of CTAs; ties -> the widest W extent (coalescing);
+  // the TMA box of a strided read spans t*es source elements per axis (<= 256)
   int tw = 1, th = 1, td = 1;
   long long best = -1;
-  for (int a = 1; a <= (W < 128 ? W : 128); ++a)
-    for (int b = 1; a * b <= 128 && b <= H; ++b) {
+  for (int a = 1; a <= (gw < 128 ? gw : 128); ++a)
+    for (int b = 1; a * b <= 128 && b <= gh; ++b) {
       int c = 128 / (a * b);
-      if (c > D) c = D;
-      const long long tiles = (long long)((W + a - 1) / a) * ((H + b - 1) / b) * ((D + c - 1) / c);
+      if (c > gd) c = gd;
+      if (a * es_w > 256 || b * es_h > 256 || c * es_d > 256) continue;
+      const long long tiles = (long long)((gw + a - 1) / a) * ((gh + b - 1) / b) * ((gd + c - 1) / c);
       if (best < 0 || tiles < best || (tiles == best && a > tw && a <= 32)) {
         best = tiles; tw = a; th = b; td = c;
       }
     }
   p.tw = tw; p.th = th; p.td = td;
-  p.nw = (W + tw - 1) / tw; p.nh = (H + th - 1) / th; p.nd = (D + td - 1) / td;
+  p.nw = (gw + tw - 1) / tw; p.nh = (gh + th - 1) / th; p.nd = (gd + td - 1) / td;
   const int bn = pick_block_n(Cout);
   const int cin_pad = p.kblocks * GEMM_BK;
   CUtensorMap tmA, tmB;
   {
-    cuuint64_t dims[5] = {(cuuint64_t)Cin, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)D, (cuuint64_t)B};
-    cuuint64_t str[4] = {(cuuint64_t)ldx * 2, (cuuint64_t)ldx * 2 * W, (cuuint64_t)ldx * 2 * W * H,
-                         (cuuint64_t)ldx * 2 * W * H * D};
-    cuuint32_t box[5] = {GEMM_BK, (cuuint32_t)tw, (cuuint32_t)th, (cuuint32_t)td, 1};
-    int rc = encode_bf16_map(&tmA, x, 5, dims, str, box, "conv input");
+    cuuint64_t dims[5] = {(cuuint64_t)Cin, (cuuint64_t)Wi, (cuuint64_t)Hi, (cuuint64_t)Di, (cuuint64_t)B};
+    cuuint64_t str[4] = {(cuuint64_t)ldx * 2, (cuuint64_t)ldx * 2 * Wi, (cuuint64_t)ldx * 2 * Wi * Hi,
+                         (cuuint64_t)ldx * 2 * Wi * Hi * Di};
+    cuuint32_t box[5] = {GEMM_BK, (cuuint32_t)(tw * es_w), (cuuint32_t)(th * es_h), (cuuint32_t)(td * es_d), 1};
+    cuuint32_t estr[5] = {1, (cuuint32_t)es_w, (cuuint32_t)es_h, (cuuint32_t)es_d, 1};
+    int rc = encode_bf16_map(&tmA, x, 5, dims, str, box, "conv input", estr);
     if (rc) return rc;
   }
   {
-    cuuint64_t dims[2] = {(cuuint64_t)p.taps * cin_pad, (cuuint64_t)Cout};
-    cuuint64_t str[1] = {(cuuint64_t)p.taps * cin_pad * 2};
+    cuuint64_t dims[2] = {(cuuint64_t)w_taps_total * cin_pad, (cuuint64_t)Cout};
+    cuuint64_t str[1] = {(cuuint64_t)w_taps_total * cin_pad * 2};
     cuuint32_t box[2] = {GEMM_BK, (cuuint32_t)bn};
     int rc = encode_bf16_map(&tmB, wpack, 2, dims, str, box, "conv weights");
     if (rc) return rc;
   }
-  return launch_gemm(tmA, tmB, p, (long long)B * p.nd * p.nh * p.nw, (cudaStream_t)stream);
+  return launch_gemm(tmA, tmB, p, (long long)B * p.nd * p.nh * p.nw, stream);
+}
+
+static int conv_common_checks(const char* who, const void* x, const void* w, const void* out, long long ldx, int Cin,
+                              long long ldo, int Cout, int out_dtype) {
+  NEXTOU_REQUIRE(x && w && out, "%s: null pointer", who);
+  NEXTOU_REQUIRE(Cin > 0 && Cout > 0, "%s: bad channel counts", who);
+  NEXTOU_REQUIRE(ldx % 8 == 0 && ldx >= Cin && ldo % 8 == 0 && ldo >= Cout, "%s: pitches must be multiples of 8", who);
+  NEXTOU_REQUIRE(((uintptr_t)x & 15) == 0 && ((uintptr_t)w & 15) == 0 && ((uintptr_t)out & 15) == 0, "%s: 16-byte alignment", who);
+  NEXTOU_REQUIRE(out_dtype == NEXTOU_BF16 || out_dtype == NEXTOU_F32, "%s: bad out dtype", who);
+  return 0;
+}
+}  // namespace nextou
+
+// Strided convolution forward (StackedConvBlocks down-sampling convs, ED:134-141): out[o] = b + sum_k x[o*s + k - p] W[k].
+// x: bf16 NDHWC [B][Di][Hi][Wi][ldx]; wpack: bf16 [Cout][taps*cin_pad] (taps ordered (kd, kh, kw), cin_pad = ceil(Cin/64)*64);
+// out: [B*Do*Ho*Wo][ldo] with Do = (Di + 2 pd - kd) / sd + 1 (likewise H, W); columns [Cout, ldo) are zero-filled.
+// The strided gather is done by the TMA unit (tensor map with element strides), out-of-range taps are zero-filled.
+extern "C" int nextou_conv3d_ndhwc_strided_fwd(const void* x, long long ldx, int B, int Di, int Hi, int Wi, int Cin,
+                                               const void* wpack, int Cout, int kd, int kh, int kw, int sd, int sh, int sw,
+                                               int pd, int ph, int pw, const float* bias, void* out, long long ldo,
+                                               int out_dtype, void* stream) {
+  int rc = conv_common_checks("conv3d_ndhwc_strided_fwd", x, wpack, out, ldx, Cin, ldo, Cout, out_dtype);
+  if (rc) return rc;
+  NEXTOU_REQUIRE(B > 0 && Di > 0 && Hi > 0 && Wi > 0, "conv3d_ndhwc_strided_fwd: bad shape");
+  NEXTOU_REQUIRE(kd > 0 && kh > 0 && kw > 0 && kd * kh * kw <= MAX_TAPS, "conv3d_ndhwc_strided_fwd: at most %d taps", MAX_TAPS);
+  NEXTOU_REQUIRE(sd >= 1 && sh >= 1 && sw >= 1 && sd <= 8 && sh <= 8 && sw <= 8, "conv3d_ndhwc_strided_fwd: strides must be in [1, 8]");
+  NEXTOU_REQUIRE(pd >= 0 && ph >= 0 && pw >= 0 && pd < 64 && ph < 64 && pw < 64, "conv3d_ndhwc_strided_fwd: bad padding");
+  const int Do = (Di + 2 * pd - kd) / sd + 1, Ho = (Hi + 2 * ph - kh) / sh + 1, Wo = (Wi + 2 * pw - kw) / sw + 1;
+  NEXTOU_REQUIRE(Do > 0 && Ho > 0 && Wo > 0, "conv3d_ndhwc_strided_fwd: empty output");
+  TapList taps;
+  for (int a = 0; a < kd; ++a)
+    for (int b = 0; b < kh; ++b)
+      for (int c = 0; c < kw; ++c) {
+        const int t = taps.n++;
+        taps.dd[t] = a - pd; taps.dh[t] = b - ph; taps.dw[t] = c - pw; taps.wi[t] = t;
+      }
+  return launch_conv_general(x, ldx, B, Di, Hi, Wi, Cin, wpack, kd * kh * kw, Cout, taps, Do, Ho, Wo, sd, sh, sw, 1, 1, 1, 0, 0,
+                             0, Do, Ho, Wo, bias, out, ldo, out_dtype, (cudaStream_t)stream);
+}
+
+// Stride-1 'same' convolution (odd kernels): the per-tap variant of nextou_conv3d_ndhwc_halo_fwd.
+extern "C" int nextou_conv3d_ndhwc_fwd(const void* x, long long ldx, int B, int D, int H, int W, int Cin,
+                                       const void* wpack, int Cout, int kd, int kh, int kw, const float* bias,
+                                       void* out, long long ldo, int out_dtype, void* stream) {
+  NEXTOU_REQUIRE(kd % 2 == 1 && kh % 2 == 1 && kw % 2 == 1, "conv3d_ndhwc_fwd: odd kernel sizes only");
+  return nextou_conv3d_ndhwc_strided_fwd(x, ldx, B, D, H, W, Cin, wpack, Cout, kd, kh, kw, 1, 1, 1, kd / 2, kh / 2, kw / 2, bias,
+                                         out, ldo, out_dtype, stream);
+}
+
+// Data gradient of a strided convolution, and (pd = ph = pw = 0, kernel == stride) the FORWARD of a transposed
+// convolution (decoder up-sampling, ED:273-276, 321):
+//   dx[u][ci] = bias[ci] + sum_{(v, k): v*s + k - p == u} dy[v][:] . wpack_t[ci][k][:]
+// dy: bf16 NDHWC [B][Do][Ho][Wo][ldy] (Cout channels); wpack_t: bf16 [Cin][taps*cout_pad] (taps in (kd, kh, kw) order, NOT
+// flipped); dx: [B*Di*Hi*Wi][ldx].  One launch per output parity class u mod s: each class is a small stride-1 convolution
+// of dy whose results are written to every s-th voxel of dx; a class without taps (k < s) is written as bias / zeros.
+extern "C" int nextou_conv3d_ndhwc_strided_dgrad(const void* dy, long long ldy, int B, int Do, int Ho, int Wo, int Cout,
+                                                 const void* wpack_t, int Cin, int kd, int kh, int kw, int sd, int sh, int sw,
+                                                 int pd, int ph, int pw, const float* bias, void* dx, long long ldx, int Di,
+                                                 int Hi, int Wi, int out_dtype, void* stream) {
+  int rc = conv_common_checks("conv3d_ndhwc_strided_dgrad", dy, wpack_t, dx, ldy, Cout, ldx, Cin, out_dtype);
+  if (rc) return rc;
+  NEXTOU_REQUIRE(B > 0 && Do > 0 && Ho > 0 && Wo > 0 && Di > 0 && Hi > 0 && Wi > 0, "conv3d_ndhwc_strided_dgrad: bad shape");
+  NEXTOU_REQUIRE(kd > 0 && kh > 0 && kw > 0 && kd * kh * kw <= MAX_TAPS, "conv3d_ndhwc_strided_dgrad: at most %d taps", MAX_TAPS);
+  NEXTOU_REQUIRE(sd >= 1 && sh >= 1 && sw >= 1 && sd <= 8 && sh <= 8 && sw <= 8, "conv3d_ndhwc_strided_dgrad: strides must be in [1, 8]");
+  NEXTOU_REQUIRE(pd >= 0 && ph >= 0 && pw >= 0 && pd < 64 && ph < 64 && pw < 64, "conv3d_ndhwc_strided_dgrad: bad padding");
+  for (int od = 0; od < sd && od < Di; ++od)
+    for (int oh = 0; oh < sh && oh < Hi; ++oh)
+      for (int ow = 0; ow < sw && ow < Wi; ++ow) {
+        TapList taps;
+        for (int a = 0; a < kd; ++a) {
+          const int ta = od + pd - a;
+          if (((ta % sd) + sd) % sd) continue;
+          for (int b = 0; b < kh; ++b) {
+            const int tb = oh + ph - b;
+            if (((tb % sh) + sh) % sh) continue;
+            for (int c = 0; c < kw; ++c) {
+              const int tc = ow + pw - c;
+              if (((tc % sw) + sw) % sw) continue;
+              const int t = taps.n++;
+              taps.dd[t] = ta / sd; taps.dh[t] = tb / sh; taps.dw[t] = tc / sw;
+              taps.wi[t] = (a * kh + b) * kw + c;
+            }
+          }
+        }
+        const int gd = (Di - od + sd - 1) / sd, gh = (Hi - oh + sh - 1) / sh, gw = (Wi - ow + sw - 1) / sw;
+        rc = launch_conv_general(dy, ldy, B, Do, Ho, Wo, Cout, wpack_t, kd * kh * kw, Cin, taps, gd, gh, gw, 1, 1, 1, sd, sh, sw,
+                                 od, oh, ow, Di, Hi, Wi, bias, dx, ldx, out_dtype, (cudaStream_t)stream);
+        if (rc) return rc;
+      }
+  return 0;
 }
 
 // ======================================================================================================
@@ -489,6 +611,7 @@ struct WgradParams {
   int D, H, W, B;
   int td, th, tw, nd, nh, nw;     // 64-voxel brick and bricks per axis
   int kd, kh, kw, pd, ph, pw, taps;
+  int sd, sh, sw;                 // X is read at brick_origin * s + tap - pad (strided convolution / transposed convolution)
   int n_tile;                     // N per CTA (multiple of 16, <= 256)
   int n_boxes;                    // ceil(n_tile / 64)
   int tap_group;                  // taps per CTA (tap_group * n_tile <= 512 TMEM columns)
@@ -571,7 +694,7 @@ __global__ void __launch_bounds__(WG_THREADS, 1)
           const int kw_ = tap % p.kw, kh_ = (tap / p.kw) % p.kh, kd_ = tap / (p.kw * p.kh);
           for (int j = 0; j < p.n_boxes; ++j)
             tma_load_5d(st + (size_t)(2 + tp * p.n_boxes + j) * WG_BOX_BYTES, &tmX, &full_bar[stage], n0 + 64 * j,
-                        w0 + kw_ - p.pw, h0 + kh_ - p.ph, d0 + kd_ - p.pd, bn);
+                        w0 * p.sw + kw_ - p.pw, h0 * p.sh + kh_ - p.ph, d0 * p.sd + kd_ - p.pd, bn);
         }
         if (++stage == p.stages) { stage = 0; phase ^= 1; }
       }
@@ -632,19 +755,25 @@ __global__ void __launch_bounds__(WG_THREADS, 1)
 
 }  // namespace nextou
 
-// dW[Cout][taps][cin_stride] (fp32, caller zero-fills) += wgrad of a stride-1 'same' convolution.  dy: bf16 tokens
-// [B*D*H*W][ldy] (Cout channels), x: bf16 tokens [..][ldx] (Cin channels).  A 1x1 layer is kd = kh = kw = 1.
-extern "C" int nextou_conv3d_ndhwc_wgrad(const void* dy, long long ldy, const void* x, long long ldx, int B, int D, int H,
-                                         int W, int Cin, int Cout, int kd, int kh, int kw, float* dW, int cin_stride,
-                                         void* stream) {
+// General weight gradient:  dW[m][tap][n] += sum_i dy[i][m] * x[i*s + tap - pad][n]   (fp32, the caller zero-fills
+// dW[Cout][taps][cin_stride]).  dy: bf16 tokens of the DENSE grid [B][D][H][W][ldy] (Cout channels = M); x: bf16 tokens of
+// the strided-read volume [B][Dx][Hx][Wx][ldx] (Cin channels = N).  Strided convolution: dy = output gradient, x = input.
+// Transposed convolution (kernel == stride, pad 0): dy := the layer INPUT, x := the output gradient, dW = [Cin_t][tap][Cout_t].
+extern "C" int nextou_conv3d_ndhwc_strided_wgrad(const void* dy, long long ldy, const void* x, long long ldx, int B, int D,
+                                                 int H, int W, int Dx, int Hx, int Wx, int Cin, int Cout, int kd, int kh,
+                                                 int kw, int sd, int sh, int sw, int pd, int ph, int pw, float* dW,
+                                                 int cin_stride, void* stream) {
   NEXTOU_REQUIRE(dy && x && dW, "conv3d_ndhwc_wgrad: null pointer");
-  NEXTOU_REQUIRE(B > 0 && D > 0 && H > 0 && W > 0 && Cin > 0 && Cout > 0 && cin_stride >= Cin, "conv3d_ndhwc_wgrad: bad shape");
-  NEXTOU_REQUIRE(kd % 2 == 1 && kh % 2 == 1 && kw % 2 == 1, "conv3d_ndhwc_wgrad: odd kernel sizes only");
+  NEXTOU_REQUIRE(B > 0 && D > 0 && H > 0 && W > 0 && Dx > 0 && Hx > 0 && Wx > 0 && Cin > 0 && Cout > 0 && cin_stride >= Cin,
+                 "conv3d_ndhwc_wgrad: bad shape");
+  NEXTOU_REQUIRE(kd > 0 && kh > 0 && kw > 0 && sd >= 1 && sh >= 1 && sw >= 1 && sd <= 4 && sh <= 4 && sw <= 4 && pd >= 0 &&
+                 ph >= 0 && pw >= 0, "conv3d_ndhwc_wgrad: bad kernel / stride / padding");
   NEXTOU_REQUIRE(ldy % 8 == 0 && ldy >= Cout && ldx % 8 == 0 && ldx >= Cin, "conv3d_ndhwc_wgrad: pitches must be multiples of 8");
   NEXTOU_REQUIRE(((uintptr_t)dy & 15) == 0 && ((uintptr_t)x & 15) == 0, "conv3d_ndhwc_wgrad: 16-byte alignment");
   WgradParams p = {};
   p.Cout = Cout; p.Cin = Cin; p.D = D; p.H = H; p.W = W; p.B = B;
-  p.kd = kd; p.kh = kh; p.kw = kw; p.pd = kd / 2; p.ph = kh / 2; p.pw = kw / 2; p.taps = kd * kh * kw;
+  p.kd = kd; p.kh = kh; p.kw = kw; p.pd = pd; p.ph = ph; p.pw = pw; p.taps = kd * kh * kw;
+  p.sd = sd; p.sh = sh; p.sw = sw;
   p.dW = dW; p.cin_stride = cin_stride;
   // 64-voxel brick with power-of-two edges minimising the brick count (ties: widest along W)
   long long best = -1;
@@ -685,11 +814,12 @@ extern "C" int nextou_conv3d_ndhwc_wgrad(const void* dy, long long ldy, const vo
     if (rc) return rc;
   }
   {
-    cuuint64_t dims[5] = {(cuuint64_t)Cin, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)D, (cuuint64_t)B};
-    cuuint64_t str[4] = {(cuuint64_t)ldx * 2, (cuuint64_t)ldx * 2 * W, (cuuint64_t)ldx * 2 * W * H,
-                         (cuuint64_t)ldx * 2 * W * H * D};
-    cuuint32_t box[5] = {64, (cuuint32_t)p.tw, (cuuint32_t)p.th, (cuuint32_t)p.td, 1};
-    int rc = encode_bf16_map(&tmX, x, 5, dims, str, box, "wgrad X");
+    cuuint64_t dims[5] = {(cuuint64_t)Cin, (cuuint64_t)Wx, (cuuint64_t)Hx, (cuuint64_t)Dx, (cuuint64_t)B};
+    cuuint64_t str[4] = {(cuuint64_t)ldx * 2, (cuuint64_t)ldx * 2 * Wx, (cuuint64_t)ldx * 2 * Wx * Hx,
+                         (cuuint64_t)ldx * 2 * Wx * Hx * Dx};
+    cuuint32_t box[5] = {64, (cuuint32_t)(p.tw * sw), (cuuint32_t)(p.th * sh), (cuuint32_t)(p.td * sd), 1};
+    cuuint32_t estr[5] = {1, (cuuint32_t)sw, (cuuint32_t)sh, (cuuint32_t)sd, 1};
+    int rc = encode_bf16_map(&tmX, x, 5, dims, str, box, "wgrad X", estr);
     if (rc) return rc;
   }
   const size_t smem = 1024 + (size_t)p.stages * (2 + tg * p.n_boxes) * WG_BOX_BYTES + (2 * p.stages + 1) * sizeof(uint64_t) + 16;
@@ -699,4 +829,13 @@ extern "C" int nextou_conv3d_ndhwc_wgrad(const void* dy, long long ldy, const vo
   dim3 grid((unsigned)p.ksplit, (unsigned)tiles);
   wgrad_tcgen05_kernel<<<grid, WG_THREADS, smem, (cudaStream_t)stream>>>(tmDY, tmX, p);
   return check_launch("wgrad_tcgen05_kernel");
+}
+
+// Stride-1 'same' convolution (odd kernels) / 1x1 layer (kd = kh = kw = 1): see nextou_conv3d_ndhwc_strided_wgrad.
+extern "C" int nextou_conv3d_ndhwc_wgrad(const void* dy, long long ldy, const void* x, long long ldx, int B, int D, int H,
+                                         int W, int Cin, int Cout, int kd, int kh, int kw, float* dW, int cin_stride,
+                                         void* stream) {
+  NEXTOU_REQUIRE(kd % 2 == 1 && kh % 2 == 1 && kw % 2 == 1, "conv3d_ndhwc_wgrad: odd kernel sizes only");
+  return nextou_conv3d_ndhwc_strided_wgrad(dy, ldy, x, ldx, B, D, H, W, D, H, W, Cin, Cout, kd, kh, kw, 1, 1, 1, kd / 2, kh / 2,
+                                           kw / 2, dW, cin_stride, stream);
 }

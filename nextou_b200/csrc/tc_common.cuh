@@ -192,13 +192,16 @@ inline EncodeTiledFn encode_fn() {
 }
 
 inline int encode_bf16_map(CUtensorMap* map, const void* base, int rank, const cuuint64_t* dims,
-                           const cuuint64_t* strides_bytes, const cuuint32_t* box, const char* what) {
+                           const cuuint64_t* strides_bytes, const cuuint32_t* box, const char* what,
+                           const cuuint32_t* elem_strides = nullptr) {
   EncodeTiledFn fn = encode_fn();
   if (!fn) {
     set_error("cuTensorMapEncodeTiled entry point unavailable");
     return NEXTOU_ERR_CUDA;
   }
   cuuint32_t estr[5] = {1, 1, 1, 1, 1};
+  if (elem_strides)   // strided traversal: the box spans box[i] source elements, ceil(box[i] / stride[i]) land in smem
+    for (int i = 0; i < rank; ++i) estr[i] = elem_strides[i];
   CUresult r = fn(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, (cuuint32_t)rank, const_cast<void*>(base), dims, strides_bytes,
                   box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);

@@ -77,6 +77,12 @@ def conv_tokens(tok: torch.Tensor, batch: int, spatial: Sequence[int], conv: tor
     if same and _bf16_path(tok):
         stats["tcgen05.conv"] += 1
         return native.conv_tokens(tok, conv.weight, conv.bias, batch, spatial), tuple(spatial)
+    plain = all(d == 1 for d in conv.dilation) and conv.groups == 1 and conv.padding_mode == "zeros" \
+        and not isinstance(conv.padding, str) and all(1 <= s <= 4 for s in stride) and len(ks) in (2, 3) \
+        and int(torch.tensor(ks).prod()) <= 64
+    if plain and _bf16_path(tok):
+        stats["tcgen05.conv_strided"] += 1
+        return native.conv_strided_tokens(tok, conv.weight, conv.bias, batch, spatial, stride, tuple(conv.padding))
     stats["cudnn.conv"] += 1
     x = ops.from_tokens(tok, batch, spatial)
     f = F.conv3d if x.dim() == 5 else F.conv2d
@@ -86,6 +92,13 @@ def conv_tokens(tok: torch.Tensor, batch: int, spatial: Sequence[int], conv: tor
 
 
 def conv_transpose_nd(x, weight, bias, stride):
+    """ConvTranspose(kernel == stride) of the decoder (ED:273-276, 321) on a logical (N, C, *spatial) tensor."""
+    ks = tuple(weight.shape[2:])
+    if tuple(stride) == ks and all(1 <= s <= 4 for s in ks) and _bf16_path(x):
+        stats["tcgen05.conv_transpose"] += 1
+        B, spatial = x.shape[0], tuple(x.shape[2:])
+        y, osp = native.conv_transpose_tokens(ops.as_tokens(x), weight, bias, B, spatial)
+        return ops.from_tokens(y, B, osp)
     stats["cudnn.conv_transpose"] += 1
     f = F.conv_transpose3d if x.dim() == 5 else F.conv_transpose2d
     return f(x, weight, bias, stride=stride)

@@ -94,3 +94,97 @@ class _ConvTokens(torch.autograd.Function):
 
 def conv_tokens(x_tok, weight, bias, batch: int, spatial: Sequence[int]):
     return _ConvTokens.apply(x_tok, weight, bias, batch, tuple(spatial))
+
+
+def _out_spatial(spatial, ks, stride, padding):
+    return tuple((n + 2 * p - k) // s + 1 for n, k, s, p in zip(spatial, ks, stride, padding))
+
+
+class _ConvStridedTokens(torch.autograd.Function):
+    """Strided convolution (the down-sampling conv of an encoder stage) on a token-major bf16 volume: forward = per-tap
+    implicit GEMM with a strided TMA gather, data gradient = one stride-1 sub-convolution per output parity class,
+    weight gradient = MN-major tcgen05 kernel with a strided X box."""
+
+    @staticmethod
+    def forward(ctx, x, weight, bias, batch, spatial, stride, padding):
+        xb = ops.tma_ready_bf16(x)
+        cout, cin = weight.shape[:2]
+        ks = tuple(weight.shape[2:])
+        y, _ = ops.conv_strided_fwd_bf16(xb, batch, spatial, cin, ops.pack_conv_weight(weight.detach()), cout, ks, stride,
+                                         padding, bias)
+        ctx.save_for_backward(xb, weight)
+        ctx.meta = (batch, tuple(spatial), tuple(stride), tuple(padding), bias is not None, None if bias is None else bias.dtype)
+        return y[:, :cout]
+
+    @staticmethod
+    def backward(ctx, dy):
+        xb, weight = ctx.saved_tensors
+        batch, spatial, stride, padding, has_bias, bdt = ctx.meta
+        cout, cin = weight.shape[:2]
+        ks = tuple(weight.shape[2:])
+        osp = _out_spatial(spatial, ks, stride, padding)
+        dyb = ops.tma_ready_bf16(dy)
+        dx = dw = db = None
+        if ctx.needs_input_grad[0]:
+            wt = ops.pack_conv_weight(weight.detach(), transpose=True)
+            dx = ops.conv_strided_dgrad_bf16(dyb, batch, osp, cout, wt, cin, ks, stride, padding, spatial)[:, :cin]
+        if ctx.needs_input_grad[1]:
+            dw = ops.conv_strided_wgrad_bf16(dyb, xb, batch, osp, spatial, cin, cout, ks, stride, padding)
+            dw = dw.permute(0, 2, 1).reshape(cout, cin, *ks).to(weight.dtype)
+        if has_bias and ctx.needs_input_grad[2]:
+            db = ops.colsum_tokens(dyb).to(bdt)
+        return dx, dw, db, None, None, None, None
+
+
+def conv_strided_tokens(x_tok, weight, bias, batch: int, spatial: Sequence[int], stride, padding):
+    """-> (token rows [rows_out, Cout], output spatial shape)."""
+    ks = tuple(weight.shape[2:])
+    y = _ConvStridedTokens.apply(x_tok, weight, bias, batch, tuple(spatial), tuple(stride), tuple(padding))
+    return y, _out_spatial(spatial, ks, stride, padding)
+
+
+class _ConvTransposeTokens(torch.autograd.Function):
+    """kernel == stride transposed convolution (decoder up-sampling, ED:273-276): every input voxel owns a disjoint
+    kd x kh x kw block of output voxels, so the forward is the strided data-gradient kernel (one tap per parity class), the
+    data gradient a strided convolution of dY and the weight gradient the strided weight-gradient kernel with the roles
+    of the operands exchanged.  weight: (Cin, Cout, *k) as nn.ConvTranspose stores it."""
+
+    @staticmethod
+    def forward(ctx, x, weight, bias, batch, spatial):
+        xb = ops.tma_ready_bf16(x)
+        cin, cout = weight.shape[:2]
+        ks = tuple(weight.shape[2:])
+        osp = tuple(n * k for n, k in zip(spatial, ks))
+        zero = (0,) * len(ks)
+        wt = ops.pack_conv_weight(weight.detach().transpose(0, 1))          # [Cout][tap][Cin pad]
+        y = ops.conv_strided_dgrad_bf16(xb, batch, spatial, cin, wt, cout, ks, ks, zero, osp, bias)
+        ctx.save_for_backward(xb, weight)
+        ctx.meta = (batch, tuple(spatial), osp, bias is not None, None if bias is None else bias.dtype)
+        return y[:, :cout]
+
+    @staticmethod
+    def backward(ctx, dy):
+        xb, weight = ctx.saved_tensors
+        batch, spatial, osp, has_bias, bdt = ctx.meta
+        cin, cout = weight.shape[:2]
+        ks = tuple(weight.shape[2:])
+        zero = (0,) * len(ks)
+        dyb = ops.tma_ready_bf16(dy)
+        dx = dw = db = None
+        if ctx.needs_input_grad[0]:
+            wp = ops.pack_conv_weight(weight.detach())                       # (Cin, Cout, k) read as a conv Cout -> Cin
+            dx, _ = ops.conv_strided_fwd_bf16(dyb, batch, osp, cout, wp, cin, ks, ks, zero, None)
+            dx = dx[:, :cin]
+        if ctx.needs_input_grad[1]:
+            dw = ops.conv_strided_wgrad_bf16(xb, dyb, batch, spatial, osp, cout, cin, ks, ks, zero)   # [Cin][tap][Cout]
+            dw = dw.permute(0, 2, 1).reshape(cin, cout, *ks).to(weight.dtype)
+        if has_bias and ctx.needs_input_grad[2]:
+            db = ops.colsum_tokens(dyb).to(bdt)
+        return dx, dw, db, None, None
+
+
+def conv_transpose_tokens(x_tok, weight, bias, batch: int, spatial: Sequence[int]):
+    """-> (token rows [rows_out, Cout], output spatial shape) of a kernel == stride transposed convolution."""
+    ks = tuple(weight.shape[2:])
+    y = _ConvTransposeTokens.apply(x_tok, weight, bias, batch, tuple(spatial))
+    return y, tuple(n * k for n, k in zip(spatial, ks))

@@ -567,12 +567,15 @@ def gemm_bf16_tn(a: torch.Tensor, b: torch.Tensor, bias: Optional[torch.Tensor] 
     return out
 
 
-def pack_conv_weight(w: torch.Tensor, transpose_flip: bool = False) -> torch.Tensor:
+def pack_conv_weight(w: torch.Tensor, transpose_flip: bool = False, transpose: bool = False) -> torch.Tensor:
     """(Cout, Cin, *k) conv weight -> bf16 [Cout, taps * cin_pad] (taps in (kd, kh, kw) order, Cin zero-padded to a
-    multiple of 64).  transpose_flip=True packs the data-gradient operator: [Cin, flipped taps * cout_pad]."""
+    multiple of 64).  transpose_flip=True packs the data-gradient operator of a stride-1 convolution: [Cin, flipped
+    taps * cout_pad]; transpose=True the un-flipped one the strided data-gradient kernel takes."""
     nd = w.dim() - 2
     if transpose_flip:
         w = w.transpose(0, 1).flip(dims=tuple(range(2, 2 + nd)))
+    elif transpose:
+        w = w.transpose(0, 1)
     co, ci = w.shape[:2]
     taps = 1
     for s in w.shape[2:]:
@@ -609,6 +612,83 @@ def conv_ndhwc_bf16(x_tok: torch.Tensor, batch: int, spatial: Sequence[int], cin
         check(fn(ptr(x_tok), ll(x_tok.stride(0)), batch, D, H, W, cin, ptr(wpack), cout, ks[0], ks[1], ks[2], ptr(bias32),
                  ptr(out), ll(out.stride(0)), dtype_code(out), cstream()), "nextou_conv3d_ndhwc_fwd")
     return out
+
+
+def _geom3(spatial, *lists):
+    """Left-pad spatial / kernel / stride / padding lists to 3-D."""
+    sp = list(spatial)
+    out = [list(v) for v in lists]
+    while len(sp) < 3:
+        sp = [1] + sp
+        out = [[1 if i < 2 else 0] + v for i, v in enumerate(out)]   # kernel 1, stride 1, padding 0
+    return (sp, *out)
+
+
+def conv_strided_fwd_bf16(x_tok: torch.Tensor, batch: int, spatial: Sequence[int], cin: int, wpack: torch.Tensor, cout: int,
+                          ksize: Sequence[int], stride: Sequence[int], padding: Sequence[int],
+                          bias: Optional[torch.Tensor] = None, out_dtype=torch.bfloat16):
+    """Strided convolution on a token-major bf16 volume -> (padded [rows_out, pad8(cout)] matrix, output spatial shape)."""
+    _need_cuda(x_tok, wpack)
+    assert x_tok.dtype == torch.bfloat16 and x_tok.stride(1) == 1 and wpack.dtype == torch.bfloat16
+    sp, ks, st, pd = _geom3(spatial, ksize, stride, padding)
+    osp = [(sp[i] + 2 * pd[i] - ks[i]) // st[i] + 1 for i in range(3)]
+    V = batch * osp[0] * osp[1] * osp[2]
+    out = torch.empty((V, pad8(cout)), device=x_tok.device, dtype=out_dtype)
+    bias32 = None if bias is None else bias.detach().float().contiguous()
+    taps = ks[0] * ks[1] * ks[2]
+    with _lib.timed("conv_pertap_tcgen05", 2 * batch * sp[0] * sp[1] * sp[2] * cin + 2 * V * cout + 2 * cin * cout * taps,
+                    2 * V * cin * cout * taps):
+        check(_lib.lib().nextou_conv3d_ndhwc_strided_fwd(ptr(x_tok), ll(x_tok.stride(0)), batch, *sp, cin, ptr(wpack), cout, *ks,
+                                                         *st, *pd, ptr(bias32), ptr(out), ll(out.stride(0)), dtype_code(out),
+                                                         cstream()), "nextou_conv3d_ndhwc_strided_fwd")
+    return out, tuple(osp[3 - len(spatial):])
+
+
+def conv_strided_dgrad_bf16(dy_tok: torch.Tensor, batch: int, out_spatial: Sequence[int], cout: int, wpack_t: torch.Tensor,
+                            cin: int, ksize: Sequence[int], stride: Sequence[int], padding: Sequence[int],
+                            in_spatial: Sequence[int], bias: Optional[torch.Tensor] = None, out_dtype=torch.bfloat16,
+                            out: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """Data gradient of a strided convolution / forward of a kernel == stride transposed convolution:
+    dy [rows_out, cout] on `out_spatial` -> padded [rows_in, pad8(cin)] on `in_spatial` (or written into `out`)."""
+    _need_cuda(dy_tok, wpack_t)
+    assert dy_tok.dtype == torch.bfloat16 and dy_tok.stride(1) == 1 and wpack_t.dtype == torch.bfloat16
+    osp, ks, st, pd = _geom3(out_spatial, ksize, stride, padding)
+    isp = list(in_spatial)
+    while len(isp) < 3:
+        isp = [1] + isp
+    V = batch * isp[0] * isp[1] * isp[2]
+    if out is None:
+        out = torch.empty((V, pad8(cin)), device=dy_tok.device, dtype=out_dtype)
+    bias32 = None if bias is None else bias.detach().float().contiguous()
+    taps = ks[0] * ks[1] * ks[2]
+    Vo = batch * osp[0] * osp[1] * osp[2]
+    with _lib.timed("conv_pertap_tcgen05", 2 * Vo * cout + 2 * V * cin + 2 * cin * cout * taps, 2 * Vo * cin * cout * taps):
+        check(_lib.lib().nextou_conv3d_ndhwc_strided_dgrad(ptr(dy_tok), ll(dy_tok.stride(0)), batch, *osp, cout, ptr(wpack_t), cin,
+                                                           *ks, *st, *pd, ptr(bias32), ptr(out), ll(out.stride(0)), *isp,
+                                                           dtype_code(out), cstream()), "nextou_conv3d_ndhwc_strided_dgrad")
+    return out
+
+
+def conv_strided_wgrad_bf16(dense_tok: torch.Tensor, strided_tok: torch.Tensor, batch: int, dense_spatial: Sequence[int],
+                            strided_spatial: Sequence[int], c_strided: int, c_dense: int, ksize: Sequence[int],
+                            stride: Sequence[int], padding: Sequence[int]) -> torch.Tensor:
+    """fp32 [c_dense, taps, c_strided] = sum_i dense[i][m] * strided[i*s + tap - pad][n] (csrc/gemm_tcgen05.cu)."""
+    _need_cuda(dense_tok, strided_tok)
+    assert dense_tok.dtype == torch.bfloat16 and strided_tok.dtype == torch.bfloat16
+    dsp, ks, st, pd = _geom3(dense_spatial, ksize, stride, padding)
+    ssp = list(strided_spatial)
+    while len(ssp) < 3:
+        ssp = [1] + ssp
+    taps = ks[0] * ks[1] * ks[2]
+    dw = torch.zeros((c_dense, taps, c_strided), device=dense_tok.device, dtype=torch.float32)
+    V = batch * dsp[0] * dsp[1] * dsp[2]
+    with _lib.timed("wgrad_tcgen05", 2 * V * c_dense + 2 * batch * ssp[0] * ssp[1] * ssp[2] * c_strided + 4 * c_dense * c_strided * taps,
+                    2 * V * c_dense * c_strided * taps):
+        check(_lib.lib().nextou_conv3d_ndhwc_strided_wgrad(ptr(dense_tok), ll(dense_tok.stride(0)), ptr(strided_tok),
+                                                           ll(strided_tok.stride(0)), batch, *dsp, *ssp, c_strided, c_dense, *ks,
+                                                           *st, *pd, ptr(dw), c_strided, cstream()),
+              "nextou_conv3d_ndhwc_strided_wgrad")
+    return dw
 
 
 def conv_wgrad_bf16(dy_tok: torch.Tensor, x_tok: torch.Tensor, batch: int, spatial: Sequence[int], cin: int, cout: int,

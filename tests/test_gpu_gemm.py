@@ -100,3 +100,86 @@ def test_conv_wgrad_mn_major(B, spatial, cin, cout, ks, halo):
     dw = ops.conv_wgrad_bf16(dt.to(DEV)[:, :cout], xt.to(DEV)[:, :cin], B, spatial, cin, cout, ks, halo=halo)
     assert dw.shape == w.shape and dw.dtype == torch.float32
     assert _rel(dw.cpu(), w.grad) < 1e-5, _rel(dw.cpu(), w.grad)
+
+
+def _tok_of(x, pad_nan=True):
+    from nextou_b200 import ops
+    B, C = x.shape[:2]
+    dim = x.dim() - 2
+    t = torch.full((B * x[0, 0].numel(), ops.pad8(C)), float("nan") if pad_nan else 0.0, dtype=torch.bfloat16)
+    t[:, :C] = x.permute(0, *range(2, 2 + dim), 1).reshape(-1, C)
+    return t
+
+
+def _vol_of(tok, B, C, spatial):
+    dim = len(spatial)
+    return tok.float().cpu()[:, :C].reshape(B, *spatial, C).permute(0, dim + 1, *range(1, dim + 1))
+
+
+@pytest.mark.parametrize("B,spatial,cin,cout,ks,stride", [
+    (1, (8, 16, 24), 33, 66, (3, 3, 3), (1, 2, 2)),      # enc s1 conv0
+    (1, (8, 12, 16), 66, 132, (3, 3, 3), (2, 2, 2)),     # enc s2
+    (2, (4, 14, 12), 264, 324, (3, 3, 3), (2, 2, 2)),    # enc s4 (batch 2)
+    (1, (8, 14, 12), 324, 324, (3, 3, 3), (2, 2, 2)),    # enc s5
+    (1, (6, 10, 14), 16, 40, (3, 3, 3), (2, 2, 2)),      # even, small channels
+    (1, (7, 9, 11), 24, 24, (3, 3, 3), (2, 2, 2)),       # odd extents
+    (2, (16, 20), 33, 66, (3, 3), (2, 2)),               # 2-D
+    (1, (8, 12, 12), 32, 32, (1, 1, 1), (2, 2, 2)),      # k < stride: parity classes without taps
+])
+def test_conv_strided_fwd_bwd(B, spatial, cin, cout, ks, stride):
+    """Strided convolution: forward, data gradient (parity classes) and weight gradient (strided X box) through the
+    autograd wrapper vs F.conv on the same bf16-valued operands."""
+    from nextou_b200 import native
+    g = torch.Generator().manual_seed(cin + 3 * cout)
+    dim = len(spatial)
+    pad = tuple((k - 1) // 2 for k in ks)
+    x = torch.randn(B, cin, *spatial, generator=g).bfloat16()
+    w = (torch.randn(cout, cin, *ks, generator=g) / (cin * 9) ** 0.5).bfloat16().float()
+    bias = torch.randn(cout, generator=g)
+    conv = F.conv3d if dim == 3 else F.conv2d
+    xr, wr, br = x.float().requires_grad_(True), w.clone().requires_grad_(True), bias.clone().requires_grad_(True)
+    want = conv(xr, wr, br, stride=stride, padding=pad)
+    dy = torch.randn(want.shape, generator=g).bfloat16()
+    want.backward(dy.float())
+
+    xt = _tok_of(x).to(DEV)[:, :cin].requires_grad_(True)
+    wd, bd = w.to(DEV).requires_grad_(True), bias.to(DEV).requires_grad_(True)
+    y, osp = native.conv_strided_tokens(xt, wd, bd, B, spatial, stride, pad)
+    assert tuple(osp) == tuple(want.shape[2:])
+    got = _vol_of(y.detach(), B, cout, osp)
+    assert _rel(got, want.detach()) < 6e-3, _rel(got, want.detach())                 # bf16 output rounding
+    y.backward(_tok_of(dy, pad_nan=False).to(DEV)[:, :cout])
+    gx = _vol_of(xt.grad, B, cin, spatial)
+    assert _rel(gx, xr.grad) < 6e-3, _rel(gx, xr.grad)
+    assert _rel(wd.grad.cpu(), wr.grad) < 1e-4, _rel(wd.grad.cpu(), wr.grad)
+    assert _rel(bd.grad.cpu(), br.grad) < 1e-4
+
+
+@pytest.mark.parametrize("B,spatial,cin,cout,ks", [
+    (1, (4, 7, 6), 324, 324, (2, 2, 2)), (1, (4, 14, 12), 324, 264, (2, 2, 2)), (2, (4, 6, 8), 264, 132, (2, 2, 2)),
+    (1, (8, 12, 16), 132, 66, (2, 2, 2)), (1, (8, 12, 16), 66, 33, (1, 2, 2)), (2, (10, 12), 66, 33, (2, 2))])
+def test_conv_transpose_fwd_bwd(B, spatial, cin, cout, ks):
+    """kernel == stride transposed convolution (decoder up-sampling) vs F.conv_transpose."""
+    from nextou_b200 import native
+    g = torch.Generator().manual_seed(cin + 5 * cout)
+    dim = len(spatial)
+    x = torch.randn(B, cin, *spatial, generator=g).bfloat16()
+    w = (torch.randn(cin, cout, *ks, generator=g) / cin ** 0.5).bfloat16().float()
+    bias = torch.randn(cout, generator=g)
+    convt = F.conv_transpose3d if dim == 3 else F.conv_transpose2d
+    xr, wr, br = x.float().requires_grad_(True), w.clone().requires_grad_(True), bias.clone().requires_grad_(True)
+    want = convt(xr, wr, br, stride=ks)
+    dy = torch.randn(want.shape, generator=g).bfloat16()
+    want.backward(dy.float())
+
+    xt = _tok_of(x).to(DEV)[:, :cin].requires_grad_(True)
+    wd, bd = w.to(DEV).requires_grad_(True), bias.to(DEV).requires_grad_(True)
+    y, osp = native.conv_transpose_tokens(xt, wd, bd, B, spatial)
+    assert tuple(osp) == tuple(want.shape[2:])
+    got = _vol_of(y.detach(), B, cout, osp)
+    assert _rel(got, want.detach()) < 6e-3, _rel(got, want.detach())
+    y.backward(_tok_of(dy, pad_nan=False).to(DEV)[:, :cout])
+    gx = _vol_of(xt.grad, B, cin, spatial)
+    assert _rel(gx, xr.grad) < 6e-3, _rel(gx, xr.grad)
+    assert _rel(wd.grad.cpu(), wr.grad) < 1e-4, _rel(wd.grad.cpu(), wr.grad)
+    assert _rel(bd.grad.cpu(), br.grad) < 1e-4
