@@ -198,6 +198,11 @@ int nextou_norm_apply(const void* x, int dtype, int C, long long rows, int insta
 int nextou_norm_bwd(const void* x, const void* dy, int dtype, int C, long long rows, int instances,
                     const float* mean, const float* invstd, const float* gamma, const float* beta, float slope,
                     float* partial, float* sums, void* dx, void* stream);
+/* Same, and additionally dx_colsum[inst][C] = sum_rows dx (as stored) when dx_colsum != NULL: the bias gradient of the
+ * convolution / linear layer that feeds this normalisation, for free while dx is written (`partial` is reused). */
+int nextou_norm_bwd_colsum(const void* x, const void* dy, int dtype, int C, long long rows, int instances,
+                           const float* mean, const float* invstd, const float* gamma, const float* beta, float slope,
+                           float* partial, float* sums, void* dx, float* dx_colsum, void* stream);
 /* column sums of a dense [rows][C] matrix: sums[0][C] = sum_r x, sums[1][C] = sum_r x^2 (fp32); `partial` as for
  * nextou_norm_stats with instances = 1.  Bias gradients of the 1x1 / spatial convolutions (d bias = colsum(dY)). */
 int nextou_colsum(const void* x, int dtype, int C, long long rows, float* partial, float* sums, void* stream);

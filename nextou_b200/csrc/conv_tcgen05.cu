@@ -47,6 +47,7 @@ struct ConvParams {
   long long ldc;
   int out_dtype;
   const float* bias;
+  int row32;             // every output row starts 32-byte aligned (256-bit stores)
   long long* dbg;        // optional [16] cycle counters written by CTA (0,0); NULL in production
 };
 
@@ -68,6 +69,30 @@ __device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
   asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
 
+// Issue the MMAs of NT consecutive in-plane taps of a 3x3 kernel (NT = 9: the whole plane, 3: one kernel row, 1: one tap)
+// x KS K16-steps with compile-time descriptor deltas: per MMA two 64-bit adds + the tcgen05.mma, nothing else.
+// adesc0 / bdesc0 = descriptors of the group's first tap at k = 0; bstep = one tap's weight tile in 16-byte units.
+template <int KS, int NT>
+__device__ __forceinline__ void issue_group_3x3(uint32_t tacc, uint64_t adesc0, uint64_t bdesc0, uint32_t bstep, uint32_t idesc,
+                                                uint32_t accum_first) {
+  constexpr int BOXW = CV_TW + 2;
+#pragma unroll
+  for (int j = 0; j < NT; ++j) {
+    const uint32_t aoff = (uint32_t)((j / 3) * BOXW + (j % 3)) * 8u;   // (kh * box_w + kw) rows of 128 B, in 16-byte units
+#pragma unroll
+    for (int k = 0; k < KS; ++k)
+      umma_f16(tacc, adesc0 + (uint64_t)(aoff + 2 * k), bdesc0 + (uint64_t)(j * bstep + 2 * k), idesc,
+               (j | k) != 0 ? 1u : accum_first);
+  }
+}
+template <int KS>
+__device__ __forceinline__ void issue_group_3x3_nt(int nt, uint32_t tacc, uint64_t adesc0, uint64_t bdesc0, uint32_t bstep,
+                                                   uint32_t idesc, uint32_t accum_first) {
+  if (nt == 9) issue_group_3x3<KS, 9>(tacc, adesc0, bdesc0, bstep, idesc, accum_first);
+  else if (nt == 3) issue_group_3x3<KS, 3>(tacc, adesc0, bdesc0, bstep, idesc, accum_first);
+  else issue_group_3x3<KS, 1>(tacc, adesc0, bdesc0, bstep, idesc, accum_first);
+}
+
 __global__ void __launch_bounds__(CV_THREADS, 1)
     conv_halo_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                              const ConvParams p) {
@@ -85,8 +110,10 @@ __global__ void __launch_bounds__(CV_THREADS, 1)
   uint64_t* tmem_empty = tmem_full + 2;        // [2]
   uint32_t* tmem_holder = reinterpret_cast<uint32_t*>(tmem_empty + 2);
 
+  __shared__ __align__(16) float sbias[256];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int n0 = blockIdx.y * p.block_n;
+  stage_bias(sbias, p.bias, n0, p.N, p.block_n);
 
   if (warp == 0 && lane == 0) {
     prefetch_tmap(&tmA);
@@ -161,6 +188,7 @@ __global__ void __launch_bounds__(CV_THREADS, 1)
       const uint32_t idesc = make_idesc_bf16(128, p.block_n);
       const uint32_t sbo = (uint32_t)p.box_w * 128;
       const int last_ksteps = (p.Cin - (p.kblocks - 1) * 64 + 15) / 16;   // K16 steps of the last (ragged) slab
+      const bool fast33 = p.kh == 3 && p.kw == 3 && (p.b_group == 9 || p.b_group == 3 || p.b_group == 1);
       int sa = 0, sb = 0;
       uint32_t pa = 0, pb = 0;
       int it = 0;
@@ -190,7 +218,20 @@ __global__ void __launch_bounds__(CV_THREADS, 1)
             if (dbg) w_b += clock64() - c0;
             tc_fence_after();
             const uint32_t bbase = smem_u32(smB + (size_t)sb * b_stage_bytes);
-            if (elect_one()) {
+            if (fast33) {
+              if (elect_one()) {
+                const uint64_t ad = make_kmajor_sw128_desc_rows(abase + (uint32_t)(kh_ * p.box_w + kw_) * 128, sbo);
+                const uint64_t bd = make_kmajor_sw128_desc(bbase);
+                const uint32_t bstep = (uint32_t)b_bytes >> 4;
+                switch (ksteps) {
+                  case 4: issue_group_3x3_nt<4>(nt, tacc, ad, bd, bstep, idesc, first_mma ^ 1u); break;
+                  case 3: issue_group_3x3_nt<3>(nt, tacc, ad, bd, bstep, idesc, first_mma ^ 1u); break;
+                  case 2: issue_group_3x3_nt<2>(nt, tacc, ad, bd, bstep, idesc, first_mma ^ 1u); break;
+                  default: issue_group_3x3_nt<1>(nt, tacc, ad, bd, bstep, idesc, first_mma ^ 1u); break;
+                }
+                if (!p.b_resident) umma_commit(&emptyB[sb]);
+              }
+            } else if (elect_one()) {
               int kh2 = kh_, kw2 = kw_;
               for (int j = 0; j < nt; ++j) {
                 const uint32_t astart = abase + (uint32_t)(kh2 * p.box_w + kw2) * 128;
@@ -242,6 +283,12 @@ __global__ void __launch_bounds__(CV_THREADS, 1)
       mbar_wait(&tmem_full[acc], (it >> 1) & 1);
       if (dbg) e_wait += clock64() - c0;
       tc_fence_after();
+      if (p.out_dtype == NEXTOU_BF16) {
+        __nv_bfloat16* dst = out_row >= 0 ? reinterpret_cast<__nv_bfloat16*>(p.C) + out_row * p.ldc + n0 : nullptr;
+        const long long left = p.ldc - n0;
+        epilogue_row_bf16(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * p.block_n), p.block_n, sbias, dst,
+                          (int)(left < p.block_n ? left : p.block_n), p.row32 != 0);
+      } else
       for (int c = 0; c < p.block_n; c += 16) {
         uint32_t raw[16];
         tmem_ld16(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * p.block_n + c), raw);
@@ -304,6 +351,7 @@ extern "C" int nextou_conv3d_ndhwc_halo_fwd(const void* x, long long ldx, int B,
   p.box_rows = p.box_w * (CV_TH + kh - 1);
   p.a_stage_bytes = (p.box_rows * 128 + 1023) / 1024 * 1024;
   p.C = out; p.ldc = ldo; p.out_dtype = out_dtype; p.bias = bias; p.dbg = g_conv_dbg;
+  p.row32 = (ldo % 16 == 0 && ((uintptr_t)out & 31) == 0) ? 1 : 0;
   const int taps = kd * kh * kw, inplane = kh * kw;
   const int cin_pad = p.kblocks * 64;
   const int b_bytes = p.block_n * 128;
@@ -459,6 +507,7 @@ __global__ void __launch_bounds__(WH_THREADS, 1)
     if (nb > 0) {
       const uint32_t idesc = make_idesc_bf16(128, p.n_tile) | (1u << 15) | (1u << 16);  // both operands MN-major
       const uint32_t sbo_x = (uint32_t)p.box_w * 128;
+      const bool fast33 = p.kh == 3 && p.kw == 3;
       int st = 0;
       uint32_t ph = 0;
       for (long long i = 0; i < nb; ++i) {
@@ -466,7 +515,24 @@ __global__ void __launch_bounds__(WH_THREADS, 1)
         tc_fence_after();
         const uint32_t sp = smem_u32(smem + (size_t)st * stage_bytes);
         const uint32_t xb = sp + 2 * 8192;
-        if (elect_one()) {
+        if (fast33) {
+          if (elect_one()) {
+            // compile-time descriptor deltas: tap (kh, kw) starts (kh*10 + kw) rows into the haloed box, a K16 step
+            // advances dY by 16 rows (2048 B) and X by two 8-voxel groups (2 box rows of 10 x 128 B)
+            const uint64_t ad0 = make_mnmajor_sw128_desc2(sp, 8192, 1024);
+            const uint64_t bd0 = make_mnmajor_sw128_desc2(xb, (uint32_t)p.xbox_bytes, 1280);
+            const uint32_t accum0 = i != 0 ? 1u : 0u;
+#pragma unroll
+            for (int tp = 0; tp < 9; ++tp) {
+              const uint32_t toff = (uint32_t)((tp / 3) * 10 + (tp % 3)) * 8u;
+#pragma unroll
+              for (int k = 0; k < 4; ++k)
+                umma_f16(tmem_base + (uint32_t)(tp * p.n_tile), ad0 + (uint64_t)(k * 128), bd0 + (uint64_t)(toff + k * 160), idesc,
+                         k != 0 ? 1u : accum0);
+            }
+            umma_commit(&empty_bar[st]);
+          }
+        } else if (elect_one()) {
           int kh_ = 0, kw_ = 0;
           for (int tp = 0; tp < inplane; ++tp) {
             const uint32_t xstart = xb + (uint32_t)(kh_ * p.box_w + kw_) * 128;

@@ -48,6 +48,7 @@ struct GemmParams {
   int Do, Ho, Wo;
   int last_ksteps;     // K16 steps of the last (ragged) 64-channel block
   int zero_fill;       // no taps at all: write bias / zeros
+  int row32;           // every output row starts 32-byte aligned (256-bit stores)
   signed char tap_dd[MAX_TAPS], tap_dh[MAX_TAPS], tap_dw[MAX_TAPS];
   short tap_wi[MAX_TAPS];
 };
@@ -67,8 +68,10 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1)
   uint64_t* tmem_full_bar = empty_bar + p.stages;
   uint32_t* tmem_base_holder = reinterpret_cast<uint32_t*>(tmem_full_bar + 1);
 
+  __shared__ __align__(16) float sbias[256];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int n0 = blockIdx.y * p.block_n;
+  stage_bias(sbias, p.bias, n0, p.N, p.block_n);
 
   // output brick of this CTA
   int m0 = blockIdx.x * GEMM_BM;  // plain GEMM: first row
@@ -162,6 +165,12 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1)
     } else if (m0 + r < p.M) {
       out_row = m0 + r;
     }
+    if (p.out_dtype == NEXTOU_BF16 && !p.zero_fill) {
+      __nv_bfloat16* dst = out_row >= 0 ? reinterpret_cast<__nv_bfloat16*>(p.C) + out_row * p.ldc + n0 : nullptr;
+      const long long left = p.ldc - n0;
+      epilogue_row_bf16(tmem_base + ((uint32_t)(q * 32) << 16), p.block_n, sbias, dst,
+                        (int)(left < p.block_n ? left : p.block_n), p.row32 != 0);
+    } else
     for (int c = 0; c < p.block_n; c += 16) {
       uint32_t raw[16];
       if (!p.zero_fill) {
@@ -200,6 +209,7 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1)
 static int launch_gemm(const CUtensorMap& tmA, const CUtensorMap& tmB, GemmParams& p, long long m_tiles, cudaStream_t st) {
   p.block_n = pick_block_n(p.N);
   p.tmem_cols = pow2_cols(p.block_n);
+  p.row32 = (p.ldc % 16 == 0 && ((uintptr_t)p.C & 31) == 0) ? 1 : 0;
   const int per_stage = GEMM_BM * GEMM_BK * 2 + p.block_n * GEMM_BK * 2;
   int stages = (200 * 1024) / per_stage;
   if (stages > 4) stages = 4;
@@ -247,6 +257,7 @@ struct PGemmParams {
   long long ldc;
   int out_dtype;
   const float* bias;
+  int row32;
 };
 
 __device__ __forceinline__ void mbar_arrive_cta(uint64_t* bar) {
@@ -270,8 +281,10 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1)
   uint64_t* tmem_empty = tmem_full + 2;   // [2]
   uint32_t* tmem_holder = reinterpret_cast<uint32_t*>(tmem_empty + 2);
 
+  __shared__ __align__(16) float sbias[256];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int n0 = blockIdx.y * p.block_n;
+  stage_bias(sbias, p.bias, n0, p.N, p.block_n);
 
   if (warp == 0 && lane == 0) {
     prefetch_tmap(&tmA);
@@ -342,6 +355,12 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1)
       const int acc = it & 1;
       mbar_wait(&tmem_full[acc], (it >> 1) & 1);
       tc_fence_after();
+      if (p.out_dtype == NEXTOU_BF16) {
+        __nv_bfloat16* dst = row < p.M ? reinterpret_cast<__nv_bfloat16*>(p.C) + row * p.ldc + n0 : nullptr;
+        const long long left = p.ldc - n0;
+        epilogue_row_bf16(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * p.block_n), p.block_n, sbias, dst,
+                          (int)(left < p.block_n ? left : p.block_n), p.row32 != 0);
+      } else
       for (int c = 0; c < p.block_n; c += 16) {
         uint32_t raw[16];
         tmem_ld16(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * p.block_n + c), raw);
@@ -391,6 +410,7 @@ extern "C" int nextou_gemm_bf16_tn(const void* A, long long lda, const void* B, 
   p.tmem_cols = pow2_cols(2 * p.block_n);
   p.m_tiles = (M + GEMM_BM - 1) / GEMM_BM;
   p.C = C; p.ldc = ldc; p.out_dtype = out_dtype; p.bias = bias;
+  p.row32 = (ldc % 16 == 0 && ((uintptr_t)C & 31) == 0) ? 1 : 0;
   const int a_bytes = GEMM_BM * GEMM_BK * 2, b_bytes = p.block_n * GEMM_BK * 2;
   const int budget = 200 * 1024;
   const long long bres = (long long)p.kblocks * b_bytes;

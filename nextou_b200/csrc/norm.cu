@@ -85,6 +85,19 @@ __device__ __forceinline__ void block_channel_reduce(float (&acc)[NV][2], int C,
   }
 }
 
+// one-value variant: acc[e] is this thread's partial for channel (NV*tid + e) % C.  Writes partial[blk][C].
+__device__ __forceinline__ void block_channel_reduce1(float (&acc)[NV], int C, int R, float* smem, float* __restrict__ out) {
+  const int tid = threadIdx.x;
+#pragma unroll
+  for (int e = 0; e < NV; ++e) smem[NV * tid + e] = acc[e];
+  __syncthreads();
+  for (int ch = tid; ch < C; ch += blockDim.x) {
+    float s = 0.f;
+    for (int r = 0; r < R; ++r) s += smem[ch + r * C];
+    out[ch] = s;
+  }
+}
+
 // grid (nblk, instances); block C*R/NV threads; dynamic smem 2*C*R floats
 template <typename T>
 __global__ void norm_stats_kernel(const T* __restrict__ x, int C, int R, long long rows, float* __restrict__ partial) {
@@ -108,13 +121,20 @@ __global__ void norm_stats_kernel(const T* __restrict__ x, int C, int R, long lo
 
 // Fixed-order fp64 sum of the CTA partial rows: block = 32 columns x FIN_SLICES slices; slice s adds rows s, s+8, ...
 // (independent loads in flight), then the slices are combined in order.  `cols` = row length of `partial`.
-constexpr int FIN_SLICES = 8;
+constexpr int FIN_SLICES = 32;   // 1024 threads: the finalize is a chain of L2-latency-bound loads, so spread the rows widely
 __device__ __forceinline__ double sliced_column_sum(const float* __restrict__ rows_base, int nblk, int cols, int col,
                                                     bool valid, double* sh) {
   const int lane = threadIdx.x & 31, slice = threadIdx.x >> 5;
   double s = 0.0;
   if (valid) {
     int b = slice;
+    for (; b + 7 * FIN_SLICES < nblk; b += 8 * FIN_SLICES) {
+      float v[8];
+#pragma unroll
+      for (int u = 0; u < 8; ++u) v[u] = rows_base[(long long)(b + u * FIN_SLICES) * cols + col];
+#pragma unroll
+      for (int u = 0; u < 8; ++u) s += (double)v[u];
+    }
     for (; b + 3 * FIN_SLICES < nblk; b += 4 * FIN_SLICES) {
       const float v0 = rows_base[(long long)b * cols + col];
       const float v1 = rows_base[(long long)(b + FIN_SLICES) * cols + col];
@@ -229,16 +249,17 @@ __global__ void norm_bwd_reduce_kernel(const T* __restrict__ x, const T* __restr
   block_channel_reduce(acc, C, R, smem, partial + ((long long)blockIdx.y * gridDim.x + blockIdx.x) * 2 * C);
 }
 
-// sums[inst][2][C] (fp32) from the CTA partials, fixed order, fp64 accumulation; grid (ceil(2C/32), instances)
+// sums[inst][cols] (fp32) from the CTA partial rows [inst][nblk][cols], fixed order, fp64 accumulation;
+// grid (ceil(cols/32), instances)
 __global__ void __launch_bounds__(32 * FIN_SLICES)
-    norm_bwd_finalize_kernel(const float* __restrict__ partial, int nblk, int C, int instances,
+    norm_bwd_finalize_kernel(const float* __restrict__ partial, int nblk, int cols, int instances,
                              float* __restrict__ sums) {
   __shared__ double sh[FIN_SLICES * 32];
   const int inst = blockIdx.y;
   const int c = blockIdx.x * 32 + (threadIdx.x & 31);
-  const bool valid = c < 2 * C;
-  const double s = sliced_column_sum(partial + (long long)inst * nblk * 2 * C, nblk, 2 * C, c, valid, sh);
-  if (valid && threadIdx.x < 32) sums[(long long)inst * 2 * C + c] = (float)s;
+  const bool valid = c < cols;
+  const double s = sliced_column_sum(partial + (long long)inst * nblk * cols, nblk, cols, c, valid, sh);
+  if (valid && threadIdx.x < 32) sums[(long long)inst * cols + c] = (float)s;
 }
 
 // backward pass 2: dx = gamma * invstd * (dy' - s1/n - xhat * s2/n)
@@ -246,7 +267,9 @@ template <typename T>
 __global__ void norm_bwd_apply_kernel(const T* __restrict__ x, const T* __restrict__ dy, int C, int R, long long rows,
                                       const float* __restrict__ mean, const float* __restrict__ invstd,
                                       const float* __restrict__ gamma, const float* __restrict__ beta, float slope,
-                                      const float* __restrict__ sums, T* __restrict__ dx) {
+                                      const float* __restrict__ sums, T* __restrict__ dx,
+                                      float* __restrict__ dx_partial) {
+  extern __shared__ float smem[];
   const long long total = rows * C;
   const T* xb = x + (long long)blockIdx.y * total;
   const T* db = dy + (long long)blockIdx.y * total;
@@ -264,6 +287,7 @@ __global__ void norm_bwd_apply_kernel(const T* __restrict__ x, const T* __restri
     m1[e] = sums[(long long)blockIdx.y * 2 * C + ch] * inv_n;
     m2[e] = sums[(long long)blockIdx.y * 2 * C + C + ch] * inv_n;
   }
+  float csum[NV] = {};
 #pragma unroll 2
   for (long long off = (long long)blockIdx.x * S + NV * threadIdx.x; off < total; off += (long long)gridDim.x * S) {
     float v[NV], d[NV];
@@ -274,9 +298,12 @@ __global__ void norm_bwd_apply_kernel(const T* __restrict__ x, const T* __restri
       const float xh = (v[e] - mu[e]) * is[e];
       const float dd = d[e] * lrelu_grad(fmaf(xh, g[e], b[e]), slope);
       v[e] = g[e] * is[e] * (dd - m1[e] - xh * m2[e]);
+      csum[e] += to_f(from_f<T>(v[e]));   // column sums of dx as stored (= bias gradient of the producing conv / linear)
     }
     store_guard(ob, off, total, v);
   }
+  if (dx_partial != nullptr)
+    block_channel_reduce1(csum, C, R, smem, dx_partial + ((long long)blockIdx.y * gridDim.x + blockIdx.x) * C);
 }
 
 // eval-mode affine: y = lrelu(x * scale[c] + shift[c])  (running statistics folded by the caller)
@@ -388,6 +415,13 @@ extern "C" int nextou_norm_apply(const void* x, int dtype, int C, long long rows
 extern "C" int nextou_norm_bwd(const void* x, const void* dy, int dtype, int C, long long rows, int instances,
                                const float* mean, const float* invstd, const float* gamma, const float* beta,
                                float slope, float* partial, float* sums, void* dx, void* stream) {
+  return nextou_norm_bwd_colsum(x, dy, dtype, C, rows, instances, mean, invstd, gamma, beta, slope, partial, sums, dx, nullptr,
+                                stream);
+}
+
+extern "C" int nextou_norm_bwd_colsum(const void* x, const void* dy, int dtype, int C, long long rows, int instances,
+                                      const float* mean, const float* invstd, const float* gamma, const float* beta,
+                                      float slope, float* partial, float* sums, void* dx, float* dx_colsum, void* stream) {
   NEXTOU_REQUIRE(x && dy && dx && mean && invstd && partial && sums, "norm_bwd: null pointer");
   SweepPlan p;
   int rc = plan_sweep(C, rows, instances, p);
@@ -402,13 +436,24 @@ extern "C" int nextou_norm_bwd(const void* x, const void* dy, int dtype, int C, 
   })
   rc = check_launch("norm_bwd_reduce_kernel");
   if (rc) return rc;
-  norm_bwd_finalize_kernel<<<dim3((2 * C + 31) / 32, instances), 32 * FIN_SLICES, 0, st>>>(partial, p.nblk, C,
+  norm_bwd_finalize_kernel<<<dim3((2 * C + 31) / 32, instances), 32 * FIN_SLICES, 0, st>>>(partial, p.nblk, 2 * C,
                                                                                               instances, sums);
   rc = check_launch("norm_bwd_finalize_kernel");
   if (rc) return rc;
-  DISPATCH_T(dtype, norm_bwd_apply_kernel<T><<<grid, p.threads, 0, st>>>((const T*)x, (const T*)dy, C, p.R, rows, mean,
-                                                                        invstd, gamma, beta, slope, sums, (T*)dx);)
-  return check_launch("norm_bwd_apply_kernel");
+  // the reduce pass is done with `partial`: reuse its first instances*nblk*C floats for the dx column sums
+  float* dx_partial = dx_colsum ? partial : nullptr;
+  const size_t smem2 = dx_colsum ? p.smem / 2 : 0;
+  DISPATCH_T(dtype, {
+    rc = ensure_smem(norm_bwd_apply_kernel<T>, smem2);
+    if (rc) return rc;
+    norm_bwd_apply_kernel<T><<<grid, p.threads, smem2, st>>>((const T*)x, (const T*)dy, C, p.R, rows, mean, invstd, gamma,
+                                                            beta, slope, sums, (T*)dx, dx_partial);
+  })
+  rc = check_launch("norm_bwd_apply_kernel");
+  if (rc || !dx_colsum) return rc;
+  norm_bwd_finalize_kernel<<<dim3((C + 31) / 32, instances), 32 * FIN_SLICES, 0, st>>>(partial, p.nblk, C, instances,
+                                                                                          dx_colsum);
+  return check_launch("norm_bwd_finalize_kernel");
 }
 
 extern "C" int nextou_affine_act(const void* x, int dtype, int C, long long rows, const float* scale,
@@ -438,6 +483,6 @@ extern "C" int nextou_colsum(const void* x, int dtype, int C, long long rows, fl
   })
   rc = check_launch("norm_stats_kernel");
   if (rc) return rc;
-  norm_bwd_finalize_kernel<<<dim3((2 * C + 31) / 32, 1), 32 * FIN_SLICES, 0, st>>>(partial, p.nblk, C, 1, sums);
+  norm_bwd_finalize_kernel<<<dim3((2 * C + 31) / 32, 1), 32 * FIN_SLICES, 0, st>>>(partial, p.nblk, 2 * C, 1, sums);
   return check_launch("norm_bwd_finalize_kernel");
 }

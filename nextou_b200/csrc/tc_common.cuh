@@ -174,6 +174,77 @@ __device__ __forceinline__ void store_chunk16(OutT* row_ptr, int col0, const flo
 }
 
 
+// ---- streamlined bf16 epilogue ---------------------------------------------------------------------
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&r)[32]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]), "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+      : "r"(taddr)
+      : "memory");
+}
+__device__ __forceinline__ void st_global_128(void* p, uint32_t a, uint32_t b, uint32_t c, uint32_t d) {
+  asm volatile("st.global.v4.b32 [%0], {%1, %2, %3, %4};" ::"l"(p), "r"(a), "r"(b), "r"(c), "r"(d) : "memory");
+}
+
+// The CTA's bias slice in shared memory: sbias[i] = bias[n0 + i] for n0 + i < N, else 0 (so padded columns come out as
+// exact zeros: their accumulators are zero because the weight rows beyond N are zero-filled by TMA).
+__device__ __forceinline__ void stage_bias(float* sbias, const float* bias, int n0, int N, int block_n) {
+  for (int i = threadIdx.x; i < block_n; i += blockDim.x) sbias[i] = (bias != nullptr && n0 + i < N) ? bias[n0 + i] : 0.f;
+}
+
+// bf16 epilogue of ONE accumulator row (this thread's TMEM lane): columns [0, block_n) of the CTA's N tile are read
+// 32 at a time, biased, rounded and stored with 128/256-bit stores.  All lanes must call it (the TMEM loads are
+// warp-collective); dst == nullptr skips the stores (row outside the volume).  ncols = number of columns that exist in
+// the output row from n0 on (min(block_n, ldc - n0), a multiple of 8); row32 = every row start is 32-byte aligned.
+template <int CHUNK>
+__device__ __forceinline__ void epilogue_store_chunk(const uint32_t* raw, const float* sb, __nv_bfloat16* dst, int c, int ncols,
+                                                     bool row32) {
+  uint32_t w[CHUNK / 2];
+#pragma unroll
+  for (int g = 0; g < CHUNK / 4; ++g) {
+    const float4 b4 = *reinterpret_cast<const float4*>(sb + c + 4 * g);
+    w[2 * g] = pack_bf16x2(__uint_as_float(raw[4 * g]) + b4.x, __uint_as_float(raw[4 * g + 1]) + b4.y);
+    w[2 * g + 1] = pack_bf16x2(__uint_as_float(raw[4 * g + 2]) + b4.z, __uint_as_float(raw[4 * g + 3]) + b4.w);
+  }
+  if (dst == nullptr) return;
+  if (c + CHUNK <= ncols) {
+    if (row32) {
+#pragma unroll
+      for (int g = 0; g < CHUNK / 16; ++g) {
+        uint32_t t[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) t[j] = w[8 * g + j];
+        st_global_256(dst + c + 16 * g, t);
+      }
+    } else {
+#pragma unroll
+      for (int g = 0; g < CHUNK / 8; ++g) st_global_128(dst + c + 8 * g, w[4 * g], w[4 * g + 1], w[4 * g + 2], w[4 * g + 3]);
+    }
+  } else {
+#pragma unroll
+    for (int g = 0; g < CHUNK / 8; ++g)
+      if (c + 8 * g + 8 <= ncols) st_global_128(dst + c + 8 * g, w[4 * g], w[4 * g + 1], w[4 * g + 2], w[4 * g + 3]);
+  }
+}
+
+__device__ __forceinline__ void epilogue_row_bf16(uint32_t tmem_row, int block_n, const float* sbias, __nv_bfloat16* dst,
+                                                  int ncols, bool row32) {
+  int c = 0;
+  for (; c + 32 <= block_n; c += 32) {
+    uint32_t raw[32];
+    tmem_ld32(tmem_row + (uint32_t)c, raw);
+    tmem_ld_wait();
+    epilogue_store_chunk<32>(raw, sbias, dst, c, ncols, row32);
+  }
+  if (c < block_n) {   // block_n is a multiple of 16
+    uint32_t raw[16];
+    tmem_ld16(tmem_row + (uint32_t)c, raw);
+    tmem_ld_wait();
+    epilogue_store_chunk<16>(raw, sbias, dst, c, ncols, row32);
+  }
+}
+
+
 // ---- host side: tensor maps -----------------------------------------------------------------------
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
                                   const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,

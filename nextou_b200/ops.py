@@ -753,6 +753,29 @@ def _norm_partial(C, rows, instances, device):
     return torch.empty(instances * nblk.value * 2 * C, device=device, dtype=torch.float32)
 
 
+class _DxColsum:
+    """Hand-over of the per-channel column sums that the normalisation backward computes while it writes dx, to the
+    backward of the producing convolution / linear layer, whose bias gradient they are.  Holds ONE entry (the most recent
+    normalisation backward) together with a reference to dx, so the address cannot be recycled while the entry is live."""
+    entry = None
+
+    @classmethod
+    def put(cls, dx_full, sums):
+        cls.entry = (dx_full, sums)
+
+    @classmethod
+    def take(cls, tok):
+        e, cls.entry = cls.entry, None
+        if e is None:
+            return None
+        dx, sums = e
+        if (tok.data_ptr() == dx.data_ptr() and tok.dtype == dx.dtype and tok.dim() == 2 and tok.shape[0] == dx.shape[0]
+                and tok.stride(0) == dx.stride(0) and tok.stride(1) == 1 and tok.shape[1] <= dx.shape[1]):
+            s = sums[0] if sums.shape[0] == 1 else sums.sum(0)
+            return s[:tok.shape[1]]
+        return None
+
+
 class _NormAct(torch.autograd.Function):
     """Train-mode normalisation with batch statistics + optional LeakyReLU (slope 1.0 = none)."""
 
@@ -792,12 +815,16 @@ class _NormAct(torch.autograd.Function):
         partial = _norm_partial(P, rows, instances, xf.device)
         sums = torch.empty(instances * 2 * P, device=xf.device, dtype=torch.float32)
         dx = torch.empty_like(xf)
-        check(_lib.lib().nextou_norm_bwd(ptr(xf), ptr(dyf), dtype_code(xf), P, ll(rows), instances, ptr(mean), ptr(invstd),
-                                         ptr(g32), ptr(b32), cf(slope), ptr(partial), ptr(sums), ptr(dx), cstream()),
-              "nextou_norm_bwd")
+        dxsum = torch.empty((instances, P), device=xf.device, dtype=torch.float32)
+        check(_lib.lib().nextou_norm_bwd_colsum(ptr(xf), ptr(dyf), dtype_code(xf), P, ll(rows), instances, ptr(mean),
+                                                ptr(invstd), ptr(g32), ptr(b32), cf(slope), ptr(partial), ptr(sums), ptr(dx),
+                                                ptr(dxsum), cstream()), "nextou_norm_bwd_colsum")
+        # the column sums of dx are the bias gradient of the layer that produced x: colsum_tokens() picks them up
+        _DxColsum.put(dx, dxsum)
         dgamma = dbeta = None
         if affine:
-            s = sums.view(instances, 2, P).sum(0)
+            s = sums.view(instances, 2, P)
+            s = s[0] if instances == 1 else s.sum(0)
             dbeta, dgamma = s[0, :C].to(pdt), s[1, :C].to(pdt)
         return dx[:, :C], dgamma, dbeta, None, None, None, None, None, None
 
@@ -864,7 +891,11 @@ def cat_tokens(a, b):
 
 
 def colsum_tokens(tok: torch.Tensor) -> torch.Tensor:
-    """fp32 [C] column sums of a [rows, C] token view (bias gradients), one streaming pass (csrc/norm.cu)."""
+    """fp32 [C] column sums of a [rows, C] token view (bias gradients): taken from the normalisation backward that just
+    wrote `tok` when there is one, else one streaming pass (csrc/norm.cu)."""
+    hit = _DxColsum.take(tok)
+    if hit is not None:
+        return hit
     xf, C = _physical_rows(tok)
     _need_cuda(xf)
     T, P = xf.shape
