@@ -71,6 +71,14 @@ int nextou_knn_normalize(const void* x, int x_dtype, long long ldx, long long x_
 int nextou_knn_topk(const float* xn, const float* sqx, int ldn, const float* yn, const float* sqy,
                     int ldm, const float* relpos, int B, int N, int M, int C, int k, int dilation,
                     int64_t* out_idx, int32_t* out_idx32, void* stream);
+/* Same with a caller-allocated workspace: when nextou_knn_topk_workspace_bytes(B, N, M) > 0 the candidates of the big
+ * cross-graph sites (Pool-GNN, N = 10752 / 1344 queries x M = 1344 candidates) are split over CTAs, each leaving a sorted
+ * partial list per query row in the workspace, merged by a second kernel (identical result: the order (distance, index)
+ * is total).  workspace == NULL falls back to the unsplit kernel. */
+size_t nextou_knn_topk_workspace_bytes(int B, int N, int M);
+int nextou_knn_topk_ws(const float* xn, const float* sqx, int ldn, const float* yn, const float* sqy, int ldm,
+                       const float* relpos, int B, int N, int M, int C, int k, int dilation, int64_t* out_idx,
+                       int32_t* out_idx32, void* workspace, size_t workspace_bytes, void* stream);
 
 /* ------------------------------------------------------------------------------------------
  * Max-relative message passing.  Replaces MRConv.forward lines 401-409

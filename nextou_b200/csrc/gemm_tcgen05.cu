@@ -754,17 +754,14 @@ __global__ void __launch_bounds__(WG_THREADS, 1)
     tc_fence_after();
     const int q = warp & 3;
     const int co = m0 + q * 32 + lane;
+    const bool vec = (p.cin_stride & 3) == 0 && (reinterpret_cast<uintptr_t>(p.dW) & 15) == 0;
     for (int tp = 0; tp < ntaps; ++tp) {
       for (int c = 0; c < p.n_tile; c += 16) {
         uint32_t raw[16];
         tmem_ld16(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(tp * p.n_tile + c), raw);
         tmem_ld_wait();
-        if (co < p.Cout) {
-          float* dst = p.dW + ((long long)co * p.taps + (tap0 + tp)) * p.cin_stride + n0 + c;
-#pragma unroll
-          for (int j = 0; j < 16; ++j)
-            if (n0 + c + j < p.Cin) atomicAdd(dst + j, __uint_as_float(raw[j]));
-        }
+        if (co < p.Cout)   // columns in [Cin, cin_stride) receive exact zeros (X channels beyond Cin are zero-filled by TMA)
+          red_add_row16(p.dW + ((long long)co * p.taps + (tap0 + tp)) * p.cin_stride + n0 + c, raw, p.cin_stride - n0 - c, vec);
       }
     }
   }
@@ -820,7 +817,7 @@ extern "C" int nextou_conv3d_ndhwc_strided_wgrad(const void* dy, long long ldy, 
   p.tmem_cols = pow2_cols(tg * p.n_tile);
   const long long tiles = (long long)p.n_groups * p.n_mtiles * p.n_ntiles;
   long long ksplit = (2LL * num_sms() + tiles - 1) / tiles;
-  if (ksplit > p.total_bricks) ksplit = p.total_bricks;
+  if (ksplit > p.total_bricks / 24) ksplit = p.total_bricks / 24;   // >= 24 K blocks per CTA amortise prologue + reduction
   if (ksplit < 1) ksplit = 1;
   p.ksplit = (int)ksplit;
   p.stages = 2;   // small stages keep several CTAs resident per SM (measured better than a deeper ring here)

@@ -121,7 +121,8 @@ __global__ void __launch_bounds__(KnnCfg<BM, BN, TM, TN>::NT)
     knn_topk_kernel(const float* __restrict__ xn, const float* __restrict__ sqx, int ldn,
                     const float* __restrict__ yn, const float* __restrict__ sqy, int ldm,
                     const float* __restrict__ relpos, int N, int M, int C, int k, int dilation,
-                    int64_t* __restrict__ out, int32_t* __restrict__ out32) {
+                    int64_t* __restrict__ out, int32_t* __restrict__ out32, float* __restrict__ part_d,
+                    int* __restrict__ part_i) {
   using Cfg = KnnCfg<BM, BN, TM, TN>;
   constexpr int KC = KNN_KC, TX = Cfg::TX, TY = Cfg::TY, NT = Cfg::NT, DS = Cfg::DS;
   extern __shared__ __align__(16) float smem[];
@@ -145,7 +146,28 @@ __global__ void __launch_bounds__(KnnCfg<BM, BN, TM, TN>::NT)
     Li[t] = INT_MAX;
   }
 
-  for (int j0 = 0; j0 < M; j0 += BN) {
+  // candidate range of this CTA: gridDim.z > 1 splits the BN-wide chunks over CTAs, each of which leaves a sorted
+  // partial top-32 list per row in (part_d, part_i) for knn_merge_kernel
+  const int nchunks = (M + BN - 1) / BN;
+  const int cpz = (nchunks + gridDim.z - 1) / gridDim.z;
+  const int jbeg = blockIdx.z * cpz * BN;
+  const int jend = min(M, (int)(blockIdx.z + 1) * cpz * BN);
+  const bool split = gridDim.z > 1;
+
+  if (split && jbeg >= jend) {   // defensive: a CTA without candidates still owes the merge its (empty) lists
+    __syncthreads();
+    for (int t = tid; t < BM * 32; t += NT) {
+      const int gi = i0 + t / 32;
+      if (gi < N) {
+        const long long o = (((long long)b * N + gi) * gridDim.z + blockIdx.z) * 32 + (t & 31);
+        part_d[o] = Ld[t];
+        part_i[o] = Li[t];
+      }
+    }
+    return;
+  }
+
+  for (int j0 = jbeg; j0 < jend; j0 += BN) {
     float acc[TM][TN];
 #pragma unroll
     for (int i = 0; i < TM; ++i)
@@ -183,10 +205,15 @@ __global__ void __launch_bounds__(KnnCfg<BM, BN, TM, TN>::NT)
 #pragma unroll
       for (int kc = 0; kc < KC; ++kc) {
         float a[TM], bb[TN];
+        if constexpr (TM >= 4) {
 #pragma unroll
-        for (int g = 0; g < TM / 4; ++g) {
-          const float4 v = *reinterpret_cast<const float4*>(xs + kc * BM + g * 4 * TY + ty * 4);
-          a[g * 4 + 0] = v.x; a[g * 4 + 1] = v.y; a[g * 4 + 2] = v.z; a[g * 4 + 3] = v.w;
+          for (int g = 0; g < TM / 4; ++g) {
+            const float4 v = *reinterpret_cast<const float4*>(xs + kc * BM + g * 4 * TY + ty * 4);
+            a[g * 4 + 0] = v.x; a[g * 4 + 1] = v.y; a[g * 4 + 2] = v.z; a[g * 4 + 3] = v.w;
+          }
+        } else {
+#pragma unroll
+          for (int i = 0; i < TM; ++i) a[i] = xs[kc * BM + ty * TM + i];
         }
 #pragma unroll
         for (int g = 0; g < TN / 4; ++g) {
@@ -204,7 +231,7 @@ __global__ void __launch_bounds__(KnnCfg<BM, BN, TM, TN>::NT)
     // epilogue: distances -> shared tile
 #pragma unroll
     for (int i = 0; i < TM; ++i) {
-      const int row = (i / 4) * 4 * TY + ty * 4 + (i % 4);
+      const int row = TM >= 4 ? (i / 4) * 4 * TY + ty * 4 + (i % 4) : ty * TM + i;
       const int gi = i0 + row;
       const float sx = (gi < N) ? sqx[(long long)b * N + gi] : 0.f;
 #pragma unroll
@@ -226,55 +253,136 @@ __global__ void __launch_bounds__(KnnCfg<BM, BN, TM, TN>::NT)
     }
     __syncthreads();
 
-    // per-row running top-32 (one warp per row, rows strided over the warps)
-    for (int row = warp; row < BM; row += NT / 32) {
-      const int gi = i0 + row;
-      if (gi >= N) continue;
-      float td = Ld[row * 32 + lane];
-      int ti = Li[row * 32 + lane];
+    // per-row running top-32 (one FULL warp per row, rows strided over the full warps).  Only candidates that beat the
+    // current K-th best can change the answer: a few of them are inserted one by one into the sorted list held across
+    // the lanes (ballot -> position, shfl_up -> shift); many of them (the first chunks) take the bitonic sort + merge.
+    // Both paths keep the list sorted by the strict total order (distance, index), so the result is unique.
+    constexpr int NFULL = NT / 32;
+    if (warp < NFULL) {
+      for (int row = warp; row < BM; row += NFULL) {
+        const int gi = i0 + row;
+        if (gi >= N) continue;
+        float td = Ld[row * 32 + lane];
+        int ti = Li[row * 32 + lane];
 #pragma unroll 1
-      for (int s = 0; s < BN / 32; ++s) {
-        const int gj = j0 + s * 32 + lane;
-        float d = Ds[row * DS + s * 32 + lane];
-        int ci = gj;
-        if (gj >= M) {
-          d = __int_as_float(0x7f800000);
-          ci = INT_MAX;
+        for (int s = 0; s < (BN + 31) / 32; ++s) {
+          const int col = s * 32 + lane;
+          const int gj = j0 + col;
+          float d = __int_as_float(0x7f800000);
+          int ci = INT_MAX;
+          if (col < BN && gj < M) {
+            d = Ds[row * DS + col];
+            ci = gj;
+          }
+          const float thr_d = __shfl_sync(0xffffffffu, td, K - 1);
+          const int thr_i = __shfl_sync(0xffffffffu, ti, K - 1);
+          unsigned q = __ballot_sync(0xffffffffu, cand_less(d, ci, thr_d, thr_i));
+          if (q == 0u) continue;
+          if (__popc(q) > 10) {
+            bitonic_sort32(d, ci, lane);
+            const float rd = __shfl_sync(0xffffffffu, d, 31 - lane);
+            const int ri = __shfl_sync(0xffffffffu, ci, 31 - lane);
+            if (cand_less(rd, ri, td, ti)) {
+              td = rd;
+              ti = ri;
+            }
+            bitonic_merge32(td, ti, lane);
+          } else {
+            while (q) {
+              const int src = __ffs(q) - 1;
+              q &= q - 1;
+              const float cd = __shfl_sync(0xffffffffu, d, src);
+              const int cx = __shfl_sync(0xffffffffu, ci, src);
+              const unsigned m = __ballot_sync(0xffffffffu, cand_less(cd, cx, td, ti));
+              if (m == 0u) continue;
+              const int pos = __ffs(m) - 1;          // the list is sorted: lanes >= pos hold larger entries
+              const float ud = __shfl_up_sync(0xffffffffu, td, 1);
+              const int ui = __shfl_up_sync(0xffffffffu, ti, 1);
+              if (lane > pos) {
+                td = ud;
+                ti = ui;
+              } else if (lane == pos) {
+                td = cd;
+                ti = cx;
+              }
+            }
+          }
         }
-        const float thr = __shfl_sync(0xffffffffu, td, K - 1);
-        if (!__any_sync(0xffffffffu, d < thr)) continue;
-        bitonic_sort32(d, ci, lane);
-        const float rd = __shfl_sync(0xffffffffu, d, 31 - lane);
-        const int ri = __shfl_sync(0xffffffffu, ci, 31 - lane);
-        if (cand_less(rd, ri, td, ti)) {
-          td = rd;
-          ti = ri;
+        Ld[row * 32 + lane] = td;
+        Li[row * 32 + lane] = ti;
+        if (j0 + BN >= jend) {
+          if (split) {
+            const long long o = (((long long)b * N + gi) * gridDim.z + blockIdx.z) * 32 + lane;
+            part_d[o] = td;
+            part_i[o] = ti;
+          } else if (lane < K && (lane % dilation) == 0) {
+            const long long o = ((long long)b * N + gi) * k + lane / dilation;
+            out[o] = ti;
+            if (out32) out32[o] = ti;
+          }
         }
-        bitonic_merge32(td, ti, lane);
-      }
-      Ld[row * 32 + lane] = td;
-      Li[row * 32 + lane] = ti;
-      if (j0 + BN >= M && lane < K && (lane % dilation) == 0) {
-        const long long o = ((long long)b * N + gi) * k + lane / dilation;
-        out[o] = ti;
-        if (out32) out32[o] = ti;
       }
     }
     __syncthreads();
   }
 }
 
+// merges the `parts` sorted partial lists of each row (one warp per row) and writes the k*dilation best
+__global__ void __launch_bounds__(256) knn_merge_kernel(const float* __restrict__ part_d, const int* __restrict__ part_i,
+                                                        long long rows, int parts, int k, int dilation,
+                                                        int64_t* __restrict__ out, int32_t* __restrict__ out32) {
+  const int lane = threadIdx.x & 31;
+  const long long row = (long long)blockIdx.x * 8 + (threadIdx.x >> 5);
+  if (row >= rows) return;
+  const long long base = row * parts * 32;
+  float td = part_d[base + lane];
+  int ti = part_i[base + lane];
+  for (int z = 1; z < parts; ++z) {
+    const float rd = part_d[base + z * 32 + 31 - lane];   // the other list, reversed -> bitonic sequence of 64
+    const int ri = part_i[base + z * 32 + 31 - lane];
+    if (cand_less(rd, ri, td, ti)) {
+      td = rd;
+      ti = ri;
+    }
+    bitonic_merge32(td, ti, lane);
+  }
+  if (lane < k * dilation && (lane % dilation) == 0) {
+    const long long o = row * k + lane / dilation;
+    out[o] = ti;
+    if (out32) out32[o] = ti;
+  }
+}
+
 template <int BM, int BN, int TM, int TN>
 static int launch_topk(const float* xn, const float* sqx, int ldn, const float* yn, const float* sqy, int ldm,
                        const float* relpos, int B, int N, int M, int C, int k, int dilation, int64_t* out,
-                       int32_t* out32, cudaStream_t st) {
+                       int32_t* out32, cudaStream_t st, int msplit = 1, void* workspace = nullptr) {
   using Cfg = KnnCfg<BM, BN, TM, TN>;
   auto kern = knn_topk_kernel<BM, BN, TM, TN>;
   int rc = ensure_smem(kern, Cfg::smem_bytes);
   if (rc) return rc;
-  dim3 grid((N + BM - 1) / BM, B);
-  kern<<<grid, Cfg::NT, Cfg::smem_bytes, st>>>(xn, sqx, ldn, yn, sqy, ldm, relpos, N, M, C, k, dilation, out, out32);
-  return check_launch("knn_topk_kernel");
+  dim3 grid((N + BM - 1) / BM, B, msplit);
+  const long long rows = (long long)B * N;
+  float* part_d = reinterpret_cast<float*>(workspace);
+  int* part_i = reinterpret_cast<int*>(part_d + (msplit > 1 ? rows * msplit * 32 : 0));
+  kern<<<grid, Cfg::NT, Cfg::smem_bytes, st>>>(xn, sqx, ldn, yn, sqy, ldm, relpos, N, M, C, k, dilation, out, out32, part_d,
+                                               part_i);
+  rc = check_launch("knn_topk_kernel");
+  if (rc || msplit == 1) return rc;
+  knn_merge_kernel<<<(unsigned)((rows + 7) / 8), 256, 0, st>>>(part_d, part_i, rows, msplit, k, dilation, out, out32);
+  return check_launch("knn_merge_kernel");
+}
+
+// candidate-split plan of the big cross-graph sites: 128-row tiles, one or more 168-wide chunks per CTA
+static int knn_msplit(int B, int N, int M) {
+  if (M % 168 != 0 || N <= 168 || M < 2 * 168) return 1;
+  const long long row_tiles = (long long)((N + 127) / 128) * B;
+  const int nchunks = M / 168;
+  long long ms = (4LL * num_sms() + row_tiles - 1) / row_tiles;
+  if (ms > nchunks) ms = nchunks;
+  if (ms < 1) ms = 1;
+  const long long cpz = (nchunks + ms - 1) / ms;   // chunks per CTA; drop the CTAs that would be left without a chunk
+  return (int)((nchunks + cpz - 1) / cpz);
 }
 
 }  // namespace nextou
@@ -299,9 +407,20 @@ extern "C" int nextou_knn_normalize(const void* x, int x_dtype, long long ldx, l
   return check_launch("knn_normalize_kernel");
 }
 
+extern "C" size_t nextou_knn_topk_workspace_bytes(int B, int N, int M) {
+  const int ms = knn_msplit(B, N, M);
+  return ms > 1 ? (size_t)B * N * ms * 32 * 8 : 0;
+}
+
 extern "C" int nextou_knn_topk(const float* xn, const float* sqx, int ldn, const float* yn, const float* sqy, int ldm,
                                const float* relpos, int B, int N, int M, int C, int k, int dilation, int64_t* out_idx,
                                int32_t* out_idx32, void* stream) {
+  return nextou_knn_topk_ws(xn, sqx, ldn, yn, sqy, ldm, relpos, B, N, M, C, k, dilation, out_idx, out_idx32, nullptr, 0, stream);
+}
+
+extern "C" int nextou_knn_topk_ws(const float* xn, const float* sqx, int ldn, const float* yn, const float* sqy, int ldm,
+                                  const float* relpos, int B, int N, int M, int C, int k, int dilation, int64_t* out_idx,
+                                  int32_t* out_idx32, void* workspace, size_t workspace_bytes, void* stream) {
   NEXTOU_REQUIRE(xn && sqx && yn && sqy && out_idx, "knn_topk: null pointer");
   NEXTOU_REQUIRE(B > 0 && N > 0 && M > 0 && C > 0, "knn_topk: bad shape B=%d N=%d M=%d C=%d", B, N, M, C);
   NEXTOU_REQUIRE(B <= 65535, "knn_topk: B=%d > 65535", B);
@@ -309,6 +428,17 @@ extern "C" int nextou_knn_topk(const float* xn, const float* sqx, int ldn, const
   NEXTOU_REQUIRE(k * dilation <= M, "knn_topk: k*dilation=%d > M=%d (topk would fail, TE:87)", k * dilation, M);
   NEXTOU_REQUIRE(ldn >= N && ldn % 4 == 0 && ldm >= M && ldm % 4 == 0, "knn_topk: ldn/ldm must be padded to 4");
   cudaStream_t st = (cudaStream_t)stream;
+  if (M % 168 == 0) {   // every NexToU site: windows of 4x7x6 = 168 tokens and their multiples -> exact-fit candidate chunks
+    if (N <= 168)   // windows: three 56-row tiles per window (measured faster than one 168 x 168 CTA with 8 x 8 register tiles)
+      return launch_topk<56, 168, 4, 8>(xn, sqx, ldn, yn, sqy, ldm, relpos, B, N, M, C, k, dilation, out_idx, out_idx32, st);
+    // cross-graph sites with many candidates: the per-(i, j) channel chain must stay sequential for bit-exactness, so the
+    // parallelism comes from splitting the CANDIDATES over CTAs (sorted partial lists, merged by knn_merge_kernel)
+    const int ms = knn_msplit(B, N, M);
+    if (ms > 1 && workspace != nullptr && workspace_bytes >= (size_t)B * N * ms * 32 * 8)
+      return launch_topk<128, 168, 8, 8>(xn, sqx, ldn, yn, sqy, ldm, relpos, B, N, M, C, k, dilation, out_idx, out_idx32, st, ms,
+                                         workspace);
+    return launch_topk<64, 168, 4, 8>(xn, sqx, ldn, yn, sqy, ldm, relpos, B, N, M, C, k, dilation, out_idx, out_idx32, st);
+  }
   const long long tiles128 = (long long)((N + 127) / 128) * B;
   if (tiles128 >= 2LL * num_sms())
     return launch_topk<128, 128, 8, 8>(xn, sqx, ldn, yn, sqy, ldm, relpos, B, N, M, C, k, dilation, out_idx, out_idx32, st);

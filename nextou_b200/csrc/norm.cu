@@ -106,7 +106,7 @@ __global__ void norm_stats_kernel(const T* __restrict__ x, int C, int R, long lo
   const T* base = x + (long long)blockIdx.y * total;
   const long long S = (long long)C * R;
   float acc[NV][2] = {};
-#pragma unroll 2
+#pragma unroll 4
   for (long long off = (long long)blockIdx.x * S + NV * threadIdx.x; off < total; off += (long long)gridDim.x * S) {
     float v[NV];
     load_guard(base, off, total, v);
@@ -359,6 +359,10 @@ static int plan_sweep(int C, long long rows, int instances, SweepPlan& p) {
   p.threads = C * R / NV;
   const long long sweeps = (rows + R - 1) / R;
   long long nblk = (8LL * num_sms() + instances - 1) / instances;   // 4 resident CTAs / SM x 2 waves
+  // small (L2-resident) tensors: fewer, fatter CTAs -> fewer partial rows for the latency-bound finalize (>= 16 sweeps each)
+  const long long fat = (sweeps + 15) / 16;
+  const long long floor_blk = (2LL * num_sms() + instances - 1) / instances;
+  if (nblk > fat) nblk = fat > floor_blk ? fat : floor_blk;
   if (nblk > sweeps) nblk = sweeps;
   if (nblk < 1) nblk = 1;
   p.nblk = (int)nblk;

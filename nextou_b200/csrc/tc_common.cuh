@@ -245,6 +245,26 @@ __device__ __forceinline__ void epilogue_row_bf16(uint32_t tmem_row, int block_n
 }
 
 
+// ---- split-K reduction of weight-gradient tiles: 16 consecutive fp32 columns of one row, vector reds when aligned ----
+__device__ __forceinline__ void red_add_v4(float* p, float a, float b, float c, float d) {
+  asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(p), "f"(a), "f"(b), "f"(c), "f"(d) : "memory");
+}
+// adds raw[0..16) to dst[0..16), limited to the first `avail` columns; vec = dst is 16-byte aligned
+__device__ __forceinline__ void red_add_row16(float* dst, const uint32_t (&raw)[16], int avail, bool vec) {
+#pragma unroll
+  for (int g = 0; g < 4; ++g) {
+    if (vec && 4 * g + 4 <= avail) {
+      red_add_v4(dst + 4 * g, __uint_as_float(raw[4 * g]), __uint_as_float(raw[4 * g + 1]), __uint_as_float(raw[4 * g + 2]),
+                 __uint_as_float(raw[4 * g + 3]));
+    } else {
+#pragma unroll
+      for (int j = 0; j < 4; ++j)
+        if (4 * g + j < avail) atomicAdd(dst + 4 * g + j, __uint_as_float(raw[4 * g + j]));
+    }
+  }
+}
+
+
 // ---- host side: tensor maps -----------------------------------------------------------------------
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
                                   const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,

@@ -207,9 +207,13 @@ def knn_topk(xn, sqx, yn=None, sqy=None, relpos: Optional[torch.Tensor] = None, 
     out32 = torch.empty((B, N, k), device=xn.device, dtype=torch.int32) if want_i32 else None
     # algorithmic traffic / work of this launch: operands once + relpos once + int64 indices
     nbytes = 4 * B * C * (N + (M if yn is not xn else 0)) + (4 * N * M if relpos is not None else 0) + 8 * B * N * k
+    L = _lib.lib()
+    L.nextou_knn_topk_workspace_bytes.restype = ctypes.c_size_t
+    ws_bytes = int(L.nextou_knn_topk_workspace_bytes(B, N, M))
+    ws = torch.empty(ws_bytes, device=xn.device, dtype=torch.uint8) if ws_bytes else None
     with _lib.timed("knn_topk", nbytes, 2 * B * N * M * C):
-        check(_lib.lib().nextou_knn_topk(ptr(xn), ptr(sqx), ldn, ptr(yn), ptr(sqy), ldm, ptr(relpos), B, N, M, C, k,
-                                         dilation, ptr(out), ptr(out32), cstream()), "nextou_knn_topk")
+        check(L.nextou_knn_topk_ws(ptr(xn), ptr(sqx), ldn, ptr(yn), ptr(sqy), ldm, ptr(relpos), B, N, M, C, k, dilation,
+                                   ptr(out), ptr(out32), ptr(ws), ctypes.c_size_t(ws_bytes), cstream()), "nextou_knn_topk_ws")
     return out, out32
 
 
@@ -680,15 +684,16 @@ def conv_strided_wgrad_bf16(dense_tok: torch.Tensor, strided_tok: torch.Tensor, 
     while len(ssp) < 3:
         ssp = [1] + ssp
     taps = ks[0] * ks[1] * ks[2]
-    dw = torch.zeros((c_dense, taps, c_strided), device=dense_tok.device, dtype=torch.float32)
+    cs = (c_strided + 3) // 4 * 4
+    dw = torch.zeros((c_dense, taps, cs), device=dense_tok.device, dtype=torch.float32)
     V = batch * dsp[0] * dsp[1] * dsp[2]
     with _lib.timed("wgrad_tcgen05", 2 * V * c_dense + 2 * batch * ssp[0] * ssp[1] * ssp[2] * c_strided + 4 * c_dense * c_strided * taps,
                     2 * V * c_dense * c_strided * taps):
         check(_lib.lib().nextou_conv3d_ndhwc_strided_wgrad(ptr(dense_tok), ll(dense_tok.stride(0)), ptr(strided_tok),
                                                            ll(strided_tok.stride(0)), batch, *dsp, *ssp, c_strided, c_dense, *ks,
-                                                           *st, *pd, ptr(dw), c_strided, cstream()),
+                                                           *st, *pd, ptr(dw), cs, cstream()),
               "nextou_conv3d_ndhwc_strided_wgrad")
-    return dw
+    return dw[:, :, :c_strided]
 
 
 def conv_wgrad_bf16(dy_tok: torch.Tensor, x_tok: torch.Tensor, batch: int, spatial: Sequence[int], cin: int, cout: int,
@@ -703,15 +708,16 @@ def conv_wgrad_bf16(dy_tok: torch.Tensor, x_tok: torch.Tensor, batch: int, spati
         sp, ks = [1] + sp, [1] + ks
     D, H, W = sp
     taps = ks[0] * ks[1] * ks[2]
-    dw = torch.zeros((cout, taps, cin), device=x_tok.device, dtype=torch.float32)
+    cs = (cin + 3) // 4 * 4                                     # 16-byte rows: the split-K reduction uses vector reds
+    dw = torch.zeros((cout, taps, cs), device=x_tok.device, dtype=torch.float32)
     use_halo = (CONV_HALO if halo is None else halo) and ks[1] in (1, 3) and ks[2] in (1, 3) and taps > 1
     fn = _lib.lib().nextou_conv3d_ndhwc_halo_wgrad if use_halo else _lib.lib().nextou_conv3d_ndhwc_wgrad
     V = batch * D * H * W
     with _lib.timed("wgrad_halo_tcgen05" if use_halo else "wgrad_tcgen05", 2 * V * (cin + cout) + 4 * cin * cout * taps,
                     2 * V * cin * cout * taps):
         check(fn(ptr(dy_tok), ll(dy_tok.stride(0)), ptr(x_tok), ll(x_tok.stride(0)), batch, D, H, W, cin, cout, ks[0], ks[1],
-                 ks[2], ptr(dw), cin, cstream()), "nextou_conv3d_ndhwc_wgrad")
-    return dw.permute(0, 2, 1).reshape(cout, cin, *ksize)
+                 ks[2], ptr(dw), cs, cstream()), "nextou_conv3d_ndhwc_wgrad")
+    return dw[:, :, :cin].permute(0, 2, 1).reshape(cout, cin, *ksize)
 
 
 # ----------------------------------------------------------------------------------------------

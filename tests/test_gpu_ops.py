@@ -59,8 +59,9 @@ def test_knn_reference_golden_tie_aware():
             assert torch.allclose(dm, dr, rtol=0, atol=1e-5), (name, b, i)
 
 
-@pytest.mark.parametrize("shape", [(1, 10752, 1344, 264, 28), (1, 10752, 168, 132, 14), (64, 168, 0, 264, 14)],
-                         ids=["pool_s3_full", "pool_s2_full", "swin_s3_full"])
+@pytest.mark.parametrize("shape", [(1, 10752, 1344, 264, 28), (1, 10752, 168, 132, 14), (64, 168, 0, 264, 14),
+                                   (128, 168, 0, 132, 7), (2, 1344, 1344, 324, 32)],
+                         ids=["pool_s3_full", "pool_s2_full", "swin_s3_full", "swin_s2_128win", "pool_s4_x2"])
 def test_knn_full_size_sites_bit_exact(shape):
     B, N, M, C, k = shape
     g = torch.Generator().manual_seed(5)

@@ -38,8 +38,57 @@ def timeit(fn, reps=5):
     return e0.elapsed_time(e1) / reps
 
 
+STRIDED = [  # (name, in spatial, cin, cout, ksize, stride)
+    ("enc s1 conv0", (64, 224, 192), 33, 66, (3, 3, 3), (1, 2, 2)),
+    ("enc s2 conv", (64, 112, 96), 66, 132, (3, 3, 3), (2, 2, 2)),
+    ("enc s3 conv", (32, 56, 48), 132, 264, (3, 3, 3), (2, 2, 2)),
+    ("enc s4 conv", (16, 28, 24), 264, 324, (3, 3, 3), (2, 2, 2)),
+    ("enc s5 conv", (8, 14, 12), 324, 324, (3, 3, 3), (2, 2, 2)),
+]
+TRANSP = [  # (name, in spatial, cin, cout, stride)
+    ("transp 0", (4, 7, 6), 324, 324, (2, 2, 2)), ("transp 1", (8, 14, 12), 324, 264, (2, 2, 2)),
+    ("transp 2", (16, 28, 24), 264, 132, (2, 2, 2)), ("transp 3", (32, 56, 48), 132, 66, (2, 2, 2)),
+    ("transp 4", (64, 112, 96), 66, 33, (1, 2, 2)),
+]
+
+
+def strided():
+    dev = "cuda"
+    print(f"{'layer':16s} {'fwd ms':>8s} {'dgrad ms':>9s} {'wgrad ms':>9s}   (strided convs)")
+    for name, sp, cin, cout, ks, st in STRIDED:
+        pad = tuple((k - 1) // 2 for k in ks)
+        osp = tuple((n + 2 * p - k) // s + 1 for n, k, s, p in zip(sp, ks, st, pad))
+        V, Vo = sp[0] * sp[1] * sp[2], osp[0] * osp[1] * osp[2]
+        x = torch.randn(V, ops.pad8(cin), device=dev).bfloat16()[:, :cin]
+        dy = torch.randn(Vo, ops.pad8(cout), device=dev).bfloat16()[:, :cout]
+        w = torch.randn(cout, cin, *ks, device=dev) * 0.05
+        wp, wt = ops.pack_conv_weight(w), ops.pack_conv_weight(w, transpose=True)
+        f = timeit(lambda: ops.conv_strided_fwd_bf16(x, 1, sp, cin, wp, cout, ks, st, pad))
+        d = timeit(lambda: ops.conv_strided_dgrad_bf16(dy, 1, osp, cout, wt, cin, ks, st, pad, sp))
+        g = timeit(lambda: ops.conv_strided_wgrad_bf16(dy, x, 1, osp, sp, cin, cout, ks, st, pad))
+        print(f"{name:16s} {f:8.3f} {d:9.3f} {g:9.3f}")
+    print(f"{'layer':16s} {'fwd ms':>8s} {'dgrad ms':>9s} {'wgrad ms':>9s}   (transposed convs)")
+    for name, sp, cin, cout, ks in TRANSP:
+        osp = tuple(n * k for n, k in zip(sp, ks))
+        V, Vo = sp[0] * sp[1] * sp[2], osp[0] * osp[1] * osp[2]
+        x = torch.randn(V, ops.pad8(cin), device=dev).bfloat16()[:, :cin]
+        dy = torch.randn(Vo, ops.pad8(cout), device=dev).bfloat16()[:, :cout]
+        w = torch.randn(cin, cout, *ks, device=dev) * 0.05
+        wt, wp = ops.pack_conv_weight(w.transpose(0, 1)), ops.pack_conv_weight(w)
+        zero = (0, 0, 0)
+        f = timeit(lambda: ops.conv_strided_dgrad_bf16(x, 1, sp, cin, wt, cout, ks, ks, zero, osp))
+        d = timeit(lambda: ops.conv_strided_fwd_bf16(dy, 1, osp, cout, wp, cin, ks, ks, zero))
+        g = timeit(lambda: ops.conv_strided_wgrad_bf16(x, dy, 1, sp, osp, cout, cin, ks, ks, zero))
+        print(f"{name:16s} {f:8.3f} {d:9.3f} {g:9.3f}")
+    print()
+
+
 def main(which="all"):
     dev = "cuda"
+    if which in ("all", "strided"):
+        strided()
+        if which == "strided":
+            return
     print(f"{'layer':16s} {'variant':8s} {'fwd ms':>8s} {'TF/s':>7s} {'dgrad ms':>9s} {'wgrad ms':>9s} {'TF/s':>7s}")
     for name, sp, cin, cout, ks in SHAPES:
         V = sp[0] * sp[1] * sp[2]

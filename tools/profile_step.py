@@ -22,7 +22,7 @@ def main():
     w = np.array([1 / (2 ** i) for i in range(5)]); w[-1] = 0
     loss_fn = DeepSupervisionWrapper(inner, (w / w.sum()).tolist())
     params = [p for p in model.parameters() if p.requires_grad]
-    opt = torch.optim.SGD(params, lr=1e-2, momentum=0.99, nesterov=True, weight_decay=3e-5)
+    opt = torch.optim.SGD(params, lr=1e-2, momentum=0.99, nesterov=True, weight_decay=3e-5, fused=True)
     x, t = bench.synthetic_batch(0)
     x = x.to(dev); t = [a.to(dev) for a in t]
     def step():
