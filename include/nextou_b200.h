@@ -197,6 +197,10 @@ int nextou_norm_plan(int C, long long rows, int instances, int* nblk_out);
 int nextou_norm_stats(const void* x, int dtype, int C, long long rows, int instances, float eps, float* partial,
                       float* mean, float* invstd, float* running_mean, float* running_var, float momentum,
                       void* stream);
+/* Same; additionally increments *num_batches_tracked (int64, device; may be NULL) like nn.BatchNorm does in training. */
+int nextou_norm_stats_tracked(const void* x, int dtype, int C, long long rows, int instances, float eps, float* partial,
+                              float* mean, float* invstd, float* running_mean, float* running_var, float momentum,
+                              long long* num_batches_tracked, void* stream);
 /* y = lrelu((x - mean) * invstd * gamma + beta, slope); gamma / beta [C] fp32 or NULL */
 int nextou_norm_apply(const void* x, int dtype, int C, long long rows, int instances, const float* mean,
                       const float* invstd, const float* gamma, const float* beta, float slope, void* y,
@@ -260,6 +264,14 @@ int nextou_conv3d_ndhwc_strided_dgrad(const void* dy, long long ldy, int B, int 
 int nextou_conv3d_ndhwc_strided_wgrad(const void* dy, long long ldy, const void* x, long long ldx, int B, int D, int H,
                                       int W, int Dx, int Hx, int Wx, int Cin, int Cout, int kd, int kh, int kw, int sd,
                                       int sh, int sw, int pd, int ph, int pw, float* dW, int cin_stride, void* stream);
+
+/* Weight packing (one launch per layer and step): master weight w[R][Cc/groups][taps] (fp32 | bf16; nn.Conv layout
+ * (Cout, Cin/groups, *k) or nn.ConvTranspose layout (Cin, Cout, *k)) ->
+ *   A [R][taps][lda_c]  bf16 = w[r][c][t]       (forward operand;       lda_c >= Cc, zero padded)
+ *   Bt[Cc][taps][ldb_c] bf16 = w[r][c][flip(t)] (data-gradient operand; ldb_c >= R,  zero padded; may be NULL)
+ * groups > 1 expands a grouped 1x1 convolution (torch_nn.py:85) to its block-diagonal dense operand. */
+int nextou_pack_weight(const void* w, int dtype, int R, int Cc, int taps, int groups, int flip_b, void* A, int lda_c,
+                       void* Bt, int ldb_c, void* stream);
 
 #ifdef __cplusplus
 }

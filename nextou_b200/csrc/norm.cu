@@ -160,9 +160,10 @@ __device__ __forceinline__ double sliced_column_sum(const float* __restrict__ ro
 __global__ void __launch_bounds__(32 * FIN_SLICES)
     norm_finalize_kernel(const float* __restrict__ partial, int nblk, int C, long long rows, int instances, float eps,
                          float* __restrict__ mean, float* __restrict__ invstd, float* __restrict__ running_mean,
-                         float* __restrict__ running_var, float momentum) {
+                         float* __restrict__ running_var, float momentum, long long* __restrict__ num_batches_tracked) {
   __shared__ double sh[FIN_SLICES * 32];
   const int inst = blockIdx.y;
+  if (num_batches_tracked != nullptr && blockIdx.x == 0 && blockIdx.y == 0 && threadIdx.x == 0) *num_batches_tracked += 1;
   const int c = blockIdx.x * 32 + (threadIdx.x & 31);
   const bool valid = c < C;
   const float* base = partial + (long long)inst * nblk * 2 * C;
@@ -385,6 +386,13 @@ extern "C" int nextou_norm_plan(int C, long long rows, int instances, int* nblk_
 extern "C" int nextou_norm_stats(const void* x, int dtype, int C, long long rows, int instances, float eps,
                                  float* partial, float* mean, float* invstd, float* running_mean, float* running_var,
                                  float momentum, void* stream) {
+  return nextou_norm_stats_tracked(x, dtype, C, rows, instances, eps, partial, mean, invstd, running_mean, running_var,
+                                   momentum, nullptr, stream);
+}
+
+extern "C" int nextou_norm_stats_tracked(const void* x, int dtype, int C, long long rows, int instances, float eps,
+                                         float* partial, float* mean, float* invstd, float* running_mean,
+                                         float* running_var, float momentum, long long* num_batches_tracked, void* stream) {
   NEXTOU_REQUIRE(x && partial && mean && invstd, "norm_stats: null pointer");
   SweepPlan p;
   int rc = plan_sweep(C, rows, instances, p);
@@ -399,7 +407,7 @@ extern "C" int nextou_norm_stats(const void* x, int dtype, int C, long long rows
   rc = check_launch("norm_stats_kernel");
   if (rc) return rc;
   norm_finalize_kernel<<<dim3((C + 31) / 32, instances), 32 * FIN_SLICES, 0, st>>>(
-      partial, p.nblk, C, rows, instances, eps, mean, invstd, running_mean, running_var, momentum);
+      partial, p.nblk, C, rows, instances, eps, mean, invstd, running_mean, running_var, momentum, num_batches_tracked);
   return check_launch("norm_finalize_kernel");
 }
 

@@ -215,3 +215,52 @@ extern "C" int nextou_maxunpool3d_bwd(const void* dout, int dtype, long long ldo
                         (const T*)dout, ldo, arg, Carg, C2, g, (T*)dg, ldg, total);)
   return check_launch("maxunpool_bwd_kernel");
 }
+
+// ------------------------------------------------------------------------------------------------------
+// Weight packing: one launch turns an fp32 / bf16 master weight w[R][Cc/groups][taps] (nn.Conv / nn.ConvTranspose layout,
+// taps = prod(kernel)) into BOTH bf16 operand packs the tcgen05 kernels take:
+//   A[r][t][c]  (row pitch taps*lda_c)  = w[r][c][t]          forward operand   ([Cout][taps][Cin pad])
+//   Bt[c][t'][r] (row pitch taps*ldb_c) = w[r][c][t]          data-gradient operand ([Cin][taps][Cout pad]), t' = flipped t
+// zero-filled where c >= Cc / r >= R (channel padding) and, for grouped layers, outside the diagonal blocks.
+// Replaces the reshape / permute / pad / cast / block_diag chains of ATen ops per layer and step.
+// ------------------------------------------------------------------------------------------------------
+namespace nextou {
+template <typename T>
+__global__ void pack_weight_kernel(const T* __restrict__ w, int R, int Cc, int taps, int groups, int flip_b,
+                                   __nv_bfloat16* __restrict__ A, int lda_c, __nv_bfloat16* __restrict__ Bt, int ldb_c) {
+  const long long na = (long long)R * taps * lda_c, nb = Bt ? (long long)Cc * taps * ldb_c : 0;
+  const int cpg = Cc / groups, rpg = R / groups;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < na + nb; i += (long long)gridDim.x * blockDim.x) {
+    int r, c, t;
+    if (i < na) {
+      c = (int)(i % lda_c);
+      t = (int)((i / lda_c) % taps);
+      r = (int)(i / ((long long)lda_c * taps));
+    } else {
+      const long long j = i - na;
+      r = (int)(j % ldb_c);
+      int tf = (int)((j / ldb_c) % taps);
+      t = flip_b ? taps - 1 - tf : tf;
+      c = (int)(j / ((long long)ldb_c * taps));
+    }
+    float v = 0.f;
+    if (r < R && c < Cc && (groups == 1 || c / cpg == r / rpg))
+      v = to_f(w[((long long)r * cpg + (groups == 1 ? c : c % cpg)) * taps + t]);
+    if (i < na) A[i] = __float2bfloat16_rn(v);
+    else Bt[i - na] = __float2bfloat16_rn(v);
+  }
+}
+}  // namespace nextou
+
+extern "C" int nextou_pack_weight(const void* w, int dtype, int R, int Cc, int taps, int groups, int flip_b, void* A, int lda_c,
+                                  void* Bt, int ldb_c, void* stream) {
+  NEXTOU_REQUIRE(w && A, "pack_weight: null pointer");
+  NEXTOU_REQUIRE(R > 0 && Cc > 0 && taps > 0 && groups > 0 && R % groups == 0 && Cc % groups == 0 && lda_c >= Cc &&
+                     (Bt == nullptr || ldb_c >= R), "pack_weight: bad shape");
+  const long long n = (long long)R * taps * lda_c + (Bt ? (long long)Cc * taps * ldb_c : 0);
+  long long blocks = (n + 255) / 256;
+  if (blocks > 4LL * num_sms()) blocks = 4LL * num_sms();
+  DISPATCH_T(dtype, pack_weight_kernel<T><<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(
+                        (const T*)w, R, Cc, taps, groups, flip_b, (__nv_bfloat16*)A, lda_c, (__nv_bfloat16*)Bt, ldb_c);)
+  return check_launch("pack_weight_kernel");
+}

@@ -285,6 +285,14 @@ inline EncodeTiledFn encode_fn() {
 inline int encode_bf16_map(CUtensorMap* map, const void* base, int rank, const cuuint64_t* dims,
                            const cuuint64_t* strides_bytes, const cuuint32_t* box, const char* what,
                            const cuuint32_t* elem_strides = nullptr) {
+  // cuTensorMapEncodeTiled is a DRIVER call: it needs the primary context to be current in the calling thread.  PyTorch's
+  // autograd worker threads only get one through their first runtime call, so bind it here once per thread.
+  static thread_local bool ctx_bound = false;
+  if (!ctx_bound) {
+    int dev = 0;
+    if (cudaGetDevice(&dev) == cudaSuccess) cudaSetDevice(dev);
+    ctx_bound = true;
+  }
   EncodeTiledFn fn = encode_fn();
   if (!fn) {
     set_error("cuTensorMapEncodeTiled entry point unavailable");

@@ -114,13 +114,16 @@ def batch_norm_tokens(tok: torch.Tensor, bn: torch.nn.modules.batchnorm._BatchNo
     use_batch_stats = bn.training or bn.running_mean is None
     if use_batch_stats:
         stats["native.batch_norm"] += 1
-        rm = rv = None
+        rm = rv = nbt = None
         momentum = 0.0
         if bn.training and bn.track_running_stats and bn.running_mean is not None:
             rm, rv = bn.running_mean, bn.running_var
-            bn.num_batches_tracked.add_(1)
-            momentum = bn.momentum if bn.momentum is not None else 1.0 / float(bn.num_batches_tracked)
-        return ops.norm_act_tokens(tok, bn.weight, bn.bias, rm, rv, momentum, bn.eps, slope, 1)
+            if bn.momentum is not None:
+                momentum, nbt = bn.momentum, bn.num_batches_tracked      # counter incremented by the statistics kernel
+            else:                                                        # cumulative average: the factor is needed on the host
+                bn.num_batches_tracked.add_(1)
+                momentum = 1.0 / float(bn.num_batches_tracked)
+        return ops.norm_act_tokens(tok, bn.weight, bn.bias, rm, rv, momentum, bn.eps, slope, 1, nbt)
     stats["native.affine_act"] += 1
     inv = torch.rsqrt(bn.running_var.float() + bn.eps)
     scale = inv if bn.weight is None else inv * bn.weight.float()

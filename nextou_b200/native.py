@@ -22,12 +22,17 @@ class _LinearTokens(torch.autograd.Function):
     """y[T, N] = x[T, K] @ w2d[N, K]^T + b  with w2d an fp32 / bf16 master weight."""
 
     @staticmethod
-    def forward(ctx, x, w2d, bias):
+    def forward(ctx, x, w2d, bias, groups=1):
         xb = ops.tma_ready_bf16(x)
-        N, K = w2d.shape
-        wp = ops.tma_ready_bf16(w2d.detach())                   # [N, K] bf16 (padded pitch)
-        y = ops.gemm_bf16_tn(xb, wp, bias, n=N)[:, :N]
+        N = w2d.shape[0]
+        K = w2d.shape[1] * groups
+        # one launch packs the forward operand [N, K] and the data-gradient operand [K, N] (bf16, padded pitches); a grouped
+        # layer (TN:85) becomes the block-diagonal dense operand, which keeps the output token-major without a permute
+        wp, wt = ops.pack_weight_pair(w2d, conv=False, groups=groups, want_b=ctx.needs_input_grad[0])
+        y = ops.gemm_bf16_tn(xb, wp[:, :K], bias, n=N)[:, :N]
         ctx.save_for_backward(xb, w2d)
+        ctx.wt = wt
+        ctx.groups = groups
         ctx.has_bias = bias is not None
         ctx.bias_dtype = None if bias is None else bias.dtype
         return y
@@ -35,18 +40,22 @@ class _LinearTokens(torch.autograd.Function):
     @staticmethod
     def backward(ctx, dy):
         xb, w2d = ctx.saved_tensors
-        N, K = w2d.shape
+        g = ctx.groups
+        N = w2d.shape[0]
+        K = w2d.shape[1] * g
         dyb = ops.tma_ready_bf16(dy)
         dx = dw = db = None
         if ctx.needs_input_grad[0]:
-            wt = ops.tma_ready_bf16(w2d.detach().t())            # [K, N] bf16: B operand of dX = dY W
-            dx = ops.gemm_bf16_tn(dyb, wt, None, n=K)[:, :K]
+            dx = ops.gemm_bf16_tn(dyb, ctx.wt[:, :N], None, n=K)[:, :K]          # dX = dY W
         if ctx.needs_input_grad[1]:
             # dW = dY^T X through the MN-major tcgen05 weight-gradient kernel (a 1x1 "convolution" over T voxels)
-            dw = ops.conv_wgrad_bf16(dyb, xb, 1, (xb.shape[0],), K, N, (1,)).reshape(N, K).to(w2d.dtype)
+            dw = ops.conv_wgrad_bf16(dyb, xb, 1, (xb.shape[0],), K, N, (1,)).reshape(N, K)
+            if g > 1:   # diagonal blocks of the dense gradient -> (Cout, Cin / groups)
+                dw = dw.view(g, N // g, g, K // g).diagonal(dim1=0, dim2=2).permute(2, 0, 1).reshape(N, K // g)
+            dw = dw.to(w2d.dtype)
         if ctx.has_bias and ctx.needs_input_grad[2]:
             db = ops.colsum_tokens(dyb).to(ctx.bias_dtype)
-        return dx, dw, db
+        return dx, dw, db, None
 
 
 def linear_tokens(x_tok: torch.Tensor, weight: torch.Tensor, bias: Optional[torch.Tensor]) -> torch.Tensor:
@@ -56,8 +65,7 @@ def linear_tokens(x_tok: torch.Tensor, weight: torch.Tensor, bias: Optional[torc
 
 def grouped_linear_tokens(x_tok: torch.Tensor, weight: torch.Tensor, bias: Optional[torch.Tensor], groups: int):
     """Grouped 1x1 convolution: the groups are the diagonal blocks of one [Cout, Cin] operand (TN:85)."""
-    w = weight.reshape(groups, weight.shape[0] // groups, -1)
-    return _LinearTokens.apply(x_tok, torch.block_diag(*w.unbind(0)), bias)
+    return _LinearTokens.apply(x_tok, weight.reshape(weight.shape[0], -1), bias, groups)
 
 
 class _ConvTokens(torch.autograd.Function):
@@ -68,8 +76,10 @@ class _ConvTokens(torch.autograd.Function):
         xb = ops.tma_ready_bf16(x)
         cout, cin = weight.shape[:2]
         ks = tuple(weight.shape[2:])
-        y = ops.conv_ndhwc_bf16(xb, batch, spatial, cin, ops.pack_conv_weight(weight.detach()), cout, ks, bias)[:, :cout]
+        wp, wt = ops.pack_weight_pair(weight, conv=True, flip_b=True, want_b=ctx.needs_input_grad[0])
+        y = ops.conv_ndhwc_bf16(xb, batch, spatial, cin, wp, cout, ks, bias)[:, :cout]
         ctx.save_for_backward(xb, weight)
+        ctx.wt = wt            # data-gradient operator: [Cin, flipped taps * cout_pad]
         ctx.meta = (batch, tuple(spatial), bias is not None, None if bias is None else bias.dtype)
         return y
 
@@ -82,8 +92,7 @@ class _ConvTokens(torch.autograd.Function):
         dyb = ops.tma_ready_bf16(dy)
         dx = dw = db = None
         if ctx.needs_input_grad[0]:
-            wpack_t = ops.pack_conv_weight(weight.detach(), transpose_flip=True)
-            dx = ops.conv_ndhwc_bf16(dyb, batch, spatial, cout, wpack_t, cin, ks, None)[:, :cin]
+            dx = ops.conv_ndhwc_bf16(dyb, batch, spatial, cout, ctx.wt, cin, ks, None)[:, :cin]
         if ctx.needs_input_grad[1]:
             dw = ops.conv_wgrad_bf16(dyb, xb, batch, spatial, cin, cout, ks)
             dw = dw.to(weight.dtype)
@@ -110,9 +119,10 @@ class _ConvStridedTokens(torch.autograd.Function):
         xb = ops.tma_ready_bf16(x)
         cout, cin = weight.shape[:2]
         ks = tuple(weight.shape[2:])
-        y, _ = ops.conv_strided_fwd_bf16(xb, batch, spatial, cin, ops.pack_conv_weight(weight.detach()), cout, ks, stride,
-                                         padding, bias)
+        wp, wt = ops.pack_weight_pair(weight, conv=True, flip_b=False, want_b=ctx.needs_input_grad[0])
+        y, _ = ops.conv_strided_fwd_bf16(xb, batch, spatial, cin, wp, cout, ks, stride, padding, bias)
         ctx.save_for_backward(xb, weight)
+        ctx.wt = wt
         ctx.meta = (batch, tuple(spatial), tuple(stride), tuple(padding), bias is not None, None if bias is None else bias.dtype)
         return y[:, :cout]
 
@@ -126,8 +136,7 @@ class _ConvStridedTokens(torch.autograd.Function):
         dyb = ops.tma_ready_bf16(dy)
         dx = dw = db = None
         if ctx.needs_input_grad[0]:
-            wt = ops.pack_conv_weight(weight.detach(), transpose=True)
-            dx = ops.conv_strided_dgrad_bf16(dyb, batch, osp, cout, wt, cin, ks, stride, padding, spatial)[:, :cin]
+            dx = ops.conv_strided_dgrad_bf16(dyb, batch, osp, cout, ctx.wt, cin, ks, stride, padding, spatial)[:, :cin]
         if ctx.needs_input_grad[1]:
             dw = ops.conv_strided_wgrad_bf16(dyb, xb, batch, osp, spatial, cin, cout, ks, stride, padding)
             dw = dw.permute(0, 2, 1).reshape(cout, cin, *ks).to(weight.dtype)
@@ -156,9 +165,11 @@ class _ConvTransposeTokens(torch.autograd.Function):
         ks = tuple(weight.shape[2:])
         osp = tuple(n * k for n, k in zip(spatial, ks))
         zero = (0,) * len(ks)
-        wt = ops.pack_conv_weight(weight.detach().transpose(0, 1))          # [Cout][tap][Cin pad]
-        y = ops.conv_strided_dgrad_bf16(xb, batch, spatial, cin, wt, cout, ks, ks, zero, osp, bias)
+        # A = [Cin][tap][Cout pad] (operand of the data gradient), Bt = [Cout][tap][Cin pad] (operand of the forward)
+        wa, wb = ops.pack_weight_pair(weight, conv=True, flip_b=False)
+        y = ops.conv_strided_dgrad_bf16(xb, batch, spatial, cin, wb, cout, ks, ks, zero, osp, bias)
         ctx.save_for_backward(xb, weight)
+        ctx.wa = wa
         ctx.meta = (batch, tuple(spatial), osp, bias is not None, None if bias is None else bias.dtype)
         return y[:, :cout]
 
@@ -172,8 +183,7 @@ class _ConvTransposeTokens(torch.autograd.Function):
         dyb = ops.tma_ready_bf16(dy)
         dx = dw = db = None
         if ctx.needs_input_grad[0]:
-            wp = ops.pack_conv_weight(weight.detach())                       # (Cin, Cout, k) read as a conv Cout -> Cin
-            dx, _ = ops.conv_strided_fwd_bf16(dyb, batch, osp, cout, wp, cin, ks, ks, zero, None)
+            dx, _ = ops.conv_strided_fwd_bf16(dyb, batch, osp, cout, ctx.wa, cin, ks, ks, zero, None)   # (Cin, Cout, k) as a conv
             dx = dx[:, :cin]
         if ctx.needs_input_grad[1]:
             dw = ops.conv_strided_wgrad_bf16(xb, dyb, batch, spatial, osp, cout, cin, ks, ks, zero)   # [Cin][tap][Cout]

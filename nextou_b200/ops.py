@@ -590,6 +590,26 @@ def pack_conv_weight(w: torch.Tensor, transpose_flip: bool = False, transpose: b
     return wp.reshape(co, taps * ci_pad).to(torch.bfloat16).contiguous()
 
 
+def pack_weight_pair(w: torch.Tensor, conv: bool, flip_b: bool = False, groups: int = 1, want_b: bool = True):
+    """Master weight (R, Cc/groups, *k) -> (A [R, taps*pa] bf16, Bt [Cc, taps*pb] bf16 | None) in ONE kernel launch
+    (csrc/pool.cu::pack_weight_kernel): A is the forward operand, Bt the data-gradient operand (taps flipped when
+    flip_b).  conv=True pads the channel axes to multiples of 64 (taps are concatenated along K), else to 8 (TMA pitch)."""
+    _need_cuda(w)
+    w = _work_dtype(w.detach()).contiguous()
+    R, cpg = w.shape[:2]
+    Cc = cpg * groups
+    taps = 1
+    for k in w.shape[2:]:
+        taps *= k
+    pad = (lambda c: (c + 63) // 64 * 64) if conv else pad8
+    pa, pb = pad(Cc), pad(R)
+    a = torch.empty((R, taps * pa), device=w.device, dtype=torch.bfloat16)
+    b = torch.empty((Cc, taps * pb), device=w.device, dtype=torch.bfloat16) if want_b else None
+    check(_lib.lib().nextou_pack_weight(ptr(w), dtype_code(w), R, Cc, taps, groups, int(flip_b), ptr(a), pa, ptr(b), pb,
+                                        cstream()), "nextou_pack_weight")
+    return a, b
+
+
 CONV_HALO = True  # use the halo-reuse kernel (csrc/conv_tcgen05.cu) whenever kh, kw are 1 or 3
 
 
@@ -786,7 +806,7 @@ class _NormAct(torch.autograd.Function):
     """Train-mode normalisation with batch statistics + optional LeakyReLU (slope 1.0 = none)."""
 
     @staticmethod
-    def forward(ctx, x, gamma, beta, running_mean, running_var, momentum, eps, slope, instances):
+    def forward(ctx, x, gamma, beta, running_mean, running_var, momentum, eps, slope, instances, tracked=None):
         xf, C = _physical_rows(x)
         _need_cuda(xf)
         T, P = xf.shape                      # P = physical row pitch >= C
@@ -800,9 +820,9 @@ class _NormAct(torch.autograd.Function):
         partial = _norm_partial(P, rows, instances, xf.device)
         mean = torch.empty(instances * P, device=xf.device, dtype=torch.float32)
         invstd = torch.empty_like(mean)
-        check(L.nextou_norm_stats(ptr(xf), dtype_code(xf), P, ll(rows), instances, cf(eps), ptr(partial), ptr(mean),
-                                  ptr(invstd), ptr(rm), ptr(rv), cf(momentum if momentum is not None else 0.0), cstream()),
-              "nextou_norm_stats")
+        check(L.nextou_norm_stats_tracked(ptr(xf), dtype_code(xf), P, ll(rows), instances, cf(eps), ptr(partial), ptr(mean),
+                                          ptr(invstd), ptr(rm), ptr(rv), cf(momentum if momentum is not None else 0.0),
+                                          ptr(tracked), cstream()), "nextou_norm_stats_tracked")
         if running_mean is not None and P != C:
             running_mean.copy_(rm[:C])
             running_var.copy_(rv[:C])
@@ -832,13 +852,17 @@ class _NormAct(torch.autograd.Function):
             s = sums.view(instances, 2, P)
             s = s[0] if instances == 1 else s.sum(0)
             dbeta, dgamma = s[0, :C].to(pdt), s[1, :C].to(pdt)
-        return dx[:, :C], dgamma, dbeta, None, None, None, None, None, None
+        return dx[:, :C], dgamma, dbeta, None, None, None, None, None, None, None
 
 
 def norm_act_tokens(x_tok, gamma, beta, running_mean=None, running_var=None, momentum=0.1, eps=1e-5, slope=1.0,
-                    instances=1):
-    """Batch norm (instances=1) / instance norm (instances=batch) with batch statistics, + LeakyReLU(slope)."""
-    return _NormAct.apply(x_tok, gamma, beta, running_mean, running_var, momentum, eps, float(slope), int(instances))
+                    instances=1, num_batches_tracked=None):
+    """Batch norm (instances=1) / instance norm (instances=batch) with batch statistics, + LeakyReLU(slope).
+    num_batches_tracked (int64 0-d CUDA tensor) is incremented by the statistics kernel."""
+    if num_batches_tracked is not None:
+        assert num_batches_tracked.dtype == torch.int64 and num_batches_tracked.is_cuda
+    return _NormAct.apply(x_tok, gamma, beta, running_mean, running_var, momentum, eps, float(slope), int(instances),
+                          num_batches_tracked)
 
 
 def affine_act_tokens(x_tok, scale, shift, slope=1.0):
