@@ -198,9 +198,14 @@ int nextou_norm_stats(const void* x, int dtype, int C, long long rows, int insta
                       float* mean, float* invstd, float* running_mean, float* running_var, float momentum,
                       void* stream);
 /* Same; additionally increments *num_batches_tracked (int64, device; may be NULL) like nn.BatchNorm does in training. */
-int nextou_norm_stats_tracked(const void* x, int dtype, int C, long long rows, int instances, float eps, float* partial,
-                              float* mean, float* invstd, float* running_mean, float* running_var, float momentum,
-                              long long* num_batches_tracked, void* stream);
+int nextou_norm_stats_tracked(const void* x, int dtype, int C, int c_valid, long long rows, int instances, float eps,
+                              float* partial, float* mean, float* invstd, float* running_mean, float* running_var,
+                              float momentum, long long* num_batches_tracked, void* stream);
+/* nextou_norm_apply with the per-channel vectors (gamma, beta) holding only c_valid <= C entries (C = physical pitch of the
+ * channel-padded rows; the padding lanes use gamma = 1, beta = 0).  Likewise c_valid in _stats_tracked (running_*) and
+ * _bwd_colsum: no padded copies of the module's parameters / buffers are needed. */
+int nextou_norm_apply_cv(const void* x, int dtype, int C, int c_valid, long long rows, int instances, const float* mean,
+                         const float* invstd, const float* gamma, const float* beta, float slope, void* y, void* stream);
 /* y = lrelu((x - mean) * invstd * gamma + beta, slope); gamma / beta [C] fp32 or NULL */
 int nextou_norm_apply(const void* x, int dtype, int C, long long rows, int instances, const float* mean,
                       const float* invstd, const float* gamma, const float* beta, float slope, void* y,
@@ -212,7 +217,7 @@ int nextou_norm_bwd(const void* x, const void* dy, int dtype, int C, long long r
                     float* partial, float* sums, void* dx, void* stream);
 /* Same, and additionally dx_colsum[inst][C] = sum_rows dx (as stored) when dx_colsum != NULL: the bias gradient of the
  * convolution / linear layer that feeds this normalisation, for free while dx is written (`partial` is reused). */
-int nextou_norm_bwd_colsum(const void* x, const void* dy, int dtype, int C, long long rows, int instances,
+int nextou_norm_bwd_colsum(const void* x, const void* dy, int dtype, int C, int c_valid, long long rows, int instances,
                            const float* mean, const float* invstd, const float* gamma, const float* beta, float slope,
                            float* partial, float* sums, void* dx, float* dx_colsum, void* stream);
 /* column sums of a dense [rows][C] matrix: sums[0][C] = sum_r x, sums[1][C] = sum_r x^2 (fp32); `partial` as for

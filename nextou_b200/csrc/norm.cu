@@ -160,7 +160,8 @@ __device__ __forceinline__ double sliced_column_sum(const float* __restrict__ ro
 __global__ void __launch_bounds__(32 * FIN_SLICES)
     norm_finalize_kernel(const float* __restrict__ partial, int nblk, int C, long long rows, int instances, float eps,
                          float* __restrict__ mean, float* __restrict__ invstd, float* __restrict__ running_mean,
-                         float* __restrict__ running_var, float momentum, long long* __restrict__ num_batches_tracked) {
+                         float* __restrict__ running_var, float momentum, long long* __restrict__ num_batches_tracked,
+                         int c_valid) {
   __shared__ double sh[FIN_SLICES * 32];
   const int inst = blockIdx.y;
   if (num_batches_tracked != nullptr && blockIdx.x == 0 && blockIdx.y == 0 && threadIdx.x == 0) *num_batches_tracked += 1;
@@ -176,7 +177,7 @@ __global__ void __launch_bounds__(32 * FIN_SLICES)
   if (var < 0.0) var = 0.0;
   mean[inst * C + c] = (float)m;
   invstd[inst * C + c] = (float)(1.0 / sqrt(var + (double)eps));
-  if (running_mean != nullptr && inst == 0) {  // batch norm: a single instance spans the whole batch
+  if (running_mean != nullptr && inst == 0 && c < c_valid) {  // batch norm: a single instance spans the whole batch
     const double unbiased = rows > 1 ? var * n / (n - 1.0) : var;
     running_mean[c] = (float)((1.0 - momentum) * (double)running_mean[c] + momentum * m);
     running_var[c] = (float)((1.0 - momentum) * (double)running_var[c] + momentum * unbiased);
@@ -187,7 +188,7 @@ __global__ void __launch_bounds__(32 * FIN_SLICES)
 template <typename T>
 __global__ void norm_apply_kernel(const T* __restrict__ x, int C, int R, long long rows, const float* __restrict__ mean,
                                   const float* __restrict__ invstd, const float* __restrict__ gamma,
-                                  const float* __restrict__ beta, float slope, T* __restrict__ y) {
+                                  const float* __restrict__ beta, float slope, T* __restrict__ y, int c_valid) {
   const long long total = rows * C;
   const T* base = x + (long long)blockIdx.y * total;
   T* obase = y + (long long)blockIdx.y * total;
@@ -196,7 +197,7 @@ __global__ void norm_apply_kernel(const T* __restrict__ x, int C, int R, long lo
 #pragma unroll
   for (int e = 0; e < NV; ++e) {
     const int ch = (NV * threadIdx.x + e) % C;
-    const float g = gamma ? gamma[ch] : 1.f, b = beta ? beta[ch] : 0.f;
+    const float g = (gamma && ch < c_valid) ? gamma[ch] : 1.f, b = (beta && ch < c_valid) ? beta[ch] : 0.f;
     sc[e] = invstd[blockIdx.y * C + ch] * g;
     sh[e] = b - mean[blockIdx.y * C + ch] * sc[e];
   }
@@ -218,7 +219,7 @@ template <typename T>
 __global__ void norm_bwd_reduce_kernel(const T* __restrict__ x, const T* __restrict__ dy, int C, int R, long long rows,
                                        const float* __restrict__ mean, const float* __restrict__ invstd,
                                        const float* __restrict__ gamma, const float* __restrict__ beta, float slope,
-                                       float* __restrict__ partial) {
+                                       float* __restrict__ partial, int c_valid) {
   extern __shared__ float smem[];
   const long long total = rows * C;
   const T* xb = x + (long long)blockIdx.y * total;
@@ -230,8 +231,8 @@ __global__ void norm_bwd_reduce_kernel(const T* __restrict__ x, const T* __restr
     const int ch = (NV * threadIdx.x + e) % C;
     mu[e] = mean[blockIdx.y * C + ch];
     is[e] = invstd[blockIdx.y * C + ch];
-    g[e] = gamma ? gamma[ch] : 1.f;
-    b[e] = beta ? beta[ch] : 0.f;
+    g[e] = (gamma && ch < c_valid) ? gamma[ch] : 1.f;
+    b[e] = (beta && ch < c_valid) ? beta[ch] : 0.f;
   }
   float acc[NV][2] = {};
 #pragma unroll 2
@@ -269,7 +270,7 @@ __global__ void norm_bwd_apply_kernel(const T* __restrict__ x, const T* __restri
                                       const float* __restrict__ mean, const float* __restrict__ invstd,
                                       const float* __restrict__ gamma, const float* __restrict__ beta, float slope,
                                       const float* __restrict__ sums, T* __restrict__ dx,
-                                      float* __restrict__ dx_partial) {
+                                      float* __restrict__ dx_partial, int c_valid) {
   extern __shared__ float smem[];
   const long long total = rows * C;
   const T* xb = x + (long long)blockIdx.y * total;
@@ -283,8 +284,8 @@ __global__ void norm_bwd_apply_kernel(const T* __restrict__ x, const T* __restri
     const int ch = (NV * threadIdx.x + e) % C;
     mu[e] = mean[blockIdx.y * C + ch];
     is[e] = invstd[blockIdx.y * C + ch];
-    g[e] = gamma ? gamma[ch] : 1.f;
-    b[e] = beta ? beta[ch] : 0.f;
+    g[e] = (gamma && ch < c_valid) ? gamma[ch] : 1.f;
+    b[e] = (beta && ch < c_valid) ? beta[ch] : 0.f;
     m1[e] = sums[(long long)blockIdx.y * 2 * C + ch] * inv_n;
     m2[e] = sums[(long long)blockIdx.y * 2 * C + C + ch] * inv_n;
   }
@@ -386,12 +387,12 @@ extern "C" int nextou_norm_plan(int C, long long rows, int instances, int* nblk_
 extern "C" int nextou_norm_stats(const void* x, int dtype, int C, long long rows, int instances, float eps,
                                  float* partial, float* mean, float* invstd, float* running_mean, float* running_var,
                                  float momentum, void* stream) {
-  return nextou_norm_stats_tracked(x, dtype, C, rows, instances, eps, partial, mean, invstd, running_mean, running_var,
+  return nextou_norm_stats_tracked(x, dtype, C, C, rows, instances, eps, partial, mean, invstd, running_mean, running_var,
                                    momentum, nullptr, stream);
 }
 
-extern "C" int nextou_norm_stats_tracked(const void* x, int dtype, int C, long long rows, int instances, float eps,
-                                         float* partial, float* mean, float* invstd, float* running_mean,
+extern "C" int nextou_norm_stats_tracked(const void* x, int dtype, int C, int c_valid, long long rows, int instances,
+                                         float eps, float* partial, float* mean, float* invstd, float* running_mean,
                                          float* running_var, float momentum, long long* num_batches_tracked, void* stream) {
   NEXTOU_REQUIRE(x && partial && mean && invstd, "norm_stats: null pointer");
   SweepPlan p;
@@ -407,33 +408,41 @@ extern "C" int nextou_norm_stats_tracked(const void* x, int dtype, int C, long l
   rc = check_launch("norm_stats_kernel");
   if (rc) return rc;
   norm_finalize_kernel<<<dim3((C + 31) / 32, instances), 32 * FIN_SLICES, 0, st>>>(
-      partial, p.nblk, C, rows, instances, eps, mean, invstd, running_mean, running_var, momentum, num_batches_tracked);
+      partial, p.nblk, C, rows, instances, eps, mean, invstd, running_mean, running_var, momentum, num_batches_tracked,
+      c_valid);
   return check_launch("norm_finalize_kernel");
 }
 
 extern "C" int nextou_norm_apply(const void* x, int dtype, int C, long long rows, int instances, const float* mean,
                                  const float* invstd, const float* gamma, const float* beta, float slope, void* y,
                                  void* stream) {
+  return nextou_norm_apply_cv(x, dtype, C, C, rows, instances, mean, invstd, gamma, beta, slope, y, stream);
+}
+
+extern "C" int nextou_norm_apply_cv(const void* x, int dtype, int C, int c_valid, long long rows, int instances,
+                                    const float* mean, const float* invstd, const float* gamma, const float* beta,
+                                    float slope, void* y, void* stream) {
   NEXTOU_REQUIRE(x && y && mean && invstd, "norm_apply: null pointer");
   SweepPlan p;
   int rc = plan_sweep(C, rows, instances, p);
   if (rc) return rc;
   dim3 grid(p.nblk, instances);
   DISPATCH_T(dtype, norm_apply_kernel<T><<<grid, p.threads, 0, (cudaStream_t)stream>>>(
-                        (const T*)x, C, p.R, rows, mean, invstd, gamma, beta, slope, (T*)y);)
+                        (const T*)x, C, p.R, rows, mean, invstd, gamma, beta, slope, (T*)y, c_valid);)
   return check_launch("norm_apply_kernel");
 }
 
 extern "C" int nextou_norm_bwd(const void* x, const void* dy, int dtype, int C, long long rows, int instances,
                                const float* mean, const float* invstd, const float* gamma, const float* beta,
                                float slope, float* partial, float* sums, void* dx, void* stream) {
-  return nextou_norm_bwd_colsum(x, dy, dtype, C, rows, instances, mean, invstd, gamma, beta, slope, partial, sums, dx, nullptr,
-                                stream);
+  return nextou_norm_bwd_colsum(x, dy, dtype, C, C, rows, instances, mean, invstd, gamma, beta, slope, partial, sums, dx,
+                                nullptr, stream);
 }
 
-extern "C" int nextou_norm_bwd_colsum(const void* x, const void* dy, int dtype, int C, long long rows, int instances,
-                                      const float* mean, const float* invstd, const float* gamma, const float* beta,
-                                      float slope, float* partial, float* sums, void* dx, float* dx_colsum, void* stream) {
+extern "C" int nextou_norm_bwd_colsum(const void* x, const void* dy, int dtype, int C, int c_valid, long long rows,
+                                      int instances, const float* mean, const float* invstd, const float* gamma,
+                                      const float* beta, float slope, float* partial, float* sums, void* dx,
+                                      float* dx_colsum, void* stream) {
   NEXTOU_REQUIRE(x && dy && dx && mean && invstd && partial && sums, "norm_bwd: null pointer");
   SweepPlan p;
   int rc = plan_sweep(C, rows, instances, p);
@@ -444,7 +453,7 @@ extern "C" int nextou_norm_bwd_colsum(const void* x, const void* dy, int dtype, 
     rc = ensure_smem(norm_bwd_reduce_kernel<T>, p.smem);
     if (rc) return rc;
     norm_bwd_reduce_kernel<T><<<grid, p.threads, p.smem, st>>>((const T*)x, (const T*)dy, C, p.R, rows, mean, invstd,
-                                                              gamma, beta, slope, partial);
+                                                              gamma, beta, slope, partial, c_valid);
   })
   rc = check_launch("norm_bwd_reduce_kernel");
   if (rc) return rc;
@@ -459,7 +468,7 @@ extern "C" int nextou_norm_bwd_colsum(const void* x, const void* dy, int dtype, 
     rc = ensure_smem(norm_bwd_apply_kernel<T>, smem2);
     if (rc) return rc;
     norm_bwd_apply_kernel<T><<<grid, p.threads, smem2, st>>>((const T*)x, (const T*)dy, C, p.R, rows, mean, invstd, gamma,
-                                                            beta, slope, sums, (T*)dx, dx_partial);
+                                                            beta, slope, sums, (T*)dx, dx_partial, c_valid);
   })
   rc = check_launch("norm_bwd_apply_kernel");
   if (rc || !dx_colsum) return rc;

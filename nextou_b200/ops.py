@@ -813,22 +813,21 @@ class _NormAct(torch.autograd.Function):
         rows = T // instances
         assert rows * instances == T
         L = _lib.lib()
-        g32, b32 = _pad_vec(gamma, P, 1.0), _pad_vec(beta, P, 0.0)
+        f32 = lambda v: None if v is None else v.detach().float().contiguous()   # no copy for fp32 parameters / buffers
+        g32, b32 = f32(gamma), f32(beta)
         rm = rv = None
         if running_mean is not None:
-            rm, rv = (running_mean, running_var) if P == C else (_pad_vec(running_mean, P, 0.0), _pad_vec(running_var, P, 1.0))
+            assert running_mean.dtype == torch.float32 and running_var.dtype == torch.float32
+            rm, rv = running_mean, running_var
         partial = _norm_partial(P, rows, instances, xf.device)
         mean = torch.empty(instances * P, device=xf.device, dtype=torch.float32)
         invstd = torch.empty_like(mean)
-        check(L.nextou_norm_stats_tracked(ptr(xf), dtype_code(xf), P, ll(rows), instances, cf(eps), ptr(partial), ptr(mean),
+        check(L.nextou_norm_stats_tracked(ptr(xf), dtype_code(xf), P, C, ll(rows), instances, cf(eps), ptr(partial), ptr(mean),
                                           ptr(invstd), ptr(rm), ptr(rv), cf(momentum if momentum is not None else 0.0),
                                           ptr(tracked), cstream()), "nextou_norm_stats_tracked")
-        if running_mean is not None and P != C:
-            running_mean.copy_(rm[:C])
-            running_var.copy_(rv[:C])
         y = torch.empty_like(xf)
-        check(L.nextou_norm_apply(ptr(xf), dtype_code(xf), P, ll(rows), instances, ptr(mean), ptr(invstd), ptr(g32), ptr(b32),
-                                  cf(slope), ptr(y), cstream()), "nextou_norm_apply")
+        check(L.nextou_norm_apply_cv(ptr(xf), dtype_code(xf), P, C, ll(rows), instances, ptr(mean), ptr(invstd), ptr(g32),
+                                     ptr(b32), cf(slope), ptr(y), cstream()), "nextou_norm_apply")
         ctx.save_for_backward(xf, mean, invstd, g32, b32)
         ctx.meta = (C, P, rows, instances, slope, gamma is not None, None if gamma is None else gamma.dtype)
         return y[:, :C]
@@ -842,7 +841,7 @@ class _NormAct(torch.autograd.Function):
         sums = torch.empty(instances * 2 * P, device=xf.device, dtype=torch.float32)
         dx = torch.empty_like(xf)
         dxsum = torch.empty((instances, P), device=xf.device, dtype=torch.float32)
-        check(_lib.lib().nextou_norm_bwd_colsum(ptr(xf), ptr(dyf), dtype_code(xf), P, ll(rows), instances, ptr(mean),
+        check(_lib.lib().nextou_norm_bwd_colsum(ptr(xf), ptr(dyf), dtype_code(xf), P, C, ll(rows), instances, ptr(mean),
                                                 ptr(invstd), ptr(g32), ptr(b32), cf(slope), ptr(partial), ptr(sums), ptr(dx),
                                                 ptr(dxsum), cstream()), "nextou_norm_bwd_colsum")
         # the column sums of dx are the bias gradient of the layer that produced x: colsum_tokens() picks them up
