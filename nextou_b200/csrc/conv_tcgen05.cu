@@ -430,6 +430,7 @@ struct WgradHaloParams {
   int n_tile, n_boxes;        // Cin tile per CTA (multiple of 16), 64-channel boxes it spans
   int box_w, xbox_bytes;      // haloed X box width (rows per H line) and its 1024-aligned size
   int n_mtiles, n_ntiles, ksplit, tmem_cols, stages;
+  int grp_rows, n_rgroups;    // kernel rows (kh) per CTA and number of such groups: a CTA owns grp_rows * kw in-plane taps
   long long total_bricks;
   float* dW;
   int cin_stride;
@@ -443,6 +444,20 @@ __device__ __forceinline__ uint64_t make_mnmajor_sw128_desc2(uint32_t smem_addr,
   d |= (uint64_t)1 << 46;
   d |= (uint64_t)2 << 61;
   return d;
+}
+
+// MMAs of NROWS kernel rows x 3 kernel columns x 4 K16-steps with compile-time descriptor deltas
+template <int NROWS>
+__device__ __forceinline__ void wgrad_issue_rows(uint32_t tmem_base, int n_tile, uint64_t ad0, uint64_t bd0, uint32_t idesc,
+                                                 uint32_t accum0) {
+#pragma unroll
+  for (int tp = 0; tp < 3 * NROWS; ++tp) {
+    const uint32_t toff = (uint32_t)((tp / 3) * 10 + (tp % 3)) * 8u;
+#pragma unroll
+    for (int k = 0; k < 4; ++k)
+      umma_f16(tmem_base + (uint32_t)(tp * n_tile), ad0 + (uint64_t)(k * 128), bd0 + (uint64_t)(toff + k * 160), idesc,
+               k != 0 ? 1u : accum0);
+  }
 }
 
 __global__ void __launch_bounds__(WH_THREADS, 1)
@@ -460,10 +475,13 @@ __global__ void __launch_bounds__(WH_THREADS, 1)
   int t = blockIdx.y;
   const int nt = t % p.n_ntiles; t /= p.n_ntiles;
   const int mt = t % p.n_mtiles; t /= p.n_mtiles;
+  const int rg = t % p.n_rgroups; t /= p.n_rgroups;
   const int kd_ = t;
   const int m0 = mt * 128, n0 = nt * p.n_tile;
   const int ks = blockIdx.x;
-  const int inplane = p.kh * p.kw;
+  const int r0 = rg * p.grp_rows;                          // first kernel row of this CTA
+  const int nrows = min(p.grp_rows, p.kh - r0);
+  const int inplane = nrows * p.kw;                        // in-plane taps of this CTA: rows r0 .. r0 + nrows - 1
 
   if (warp == 0 && lane == 0) {
     prefetch_tmap(&tmDY);
@@ -478,7 +496,7 @@ __global__ void __launch_bounds__(WH_THREADS, 1)
   tc_fence_after();
   const uint32_t tmem_base = *tmem_holder;
   const long long nb = p.total_bricks > ks ? (p.total_bricks - ks + p.ksplit - 1) / p.ksplit : 0;
-  const int box_rows = p.box_w * (8 + p.kh - 1);
+  const int box_rows = p.box_w * (8 + p.grp_rows - 1);   // the X box spans only the kernel rows of this group
 
   if (warp == 0) {
     if (lane == 0) {
@@ -497,7 +515,7 @@ __global__ void __launch_bounds__(WH_THREADS, 1)
         tma_load_5d(sp, &tmDY, &full_bar[st], m0, w0, h0, d0, bn);
         tma_load_5d(sp + 8192, &tmDY, &full_bar[st], m0 + 64, w0, h0, d0, bn);
         for (int j = 0; j < p.n_boxes; ++j)
-          tma_load_5d(sp + 2 * 8192 + (size_t)j * p.xbox_bytes, &tmX, &full_bar[st], n0 + 64 * j, w0 - p.pw, h0 - p.ph,
+          tma_load_5d(sp + 2 * 8192 + (size_t)j * p.xbox_bytes, &tmX, &full_bar[st], n0 + 64 * j, w0 - p.pw, h0 - p.ph + r0,
                       d0 + kd_ - p.pd, bn);
         if (++st == p.stages) { st = 0; ph ^= 1; }
       }
@@ -517,19 +535,14 @@ __global__ void __launch_bounds__(WH_THREADS, 1)
         const uint32_t xb = sp + 2 * 8192;
         if (fast33) {
           if (elect_one()) {
-            // compile-time descriptor deltas: tap (kh, kw) starts (kh*10 + kw) rows into the haloed box, a K16 step
+            // compile-time descriptor deltas: tap (r, kw) starts (r*10 + kw) rows into the haloed box, a K16 step
             // advances dY by 16 rows (2048 B) and X by two 8-voxel groups (2 box rows of 10 x 128 B)
             const uint64_t ad0 = make_mnmajor_sw128_desc2(sp, 8192, 1024);
             const uint64_t bd0 = make_mnmajor_sw128_desc2(xb, (uint32_t)p.xbox_bytes, 1280);
             const uint32_t accum0 = i != 0 ? 1u : 0u;
-#pragma unroll
-            for (int tp = 0; tp < 9; ++tp) {
-              const uint32_t toff = (uint32_t)((tp / 3) * 10 + (tp % 3)) * 8u;
-#pragma unroll
-              for (int k = 0; k < 4; ++k)
-                umma_f16(tmem_base + (uint32_t)(tp * p.n_tile), ad0 + (uint64_t)(k * 128), bd0 + (uint64_t)(toff + k * 160), idesc,
-                         k != 0 ? 1u : accum0);
-            }
+            if (nrows == 3) wgrad_issue_rows<3>(tmem_base, p.n_tile, ad0, bd0, idesc, accum0);
+            else if (nrows == 2) wgrad_issue_rows<2>(tmem_base, p.n_tile, ad0, bd0, idesc, accum0);
+            else wgrad_issue_rows<1>(tmem_base, p.n_tile, ad0, bd0, idesc, accum0);
             umma_commit(&empty_bar[st]);
           }
         } else if (elect_one()) {
@@ -559,13 +572,13 @@ __global__ void __launch_bounds__(WH_THREADS, 1)
     const int co = m0 + q * 32 + lane;
     const bool vec = (p.cin_stride & 3) == 0 && (reinterpret_cast<uintptr_t>(p.dW) & 15) == 0;
     for (int tp = 0; tp < inplane; ++tp) {
-      const int tap = kd_ * inplane + tp;
+      const int tap = kd_ * (p.kh * p.kw) + r0 * p.kw + tp;
       for (int c = 0; c < p.n_tile; c += 16) {
         uint32_t raw[16];
         tmem_ld16(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(tp * p.n_tile + c), raw);
         tmem_ld_wait();
         if (co < p.Cout)   // columns in [Cin, cin_stride) receive exact zeros (X channels beyond Cin are zero-filled by TMA)
-          red_add_row16(p.dW + ((long long)co * (p.kd * inplane) + tap) * p.cin_stride + n0 + c, raw, p.cin_stride - n0 - c, vec);
+          red_add_row16(p.dW + ((long long)co * (p.kd * p.kh * p.kw) + tap) * p.cin_stride + n0 + c, raw, p.cin_stride - n0 - c, vec);
       }
     }
   }
@@ -591,17 +604,37 @@ extern "C" int nextou_conv3d_ndhwc_halo_wgrad(const void* dy, long long ldy, con
   p.dW = dW; p.cin_stride = cin_stride;
   p.nh = (H + 7) / 8; p.nw = (W + 7) / 8;
   p.total_bricks = (long long)B * D * p.nh * p.nw;
-  const int inplane = kh * kw;
-  int max_n = (512 / inplane) / 16 * 16;   // every in-plane tap owns n_tile TMEM columns
+  // Every in-plane tap of a CTA owns n_tile fp32 columns of tensor memory (512 in all).  One MMA costs ~62 cycles up to
+  // N = 64 and grows slowly beyond (shared-memory operand reads), so the cheapest plan has the FEWEST Cin tiles: give a CTA
+  // fewer kernel rows (more tap groups, each re-reading dY) when that lets one wide tile cover Cin.
+  p.grp_rows = kh;
+  {
+    double best = 1e30;
+    for (int rows = kh; rows >= 1; --rows) {
+      if (rows != kh && !(kh == 3 && kw == 3)) break;           // row groups only on the unrolled 3x3 path
+      int max_n = (512 / (rows * kw)) / 16 * 16;
+      if (max_n > 256) max_n = 256;
+      if (max_n < 16) continue;
+      const int nt = (Cin + max_n - 1) / max_n;
+      const int ntile = ((Cin + nt - 1) / nt + 15) / 16 * 16;
+      const int groups = (kh + rows - 1) / rows;
+      const double mma = ntile <= 64 ? 62.0 : 44.0 + 0.2 * ntile + (ntile > 160 ? 0.3 * (ntile - 160) : 0.0);
+      const double cost = (double)nt * (kh * kw * 4 * mma + groups * 350.0);   // + per-iteration barrier / dY re-read cost
+      if (cost < best * 0.97) { best = cost; p.grp_rows = rows; }
+    }
+  }
+  p.n_rgroups = (kh + p.grp_rows - 1) / p.grp_rows;
+  const int inplane = p.grp_rows * kw;       // taps per CTA
+  int max_n = (512 / inplane) / 16 * 16;
   if (max_n > 256) max_n = 256;
   p.n_ntiles = (Cin + max_n - 1) / max_n;
   p.n_tile = ((Cin + p.n_ntiles - 1) / p.n_ntiles + 15) / 16 * 16;
   p.n_boxes = (p.n_tile + 63) / 64;
   p.n_mtiles = (Cout + 127) / 128;
   p.box_w = 8 + kw - 1;
-  p.xbox_bytes = (p.box_w * (8 + kh - 1) * 128 + 1023) / 1024 * 1024;
+  p.xbox_bytes = (p.box_w * (8 + p.grp_rows - 1) * 128 + 1023) / 1024 * 1024;
   p.tmem_cols = pow2_cols(inplane * p.n_tile);
-  const long long tiles = (long long)kd * p.n_mtiles * p.n_ntiles;
+  const long long tiles = (long long)kd * p.n_rgroups * p.n_mtiles * p.n_ntiles;
   long long ksplit = (3LL * num_sms() + tiles - 1) / tiles;
   if (ksplit > p.total_bricks / 16) ksplit = p.total_bricks / 16;   // >= 16 K blocks per CTA amortise prologue + atomics
   if (ksplit < 1) ksplit = 1;
@@ -619,7 +652,7 @@ extern "C" int nextou_conv3d_ndhwc_halo_wgrad(const void* dy, long long ldy, con
     cuuint64_t dims[5] = {(cuuint64_t)Cin, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)D, (cuuint64_t)B};
     cuuint64_t str[4] = {(cuuint64_t)ldx * 2, (cuuint64_t)ldx * 2 * W, (cuuint64_t)ldx * 2 * W * H,
                          (cuuint64_t)ldx * 2 * W * H * D};
-    cuuint32_t box[5] = {64, (cuuint32_t)p.box_w, (cuuint32_t)(8 + kh - 1), 1, 1};
+    cuuint32_t box[5] = {64, (cuuint32_t)p.box_w, (cuuint32_t)(8 + p.grp_rows - 1), 1, 1};
     int rc = encode_bf16_map(&tmX, x, 5, dims, str, box, "wgrad halo X");
     if (rc) return rc;
   }
