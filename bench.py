@@ -169,7 +169,12 @@ def run_own(args):
         dist.init_process_group("nccl", device_id=dev)
     _lib.lib()  # fail loudly if the CUDA library is missing
 
-    model = H.build_product(CFG, seed=0).to(dev).train()
+    model = H.build_product(CFG, seed=0).to(dev)
+    if world > 1:
+        # what upstream nnU-Net does before wrapping the network in DDP (nnUNetTrainer.initialize): batch statistics of the
+        # 78 BatchNorm layers are then taken over the patches of ALL ranks (nextou_b200.ops.sync_norm_act_tokens)
+        model = torch.nn.SyncBatchNorm.convert_sync_batchnorm(model)
+    model = model.train()
     exclusion = make_tensors(SYNAPSE_EXCLUSION)
     exclusion_dev = [[e.to(dev) for e in p] if isinstance(p, list) else p.to(dev) for p in exclusion]
     inner = DC_and_CE_and_BTI_Loss({"batch_dice": True, "smooth": 1e-5, "do_bg": False, "ddp": world > 1}, {},
@@ -326,6 +331,7 @@ def run_own(args):
                 "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": ms / args.steps,
                 "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
                 "config": {"workload": WORKLOAD, "global_batch": world, "parallelism": f"dp{world}",
+                           "batch_norm": "per-GPU batch statistics" if world == 1 else "SyncBatchNorm over all ranks (as upstream DDP)",
                            "loss": "DeepSupervision(Dice+CE+1e-6*BTI, Synapse interactions)",
                            "optimizer": "SGD nesterov 0.99 wd 3e-5 (torch fused=True), clip 12",
                            "execution": "eager" if gstep is None else "whole-step CUDA graph replay (fwd+loss+bwd+clip+SGD)",
@@ -348,10 +354,26 @@ def run_own(args):
                                               "port on the full 64x224x192 patch, fp32, no warm-up"}
         print(json.dumps(line), flush=True)
     if world > 1:
-        dist.destroy_process_group()
+        # Tear-down: NCCL communicators that were captured into a CUDA graph can block in ncclCommDestroy while the graph is
+        # alive.  Release the graph first and never let the tear-down outlive the measurement: a watchdog ends the process.
+        sys.stdout.flush()
+        if gstep is not None:
+            gstep.graph.reset()
+            del gstep
+        torch.cuda.synchronize()
+        threading.Timer(20.0, lambda: os._exit(0)).start()
+        try:
+            dist.barrier()
+            dist.destroy_process_group()
+        finally:
+            os._exit(0)
 
 
 def main():
+    wd = float(os.environ.get("NEXTOU_BENCH_WATCHDOG", "0") or 0)
+    if wd > 0:      # diagnostics: dump every thread's Python stack if the run is still going after `wd` seconds
+        import faulthandler
+        faulthandler.dump_traceback_later(wd, repeat=False, file=sys.stderr)
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=10)

@@ -220,6 +220,15 @@ int nextou_norm_bwd(const void* x, const void* dy, int dtype, int C, long long r
 int nextou_norm_bwd_colsum(const void* x, const void* dy, int dtype, int C, int c_valid, long long rows, int instances,
                            const float* mean, const float* invstd, const float* gamma, const float* beta, float slope,
                            float* partial, float* sums, void* dx, float* dx_colsum, void* stream);
+/* The two steps of nextou_norm_bwd_colsum, separately, for SyncBatchNorm (upstream nnU-Net converts every BatchNorm with
+ * SyncBatchNorm.convert_sync_batchnorm under DDP): step 1 leaves this rank's sums, the caller all-reduces them over the
+ * ranks, step 2 takes the reduced sums and the GLOBAL row count n_total. */
+int nextou_norm_bwd_reduce(const void* x, const void* dy, int dtype, int C, int c_valid, long long rows, int instances,
+                           const float* mean, const float* invstd, const float* gamma, const float* beta, float slope,
+                           float* partial, float* sums, void* stream);
+int nextou_norm_bwd_apply(const void* x, const void* dy, int dtype, int C, int c_valid, long long rows, int instances,
+                          long long n_total, const float* mean, const float* invstd, const float* gamma, const float* beta,
+                          float slope, const float* sums, float* partial, void* dx, float* dx_colsum, void* stream);
 /* column sums of a dense [rows][C] matrix: sums[0][C] = sum_r x, sums[1][C] = sum_r x^2 (fp32); `partial` as for
  * nextou_norm_stats with instances = 1.  Bias gradients of the 1x1 / spatial convolutions (d bias = colsum(dY)). */
 int nextou_colsum(const void* x, int dtype, int C, long long rows, float* partial, float* sums, void* stream);

@@ -270,14 +270,13 @@ __global__ void norm_bwd_apply_kernel(const T* __restrict__ x, const T* __restri
                                       const float* __restrict__ mean, const float* __restrict__ invstd,
                                       const float* __restrict__ gamma, const float* __restrict__ beta, float slope,
                                       const float* __restrict__ sums, T* __restrict__ dx,
-                                      float* __restrict__ dx_partial, int c_valid) {
+                                      float* __restrict__ dx_partial, int c_valid, float inv_n) {
   extern __shared__ float smem[];
   const long long total = rows * C;
   const T* xb = x + (long long)blockIdx.y * total;
   const T* db = dy + (long long)blockIdx.y * total;
   T* ob = dx + (long long)blockIdx.y * total;
   const long long S = (long long)C * R;
-  const float inv_n = 1.f / (float)rows;
   float mu[NV], is[NV], g[NV], b[NV], m1[NV], m2[NV];
 #pragma unroll
   for (int e = 0; e < NV; ++e) {
@@ -443,7 +442,17 @@ extern "C" int nextou_norm_bwd_colsum(const void* x, const void* dy, int dtype, 
                                       int instances, const float* mean, const float* invstd, const float* gamma,
                                       const float* beta, float slope, float* partial, float* sums, void* dx,
                                       float* dx_colsum, void* stream) {
-  NEXTOU_REQUIRE(x && dy && dx && mean && invstd && partial && sums, "norm_bwd: null pointer");
+  int rc = nextou_norm_bwd_reduce(x, dy, dtype, C, c_valid, rows, instances, mean, invstd, gamma, beta, slope, partial, sums, stream);
+  if (rc) return rc;
+  return nextou_norm_bwd_apply(x, dy, dtype, C, c_valid, rows, instances, rows, mean, invstd, gamma, beta, slope, sums, partial,
+                               dx, dx_colsum, stream);
+}
+
+// backward step 1: sums[inst][0][C] = sum dy', sums[inst][1][C] = sum dy' * xhat over THIS rank's rows
+extern "C" int nextou_norm_bwd_reduce(const void* x, const void* dy, int dtype, int C, int c_valid, long long rows,
+                                      int instances, const float* mean, const float* invstd, const float* gamma,
+                                      const float* beta, float slope, float* partial, float* sums, void* stream) {
+  NEXTOU_REQUIRE(x && dy && mean && invstd && partial && sums, "norm_bwd_reduce: null pointer");
   SweepPlan p;
   int rc = plan_sweep(C, rows, instances, p);
   if (rc) return rc;
@@ -459,16 +468,30 @@ extern "C" int nextou_norm_bwd_colsum(const void* x, const void* dy, int dtype, 
   if (rc) return rc;
   norm_bwd_finalize_kernel<<<dim3((2 * C + 31) / 32, instances), 32 * FIN_SLICES, 0, st>>>(partial, p.nblk, 2 * C,
                                                                                               instances, sums);
-  rc = check_launch("norm_bwd_finalize_kernel");
+  return check_launch("norm_bwd_finalize_kernel");
+}
+
+// backward step 2: dx = gamma*invstd*(dy' - sums0/n_total - xhat*sums1/n_total); n_total = rows normalised together
+// (== rows locally; the global row count when `sums` were all-reduced over the ranks of a SyncBatchNorm)
+extern "C" int nextou_norm_bwd_apply(const void* x, const void* dy, int dtype, int C, int c_valid, long long rows,
+                                     int instances, long long n_total, const float* mean, const float* invstd,
+                                     const float* gamma, const float* beta, float slope, const float* sums, float* partial,
+                                     void* dx, float* dx_colsum, void* stream) {
+  NEXTOU_REQUIRE(x && dy && dx && mean && invstd && sums && n_total > 0, "norm_bwd_apply: null pointer");
+  NEXTOU_REQUIRE(dx_colsum == nullptr || partial != nullptr, "norm_bwd_apply: dx_colsum needs the partial workspace");
+  SweepPlan p;
+  int rc = plan_sweep(C, rows, instances, p);
   if (rc) return rc;
-  // the reduce pass is done with `partial`: reuse its first instances*nblk*C floats for the dx column sums
+  cudaStream_t st = (cudaStream_t)stream;
+  dim3 grid(p.nblk, instances);
   float* dx_partial = dx_colsum ? partial : nullptr;
   const size_t smem2 = dx_colsum ? p.smem / 2 : 0;
   DISPATCH_T(dtype, {
     rc = ensure_smem(norm_bwd_apply_kernel<T>, smem2);
     if (rc) return rc;
     norm_bwd_apply_kernel<T><<<grid, p.threads, smem2, st>>>((const T*)x, (const T*)dy, C, p.R, rows, mean, invstd, gamma,
-                                                            beta, slope, sums, (T*)dx, dx_partial, c_valid);
+                                                            beta, slope, sums, (T*)dx, dx_partial, c_valid,
+                                                            1.f / (float)n_total);
   })
   rc = check_launch("norm_bwd_apply_kernel");
   if (rc || !dx_colsum) return rc;

@@ -107,6 +107,16 @@ def conv_transpose_nd(x, weight, bias, stride):
 # ------------------------------------------------------------------------------------------------------
 # normalisation (+ LeakyReLU), csrc/norm.cu
 # ------------------------------------------------------------------------------------------------------
+def _sync_world(bn) -> int:
+    """World size over which a training-mode nn.SyncBatchNorm synchronises its statistics (1 = plain batch norm)."""
+    if not isinstance(bn, torch.nn.SyncBatchNorm) or not bn.training:
+        return 1
+    import torch.distributed as dist
+    if not (dist.is_available() and dist.is_initialized()):
+        return 1
+    return dist.get_world_size(bn.process_group)
+
+
 def batch_norm_tokens(tok: torch.Tensor, bn: torch.nn.modules.batchnorm._BatchNorm, act_slope: Optional[float] = None):
     """nn.BatchNorm semantics on token rows: batch statistics + running-stat update in training (or when the module
     tracks no running stats), running statistics in eval."""
@@ -114,6 +124,16 @@ def batch_norm_tokens(tok: torch.Tensor, bn: torch.nn.modules.batchnorm._BatchNo
     use_batch_stats = bn.training or bn.running_mean is None
     if use_batch_stats:
         stats["native.batch_norm"] += 1
+        world = _sync_world(bn)
+        if world > 1:
+            # upstream nnU-Net wraps the network in DDP after SyncBatchNorm.convert_sync_batchnorm: statistics over all ranks
+            stats["native.sync_batch_norm"] += 1
+            track = bn.track_running_stats and bn.running_mean is not None
+            if bn.momentum is None:
+                raise NotImplementedError("SyncBatchNorm with cumulative moving average (momentum=None)")
+            return ops.sync_norm_act_tokens(tok, bn.weight, bn.bias, bn.running_mean if track else None,
+                                            bn.running_var if track else None, bn.momentum, bn.eps, slope,
+                                            bn.num_batches_tracked if track else None, bn.process_group, world)
         rm = rv = nbt = None
         momentum = 0.0
         if bn.training and bn.track_running_stats and bn.running_mean is not None:

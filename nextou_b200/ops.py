@@ -854,6 +854,84 @@ class _NormAct(torch.autograd.Function):
         return dx[:, :C], dgamma, dbeta, None, None, None, None, None, None, None
 
 
+def sync_moments(sums: torch.Tensor, count: int, eps: float, group=None):
+    """Cross-rank batch statistics of a SyncBatchNorm layer (upstream nnU-Net converts every BatchNorm under DDP, SURVEY.md
+    §8e).  sums: fp32 [2, P] = this rank's (sum x, sum x^2) per channel; count: this rank's rows.  One all-reduce of
+    [2P + 1] values; returns (mean [P], invstd [P], unbiased variance [P], total row count as a python int is NOT needed on
+    the host: the count travels in the same buffer and stays on the device) -> (mean, invstd, var_unbiased, n_total tensor)."""
+    import torch.distributed as dist
+    P = sums.shape[1]
+    buf = torch.cat([sums.reshape(-1).double(), torch.full((1,), float(count), device=sums.device, dtype=torch.float64)])
+    dist.all_reduce(buf, op=dist.ReduceOp.SUM, group=group)
+    n = buf[2 * P]
+    mean = buf[:P] / n
+    var = (buf[P:2 * P] / n - mean * mean).clamp_min(0.0)
+    invstd = torch.rsqrt(var + eps)
+    unbiased = var * (n / (n - 1.0).clamp_min(1.0))
+    return mean.float(), invstd.float(), unbiased.float(), n
+
+
+class _SyncNormAct(torch.autograd.Function):
+    """Train-mode SyncBatchNorm (+ LeakyReLU): statistics over the rows of ALL ranks.  Forward: local (sum x, sum x^2) ->
+    all-reduce -> normalise; backward: local (sum dy', sum dy' xhat) -> all-reduce -> dx with the global sums and row count
+    (torch.nn.SyncBatchNorm semantics: d gamma / d beta stay local, the gradient all-reduce averages them)."""
+
+    @staticmethod
+    def forward(ctx, x, gamma, beta, running_mean, running_var, momentum, eps, slope, tracked, group, world):
+        xf, C = _physical_rows(x)
+        _need_cuda(xf)
+        T, P = xf.shape
+        L = _lib.lib()
+        f32 = lambda v: None if v is None else v.detach().float().contiguous()
+        g32, b32 = f32(gamma), f32(beta)
+        partial = _norm_partial(P, T, 1, xf.device)
+        sums = torch.empty(2 * P, device=xf.device, dtype=torch.float32)
+        check(L.nextou_colsum(ptr(xf), dtype_code(xf), P, ll(T), ptr(partial), ptr(sums), cstream()), "nextou_colsum")
+        mean, invstd, unbiased, n = sync_moments(sums.view(2, P), T, eps, group)
+        if running_mean is not None:
+            running_mean.mul_(1.0 - momentum).add_(mean[:C], alpha=momentum)
+            running_var.mul_(1.0 - momentum).add_(unbiased[:C], alpha=momentum)
+            if tracked is not None:
+                tracked.add_(1)
+        y = torch.empty_like(xf)
+        check(L.nextou_norm_apply_cv(ptr(xf), dtype_code(xf), P, C, ll(T), 1, ptr(mean), ptr(invstd), ptr(g32), ptr(b32),
+                                     cf(slope), ptr(y), cstream()), "nextou_norm_apply")
+        ctx.save_for_backward(xf, mean, invstd, g32, b32)
+        ctx.meta = (C, P, T, slope, gamma is not None, None if gamma is None else gamma.dtype, group, world)
+        return y[:, :C]
+
+    @staticmethod
+    def backward(ctx, dy):
+        import torch.distributed as dist
+        xf, mean, invstd, g32, b32 = ctx.saved_tensors
+        C, P, T, slope, affine, pdt, group, world = ctx.meta
+        L = _lib.lib()
+        dyf = _rows_like(dy, T, C, P, xf.dtype)
+        partial = _norm_partial(P, T, 1, xf.device)
+        sums = torch.empty(2 * P, device=xf.device, dtype=torch.float32)
+        check(L.nextou_norm_bwd_reduce(ptr(xf), ptr(dyf), dtype_code(xf), P, C, ll(T), 1, ptr(mean), ptr(invstd), ptr(g32),
+                                       ptr(b32), cf(slope), ptr(partial), ptr(sums), cstream()), "nextou_norm_bwd_reduce")
+        local = sums.view(2, P)
+        dgamma = dbeta = None
+        if affine:
+            dbeta, dgamma = local[0, :C].clone().to(pdt), local[1, :C].clone().to(pdt)   # `sums` is reduced in place below
+        dist.all_reduce(sums, op=dist.ReduceOp.SUM, group=group)
+        dx = torch.empty_like(xf)
+        dxsum = torch.empty((1, P), device=xf.device, dtype=torch.float32)
+        check(L.nextou_norm_bwd_apply(ptr(xf), ptr(dyf), dtype_code(xf), P, C, ll(T), 1, ll(T * world), ptr(mean), ptr(invstd),
+                                      ptr(g32), ptr(b32), cf(slope), ptr(sums), ptr(partial), ptr(dx), ptr(dxsum), cstream()),
+              "nextou_norm_bwd_apply")
+        _DxColsum.put(dx, dxsum)
+        return dx[:, :C], dgamma, dbeta, None, None, None, None, None, None, None, None
+
+
+def sync_norm_act_tokens(x_tok, gamma, beta, running_mean, running_var, momentum, eps, slope, num_batches_tracked, group,
+                         world: int):
+    """SyncBatchNorm (+ LeakyReLU) over the rows of every rank of `group` (equal row counts per rank: one patch each)."""
+    return _SyncNormAct.apply(x_tok, gamma, beta, running_mean, running_var, float(momentum), float(eps), float(slope),
+                              num_batches_tracked, group, int(world))
+
+
 def norm_act_tokens(x_tok, gamma, beta, running_mean=None, running_var=None, momentum=0.1, eps=1e-5, slope=1.0,
                     instances=1, num_batches_tracked=None):
     """Batch norm (instances=1) / instance norm (instances=batch) with batch statistics, + LeakyReLU(slope).
