@@ -123,6 +123,64 @@ __global__ void maxunpool_bwd_kernel(const T* __restrict__ dout, long long ldo, 
   dg[p * ldg + j] = dout[v * ldo + j];
 }
 
+// ---- 16-byte-vector variants (VEC channels of one voxel per thread: one set of index divisions per vector) ----
+template <typename T> struct Vec16 { static constexpr int N = 16 / sizeof(T); };
+
+template <typename T>
+__global__ void maxunpool_fwd_vec_kernel(const T* __restrict__ gsrc, long long ldg, const uint8_t* __restrict__ arg,
+                                         int Carg, int C2, PoolGeom g, T* __restrict__ out, long long ldo, long long total) {
+  constexpr int V = Vec16<T>::N;
+  const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= total) return;
+  const int groups = C2 / V;
+  const int j0 = (int)(t % groups) * V;
+  const long long v = t / groups;
+  long long p;
+  int child;
+  parent_of(g, v, p, child);
+  uint4 src = *reinterpret_cast<const uint4*>(gsrc + p * ldg + j0);
+  T* e = reinterpret_cast<T*>(&src);
+  const uint8_t* a = arg + p * Carg;
+  int ja = j0 % Carg;
+#pragma unroll
+  for (int i = 0; i < V; ++i) {
+    if (a[ja] != child) e[i] = from_f<T>(0.f);
+    if (++ja == Carg) ja = 0;
+  }
+  *reinterpret_cast<uint4*>(out + v * ldo + j0) = src;
+}
+
+template <typename T>
+__global__ void maxunpool_bwd_vec_kernel(const T* __restrict__ dout, long long ldo, const uint8_t* __restrict__ arg,
+                                         int Carg, int C2, PoolGeom g, T* __restrict__ dg, long long ldg, long long total) {
+  constexpr int V = Vec16<T>::N;
+  const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= total) return;
+  const int groups = C2 / V;
+  const int j0 = (int)(t % groups) * V;
+  const long long p = t / groups;
+  const long long v0 = child_voxel(g, p, 0);          // children differ from child 0 by a fixed voxel offset
+  const uint8_t* a = arg + p * Carg;
+  int ja = j0 % Carg;
+  uint4 res;
+  T* e = reinterpret_cast<T*>(&res);
+#pragma unroll
+  for (int i = 0; i < V; ++i) {
+    const int ch = a[ja];
+    const int dx = ch % g.pw, dy = (ch / g.pw) % g.ph, dz = ch / (g.pw * g.ph);
+    const long long v = v0 + ((long long)dz * g.H + dy) * g.W + dx;
+    e[i] = dout[v * ldo + j0 + i];
+    if (++ja == Carg) ja = 0;
+  }
+  *reinterpret_cast<uint4*>(dg + p * ldg + j0) = res;
+}
+
+template <typename T>
+static inline bool vec_ok(const void* a, long long lda, const void* b, long long ldb) {
+  constexpr int V = Vec16<T>::N;
+  return lda % V == 0 && ldb % V == 0 && ((uintptr_t)a & 15) == 0 && ((uintptr_t)b & 15) == 0;
+}
+
 static int make_geom(PoolGeom& g, int B, int D, int H, int W, int pd, int ph, int pw) {
   if (B <= 0 || D <= 0 || H <= 0 || W <= 0 || pd <= 0 || ph <= 0 || pw <= 0) {
     set_error("pool: bad geometry B=%d D=%d H=%d W=%d p=(%d,%d,%d)", B, D, H, W, pd, ph, pw);
@@ -198,8 +256,16 @@ extern "C" int nextou_maxunpool3d_fwd(const void* gsrc, int dtype, long long ldg
   if (rc) return rc;
   NEXTOU_REQUIRE(gsrc && out && arg && Carg > 0 && C2 > 0, "maxunpool3d_fwd: bad args");
   const long long total = (long long)B * D * H * W * C2;
-  DISPATCH_T(dtype, maxunpool_fwd_kernel<T><<<blocks_for(total), 256, 0, (cudaStream_t)stream>>>(
-                        (const T*)gsrc, ldg, arg, Carg, C2, g, (T*)out, ldo, total);)
+  DISPATCH_T(dtype, {
+    if (C2 % Vec16<T>::N == 0 && vec_ok<T>(gsrc, ldg, out, ldo)) {
+      const long long tv = total / Vec16<T>::N;
+      maxunpool_fwd_vec_kernel<T><<<blocks_for(tv), 256, 0, (cudaStream_t)stream>>>((const T*)gsrc, ldg, arg, Carg, C2, g,
+                                                                                     (T*)out, ldo, tv);
+    } else {
+      maxunpool_fwd_kernel<T><<<blocks_for(total), 256, 0, (cudaStream_t)stream>>>((const T*)gsrc, ldg, arg, Carg, C2, g,
+                                                                                    (T*)out, ldo, total);
+    }
+  })
   return check_launch("maxunpool_fwd_kernel");
 }
 
@@ -211,8 +277,16 @@ extern "C" int nextou_maxunpool3d_bwd(const void* dout, int dtype, long long ldo
   if (rc) return rc;
   NEXTOU_REQUIRE(dout && dg && arg && Carg > 0 && C2 > 0, "maxunpool3d_bwd: bad args");
   const long long total = (long long)B * g.Dp * g.Hp * g.Wp * C2;
-  DISPATCH_T(dtype, maxunpool_bwd_kernel<T><<<blocks_for(total), 256, 0, (cudaStream_t)stream>>>(
-                        (const T*)dout, ldo, arg, Carg, C2, g, (T*)dg, ldg, total);)
+  DISPATCH_T(dtype, {
+    if (C2 % Vec16<T>::N == 0 && vec_ok<T>(dg, ldg, dg, ldg)) {
+      const long long tv = total / Vec16<T>::N;
+      maxunpool_bwd_vec_kernel<T><<<blocks_for(tv), 256, 0, (cudaStream_t)stream>>>((const T*)dout, ldo, arg, Carg, C2, g,
+                                                                                     (T*)dg, ldg, tv);
+    } else {
+      maxunpool_bwd_kernel<T><<<blocks_for(total), 256, 0, (cudaStream_t)stream>>>((const T*)dout, ldo, arg, Carg, C2, g,
+                                                                                    (T*)dg, ldg, total);
+    }
+  })
   return check_launch("maxunpool_bwd_kernel");
 }
 
