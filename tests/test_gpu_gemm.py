@@ -183,3 +183,34 @@ def test_conv_transpose_fwd_bwd(B, spatial, cin, cout, ks):
     assert _rel(gx, xr.grad) < 6e-3, _rel(gx, xr.grad)
     assert _rel(wd.grad.cpu(), wr.grad) < 1e-4, _rel(wd.grad.cpu(), wr.grad)
     assert _rel(bd.grad.cpu(), br.grad) < 1e-4
+
+
+@pytest.mark.parametrize("R,Cc,ks,groups,conv,flip", [
+    (66, 33, (3, 3, 3), 1, True, True), (33, 66, (1, 3, 3), 1, True, False), (324, 324, (2, 2, 2), 1, True, False),
+    (132, 132, (1, 1, 1), 1, False, False), (264, 264, (1, 1, 1), 6, False, False), (14, 33, (1, 1, 1), 1, False, False),
+    (528, 132, (1, 1), 1, False, False), (24, 24, (1, 1), 4, False, False)])
+def test_pack_weight_pair(R, Cc, ks, groups, conv, flip):
+    """The one-launch operand packs equal the ATen reshape / permute / pad / block_diag chains they replace."""
+    from nextou_b200 import ops
+    g = torch.Generator().manual_seed(R + Cc)
+    w = torch.randn(R, Cc // groups, *ks, generator=g)
+    a, b = ops.pack_weight_pair(w.to(DEV), conv=conv, flip_b=flip, groups=groups)
+    taps = 1
+    for k in ks:
+        taps *= k
+    pad = (lambda c: (c + 63) // 64 * 64) if conv else ops.pad8
+    dense = w
+    if groups > 1:
+        blocks = w.reshape(groups, R // groups, Cc // groups)
+        dense = torch.block_diag(*blocks.unbind(0)).reshape(R, Cc, *ks)
+    d3 = dense.reshape(R, Cc, taps)
+    want_a = torch.zeros(R, taps, pad(Cc))
+    want_a[:, :, :Cc] = d3.permute(0, 2, 1)
+    want_b = torch.zeros(Cc, taps, pad(R))
+    src = d3.flip(2) if flip else d3
+    want_b[:, :, :R] = src.permute(1, 2, 0)
+    assert torch.equal(a.float().cpu(), want_a.reshape(R, -1).bfloat16().float())
+    assert torch.equal(b.float().cpu(), want_b.reshape(Cc, -1).bfloat16().float())
+    if conv and groups == 1:        # same as the ATen reference packer
+        assert torch.equal(a.cpu(), ops.pack_conv_weight(w))
+        assert torch.equal(b.cpu(), ops.pack_conv_weight(w, transpose_flip=True) if flip else ops.pack_conv_weight(w, transpose=True))
