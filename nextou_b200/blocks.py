@@ -72,12 +72,13 @@ class DropPath(nn.Module):
         return x * mask / keep
 
 
-def _residual(mod, out_tok, x, B, spatial):
+def _residual(mod, out_tok, short_tok, B, spatial):
     """drop_path(out) + x (ED:389, 817, 932).  drop_path is the identity for NexToU (rate 0): then the add runs on the
-    physical token rows and keeps the channel-padded layout; a real DropPath goes through the logical view."""
+    physical token rows and keeps the channel-padded layout; a real DropPath goes through the logical view.  `short_tok` is
+    the shortcut alias of the block input from ops.fork_tokens (the branch consumed the other one)."""
     if isinstance(mod.drop_path, nn.Identity):
-        return ops.from_tokens(ops.add_tokens(out_tok, ops.as_tokens(x)), B, spatial)
-    return mod.drop_path(ops.from_tokens(out_tok, B, spatial)) + x
+        return ops.from_tokens(ops.add_tokens(out_tok, short_tok), B, spatial)
+    return mod.drop_path(ops.from_tokens(out_tok, B, spatial)) + ops.from_tokens(short_tok, B, spatial)
 
 
 def _fc_bn(seq: nn.Sequential, tok: torch.Tensor, batch: int, act_slope=None) -> torch.Tensor:
@@ -104,12 +105,12 @@ class FFN(nn.Module):
 
     def forward(self, x):
         B, spatial = x.shape[0], tuple(x.shape[2:])
-        tok = ops.as_tokens(x)
+        tok, short = ops.fork_tokens(ops.as_tokens(x))
         if isinstance(self.act, nn.LeakyReLU):
             h = _fc_bn(self.fc1, tok, B, self.act.negative_slope)
         else:
             h = self.act(_fc_bn(self.fc1, tok, B))
-        return _residual(self, _fc_bn(self.fc2, h, B), x, B, spatial)
+        return _residual(self, _fc_bn(self.fc2, h, B), short, B, spatial)
 
 
 # ------------------------------------------------------------------------------------------------------
@@ -388,12 +389,13 @@ class SwinGrapher(nn.Module):
         if self.r != 1:
             raise NotImplementedError("SwinGrapher with reduce ratio r > 1 (never built by NexToU, ED:1003)")
         # fc1 (1x1 conv + BN) is order-invariant over tokens: run it on the un-partitioned volume
-        h = _fc_bn(self.fc1, ops.as_tokens(x), B)
+        tok, short = ops.fork_tokens(ops.as_tokens(x))
+        h = _fc_bn(self.fc1, tok, B)
         row_map = self._row_map(B, spatial, x.device)
         n_windows = B * _prod(spatial) // self.n
         g = self.graph_conv.forward_tokens(h, B, spatial, self.relative_pos, row_map=row_map, graphs=n_windows, n=self.n)
         g = _fc_bn(self.fc2, g, B)
-        return _residual(self, g, x, B, spatial)
+        return _residual(self, g, short, B, spatial)
 
 
 class PoolGrapher(nn.Module):
@@ -424,11 +426,12 @@ class PoolGrapher(nn.Module):
 
     def forward(self, x):
         B, spatial = x.shape[0], tuple(x.shape[2:])
-        h = _fc_bn(self.fc1, ops.as_tokens(x), B)
+        tok, short = ops.fork_tokens(ops.as_tokens(x))
+        h = _fc_bn(self.fc1, tok, B)
         n_now = _prod([s // p for s, p in zip(spatial, self.pool_size)])
         rp = _resized_relative_pos(self.relative_pos, n_now, self.n, self.r, self.ndim)
         h = _fc_bn(self.fc2, self.graph_conv.forward_tokens(h, B, spatial, rp), B)
-        return _residual(self, h, x, B, spatial)
+        return _residual(self, h, short, B, spatial)
 
 
 # ------------------------------------------------------------------------------------------------------
@@ -600,9 +603,14 @@ class NexToU_Encoder(nn.Module):
 
     def forward(self, x):
         ret = []
-        for stage in self.stages:
+        last = len(self.stages) - 1
+        for i, stage in enumerate(self.stages):
             x = stage(x)
-            ret.append(x)
+            if self.return_skips and i < last:
+                x, skip = ops.fork(x)       # next stage + decoder skip: gradients are summed in the padded token layout
+                ret.append(skip)
+            else:
+                ret.append(x)
         return ret if self.return_skips else ret[-1]
 
     def compute_conv_feature_map_size(self, input_size):
@@ -684,7 +692,11 @@ class NexToU_Decoder(nn.Module):
             if self.deep_supervision or s == last:
                 head = self.seg_layers[s if self.deep_supervision else -1]
                 B, spatial = x.shape[0], tuple(x.shape[2:])
-                seg_outputs.append(ops.from_tokens(dense.linear_tokens(ops.as_tokens(x), head), B, spatial))
+                if s != last:
+                    x, xs = ops.fork(x)     # segmentation head + next decoder stage
+                else:
+                    xs = x
+                seg_outputs.append(ops.from_tokens(dense.linear_tokens(ops.as_tokens(xs), head), B, spatial))
             low = x
         seg_outputs = seg_outputs[::-1]  # highest resolution first
         return seg_outputs if self.deep_supervision else seg_outputs[0]

@@ -977,6 +977,55 @@ def add_tokens(a, b):
     return _AddTokens.apply(a, b)
 
 
+def _sum_grads(g1: torch.Tensor, g2: torch.Tensor) -> torch.Tensor:
+    """g1 + g2 for two [rows, C] token gradients, keeping the channel-padded layout: one vectorised pass over the physical
+    rows when both share it, else one strided add INTO a padded buffer (autograd's own accumulation would produce an
+    unpadded tensor that every TMA consumer has to copy again)."""
+    a, b = _tok2d(g1), _tok2d(g2)
+    if a.dtype != b.dtype:
+        b = b.to(a.dtype)
+    fa, fb = full_rows(a), full_rows(b)
+    if fa is not None and fb is not None and fa.shape == fb.shape and fa.shape[1] % 8 == 0:
+        return (fa + fb)[:, :a.shape[1]]
+    out = padded_like(a.shape[0], a.shape[1], a.dtype, a.device)
+    torch.add(a, b, out=out)
+    return out
+
+
+class _ForkTokens(torch.autograd.Function):
+    """Explicit fan-out of a token tensor that is consumed twice (residual shortcut + branch, U-Net skip + next stage):
+    the two incoming gradients are summed HERE, in the padded token layout, instead of by autograd's accumulation."""
+
+    @staticmethod
+    def forward(ctx, tok):
+        ctx.set_materialize_grads(False)
+        return tok.view_as(tok), tok.view_as(tok)
+
+    @staticmethod
+    def backward(ctx, g1, g2):
+        if g1 is None:
+            return g2
+        if g2 is None:
+            return g1
+        return _sum_grads(g1, g2)
+
+
+def fork_tokens(tok: torch.Tensor):
+    """-> two aliases of `tok` whose gradients are summed by nextou_b200 (see _ForkTokens); a no-op without autograd."""
+    if tok.requires_grad and torch.is_grad_enabled():
+        return _ForkTokens.apply(tok)
+    return tok, tok
+
+
+def fork(x: torch.Tensor):
+    """fork_tokens for a logical (N, C, *spatial) activation."""
+    if not (x.requires_grad and torch.is_grad_enabled()):
+        return x, x
+    B, spatial = x.shape[0], tuple(x.shape[2:])
+    a, b = fork_tokens(as_tokens(x))
+    return from_tokens(a, B, spatial), from_tokens(b, B, spatial)
+
+
 class _CatTokens(torch.autograd.Function):
     @staticmethod
     def forward(ctx, a, b):
