@@ -271,6 +271,13 @@ int nextou_conv3d_ndhwc_strided_dgrad(const void* dy, long long ldy, int B, int 
                                       const void* wpack_t, int Cin, int kd, int kh, int kw, int sd, int sh, int sw, int pd,
                                       int ph, int pw, const float* bias, void* dx, long long ldx, int Di, int Hi, int Wi,
                                       int out_dtype, void* stream);
+/* Same, writing only columns [0, store_cols) of every dx row (Cin <= store_cols <= ldx, store_cols % 8 == 0; columns
+ * [Cin, store_cols) zero-filled): the up-sampled half of torch.cat((up, skip), 1) (NexToU_Encoder_Decoder.py:322) is
+ * written straight into the concatenation buffer. */
+int nextou_conv3d_ndhwc_strided_dgrad_cols(const void* dy, long long ldy, int B, int Do, int Ho, int Wo, int Cout,
+                                           const void* wpack_t, int Cin, int kd, int kh, int kw, int sd, int sh, int sw,
+                                           int pd, int ph, int pw, const float* bias, void* dx, long long ldx,
+                                           int store_cols, int Di, int Hi, int Wi, int out_dtype, void* stream);
 /* Weight gradient with a strided read:  dW[m][tap][n] += sum_i dy[i][m] * x[i*s + tap - pad][n]  (fp32, caller zero-fills
  * dW[Cout][taps][cin_stride]).  dy: bf16 tokens of the dense grid [B][D][H][W][ldy] (Cout = M channels); x: bf16 tokens of
  * the strided-read volume [B][Dx][Hx][Wx][ldx] (Cin = N channels).  Strided convolution: dy = output gradient, x = input.

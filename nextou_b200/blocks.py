@@ -685,10 +685,11 @@ class NexToU_Decoder(nn.Module):
         last = len(self.stages) - 1
         for s in range(len(self.stages)):
             tc = self.transpconvs[s]
-            up = dense.conv_transpose_nd(low, tc.weight, tc.bias, tuple(tc.stride))
             skip = skips[-(s + 2)]
-            cat = ops.cat_tokens(ops.as_tokens(up), ops.as_tokens(skip))      # torch.cat((up, skip), 1), ED:322
-            x = self.stages[s](ops.from_tokens(cat, up.shape[0], tuple(up.shape[2:])))
+            cat, gap = dense.up_cat(low, tc, skip)                           # torch.cat((transpconv(low), skip), 1), ED:321-322
+            first = self.stages[s][0] if isinstance(self.stages[s], nn.Sequential) else self.stages[s]
+            first.convs[0].conv.in_gap = gap                                 # layout of the tensor it is about to receive
+            x = self.stages[s](cat)
             if self.deep_supervision or s == last:
                 head = self.seg_layers[s if self.deep_supervision else -1]
                 B, spatial = x.shape[0], tuple(x.shape[2:])

@@ -49,6 +49,7 @@ struct GemmParams {
   int last_ksteps;     // K16 steps of the last (ragged) 64-channel block
   int zero_fill;       // no taps at all: write bias / zeros
   int row32;           // every output row starts 32-byte aligned (256-bit stores)
+  int store_cols;      // columns [0, store_cols) of an output row are written (<= ldc: the row may continue with other data)
   signed char tap_dd[MAX_TAPS], tap_dh[MAX_TAPS], tap_dw[MAX_TAPS];
   short tap_wi[MAX_TAPS];
 };
@@ -167,7 +168,7 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1)
     }
     if (p.out_dtype == NEXTOU_BF16 && !p.zero_fill) {
       __nv_bfloat16* dst = out_row >= 0 ? reinterpret_cast<__nv_bfloat16*>(p.C) + out_row * p.ldc + n0 : nullptr;
-      const long long left = p.ldc - n0;
+      const long long left = p.store_cols - n0;
       epilogue_row_bf16(tmem_base + ((uint32_t)(q * 32) << 16), p.block_n, sbias, dst,
                         (int)(left < p.block_n ? left : p.block_n), p.row32 != 0);
     } else
@@ -189,11 +190,11 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1)
           if (p.bias != nullptr && col < p.N) x += p.bias[col];
           v[j] = col < p.N ? x : 0.f;
         }
-        if (n0 + c < p.ldc) {
+        if (n0 + c < p.store_cols) {
           if (p.out_dtype == NEXTOU_BF16)
-            store_chunk16(reinterpret_cast<__nv_bfloat16*>(p.C) + out_row * p.ldc, n0 + c, v, p.ldc);
+            store_chunk16(reinterpret_cast<__nv_bfloat16*>(p.C) + out_row * p.ldc, n0 + c, v, p.store_cols);
           else
-            store_chunk16(reinterpret_cast<float*>(p.C) + out_row * p.ldc, n0 + c, v, p.ldc);
+            store_chunk16(reinterpret_cast<float*>(p.C) + out_row * p.ldc, n0 + c, v, p.store_cols);
         }
       }
     }
@@ -210,6 +211,7 @@ static int launch_gemm(const CUtensorMap& tmA, const CUtensorMap& tmB, GemmParam
   p.block_n = pick_block_n(p.N);
   p.tmem_cols = pow2_cols(p.block_n);
   p.row32 = (p.ldc % 16 == 0 && ((uintptr_t)p.C & 31) == 0) ? 1 : 0;
+  if (p.store_cols <= 0 || p.store_cols > p.ldc) p.store_cols = (int)p.ldc;
   const int per_stage = GEMM_BM * GEMM_BK * 2 + p.block_n * GEMM_BK * 2;
   int stages = (200 * 1024) / per_stage;
   if (stages > 4) stages = 4;
@@ -469,8 +471,9 @@ static int launch_conv_general(const void* x, long long ldx, int B, int Di, int 
                                int w_taps_total, int Cout, const TapList& taps, int gd, int gh, int gw,   // i-grid
                                int es_d, int es_h, int es_w, int os_d, int os_h, int os_w, int oo_d, int oo_h, int oo_w,
                                int Do, int Ho, int Wo, const float* bias, void* out, long long ldo, int out_dtype,
-                               cudaStream_t stream) {
+                               cudaStream_t stream, int store_cols = 0) {
   GemmParams p = {};
+  p.store_cols = store_cols;
   p.M = 0; p.N = Cout; p.kblocks = (Cin + GEMM_BK - 1) / GEMM_BK; p.taps = taps.n;
   p.last_ksteps = (Cin - (p.kblocks - 1) * GEMM_BK + 15) / 16;
   p.zero_fill = taps.n == 0 ? 1 : 0;
@@ -578,6 +581,19 @@ extern "C" int nextou_conv3d_ndhwc_strided_dgrad(const void* dy, long long ldy, 
                                                  const void* wpack_t, int Cin, int kd, int kh, int kw, int sd, int sh, int sw,
                                                  int pd, int ph, int pw, const float* bias, void* dx, long long ldx, int Di,
                                                  int Hi, int Wi, int out_dtype, void* stream) {
+  return nextou_conv3d_ndhwc_strided_dgrad_cols(dy, ldy, B, Do, Ho, Wo, Cout, wpack_t, Cin, kd, kh, kw, sd, sh, sw, pd, ph, pw, bias,
+                                                dx, ldx, (int)ldx, Di, Hi, Wi, out_dtype, stream);
+}
+
+// Same, writing only columns [0, store_cols) of every dx row (store_cols % 8 == 0, Cin <= store_cols <= ldx; columns
+// [Cin, store_cols) are zero-filled): the decoder writes the up-sampled half of torch.cat((up, skip), 1) (ED:322) straight
+// into the concatenation buffer, whose rows continue with the skip channels.
+extern "C" int nextou_conv3d_ndhwc_strided_dgrad_cols(const void* dy, long long ldy, int B, int Do, int Ho, int Wo, int Cout,
+                                                      const void* wpack_t, int Cin, int kd, int kh, int kw, int sd, int sh,
+                                                      int sw, int pd, int ph, int pw, const float* bias, void* dx,
+                                                      long long ldx, int store_cols, int Di, int Hi, int Wi, int out_dtype,
+                                                      void* stream) {
+  NEXTOU_REQUIRE(store_cols % 8 == 0 && store_cols >= Cin && store_cols <= ldx, "conv3d_ndhwc_strided_dgrad: bad store_cols %d", store_cols);
   int rc = conv_common_checks("conv3d_ndhwc_strided_dgrad", dy, wpack_t, dx, ldy, Cout, ldx, Cin, out_dtype);
   if (rc) return rc;
   NEXTOU_REQUIRE(B > 0 && Do > 0 && Ho > 0 && Wo > 0 && Di > 0 && Hi > 0 && Wi > 0, "conv3d_ndhwc_strided_dgrad: bad shape");
@@ -605,7 +621,7 @@ extern "C" int nextou_conv3d_ndhwc_strided_dgrad(const void* dy, long long ldy, 
         }
         const int gd = (Di - od + sd - 1) / sd, gh = (Hi - oh + sh - 1) / sh, gw = (Wi - ow + sw - 1) / sw;
         rc = launch_conv_general(dy, ldy, B, Do, Ho, Wo, Cout, wpack_t, kd * kh * kw, Cin, taps, gd, gh, gw, 1, 1, 1, sd, sh, sw,
-                                 od, oh, ow, Di, Hi, Wi, bias, dx, ldx, out_dtype, (cudaStream_t)stream);
+                                 od, oh, ow, Di, Hi, Wi, bias, dx, ldx, out_dtype, (cudaStream_t)stream, store_cols);
         if (rc) return rc;
       }
   return 0;

@@ -76,7 +76,13 @@ def conv_tokens(tok: torch.Tensor, batch: int, spatial: Sequence[int], conv: tor
         and all(d == 1 for d in conv.dilation) and conv.groups == 1
     if same and _bf16_path(tok):
         stats["tcgen05.conv"] += 1
-        return native.conv_tokens(tok, conv.weight, conv.bias, batch, spatial), tuple(spatial)
+        weight = conv.weight
+        gap = getattr(conv, "in_gap", None)
+        if gap is not None and gap[1] > gap[0] and tok.shape[1] == conv.in_channels + gap[1] - gap[0]:
+            # input = up_cat layout [up (ca) | zero gap | skip]: give the weight matching zero columns (ED:322 semantics kept)
+            ca, pa = gap
+            weight = torch.cat([weight[:, :ca], weight.new_zeros(weight.shape[0], pa - ca, *weight.shape[2:]), weight[:, ca:]], 1)
+        return native.conv_tokens(tok, weight, conv.bias, batch, spatial), tuple(spatial)
     plain = all(d == 1 for d in conv.dilation) and conv.groups == 1 and conv.padding_mode == "zeros" \
         and not isinstance(conv.padding, str) and all(1 <= s <= 4 for s in stride) and len(ks) in (2, 3) \
         and int(torch.tensor(ks).prod()) <= 64
@@ -89,6 +95,21 @@ def conv_tokens(tok: torch.Tensor, batch: int, spatial: Sequence[int], conv: tor
     y = f(x, conv.weight, conv.bias, stride=stride, padding=tuple(conv.padding), dilation=tuple(conv.dilation),
           groups=conv.groups)
     return ops.as_tokens(y), tuple(y.shape[2:])
+
+
+def up_cat(low, tconv, skip):
+    """torch.cat((tconv(low), skip), 1) of a decoder stage (ED:321-322).  On the bf16 path both halves land in one buffer
+    (native.up_cat_tokens) and the result carries a zero channel gap after the up-sampled half when its channel count is
+    not a multiple of 8; returns (tensor, gap descriptor | None) — the consuming convolution must know the gap."""
+    ks = tuple(tconv.weight.shape[2:])
+    if tuple(tconv.stride) == ks and all(1 <= s <= 4 for s in ks) and _bf16_path(low):
+        stats["tcgen05.conv_transpose"] += 1
+        B, spatial = low.shape[0], tuple(low.shape[2:])
+        y, osp, gap = native.up_cat_tokens(ops.as_tokens(low), tconv.weight, tconv.bias, ops.as_tokens(skip), B, spatial)
+        return ops.from_tokens(y, B, osp), gap
+    up = conv_transpose_nd(low, tconv.weight, tconv.bias, tuple(tconv.stride))
+    cat = ops.cat_tokens(ops.as_tokens(up), ops.as_tokens(skip))
+    return ops.from_tokens(cat, up.shape[0], tuple(up.shape[2:])), None
 
 
 def conv_transpose_nd(x, weight, bias, stride):

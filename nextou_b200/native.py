@@ -198,3 +198,61 @@ def conv_transpose_tokens(x_tok, weight, bias, batch: int, spatial: Sequence[int
     ks = tuple(weight.shape[2:])
     y = _ConvTransposeTokens.apply(x_tok, weight, bias, batch, tuple(spatial))
     return y, tuple(n * k for n, k in zip(spatial, ks))
+
+
+class _UpCatTokens(torch.autograd.Function):
+    """torch.cat((ConvTranspose(low), skip), 1) of a decoder stage (ED:321-322) in ONE buffer: the transposed convolution
+    writes its Cout channels (+ zero padding up to a multiple of 8) straight into the first columns of the concatenation
+    rows, the skip channels are copied behind them at the 16-byte aligned column pad8(Cout).  The logical result has
+    pad8(Cout) + Cskip channels (a zero gap after the up-sampled half; the consuming convolution's weight gets matching zero
+    columns, dense.conv_tokens), so both halves of the incoming gradient are TMA-ready views: no copy in the backward."""
+
+    @staticmethod
+    def forward(ctx, x, weight, bias, skip, batch, spatial):
+        xb = ops.tma_ready_bf16(x)
+        cin, cout = weight.shape[:2]
+        ks = tuple(weight.shape[2:])
+        osp = tuple(n * k for n, k in zip(spatial, ks))
+        zero = (0,) * len(ks)
+        cb = skip.shape[1]
+        pa = ops.pad8(cout)
+        rows = skip.shape[0]
+        buf = torch.empty((rows, pa + ops.pad8(cb)), device=x.device, dtype=torch.bfloat16)
+        wa, wb = ops.pack_weight_pair(weight, conv=True, flip_b=False)
+        ops.conv_strided_dgrad_bf16(xb, batch, spatial, cin, wb, cout, ks, ks, zero, osp, bias, out=buf, store_cols=pa)
+        buf[:, pa:pa + cb].copy_(skip)
+        ctx.save_for_backward(xb, weight)
+        ctx.wa = wa
+        ctx.meta = (batch, tuple(spatial), osp, bias is not None, None if bias is None else bias.dtype, pa, cb, skip.dtype)
+        return buf[:, :pa + cb]
+
+    @staticmethod
+    def backward(ctx, g):
+        xb, weight = ctx.saved_tensors
+        batch, spatial, osp, has_bias, bdt, pa, cb, sdt = ctx.meta
+        cin, cout = weight.shape[:2]
+        ks = tuple(weight.shape[2:])
+        zero = (0,) * len(ks)
+        dyb = ops.tma_ready_bf16(g[:, :cout])
+        dx = dw = db = dskip = None
+        if ctx.needs_input_grad[0]:
+            dx, _ = ops.conv_strided_fwd_bf16(dyb, batch, osp, cout, ctx.wa, cin, ks, ks, zero, None)
+            dx = dx[:, :cin]
+        if ctx.needs_input_grad[1]:
+            dw = ops.conv_strided_wgrad_bf16(xb, dyb, batch, spatial, osp, cout, cin, ks, ks, zero)
+            dw = dw.permute(0, 2, 1).reshape(cin, cout, *ks).to(weight.dtype)
+        if has_bias and ctx.needs_input_grad[2]:
+            db = ops.colsum_tokens(dyb).to(bdt)
+        if ctx.needs_input_grad[3]:
+            dskip = g[:, pa:pa + cb]
+            if dskip.dtype != sdt:
+                dskip = dskip.to(sdt)
+        return dx, dw, db, dskip, None, None
+
+
+def up_cat_tokens(x_tok, weight, bias, skip_tok, batch: int, spatial: Sequence[int]):
+    """-> (token rows [rows_out, pad8(Cout) + Cskip], output spatial shape, (Cout, pad8(Cout)) gap descriptor)."""
+    ks = tuple(weight.shape[2:])
+    y = _UpCatTokens.apply(x_tok, weight, bias, skip_tok, batch, tuple(spatial))
+    cout = weight.shape[1]
+    return y, tuple(n * k for n, k in zip(spatial, ks)), (cout, ops.pad8(cout))

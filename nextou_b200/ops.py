@@ -671,7 +671,7 @@ def conv_strided_fwd_bf16(x_tok: torch.Tensor, batch: int, spatial: Sequence[int
 def conv_strided_dgrad_bf16(dy_tok: torch.Tensor, batch: int, out_spatial: Sequence[int], cout: int, wpack_t: torch.Tensor,
                             cin: int, ksize: Sequence[int], stride: Sequence[int], padding: Sequence[int],
                             in_spatial: Sequence[int], bias: Optional[torch.Tensor] = None, out_dtype=torch.bfloat16,
-                            out: Optional[torch.Tensor] = None) -> torch.Tensor:
+                            out: Optional[torch.Tensor] = None, store_cols: Optional[int] = None) -> torch.Tensor:
     """Data gradient of a strided convolution / forward of a kernel == stride transposed convolution:
     dy [rows_out, cout] on `out_spatial` -> padded [rows_in, pad8(cin)] on `in_spatial` (or written into `out`)."""
     _need_cuda(dy_tok, wpack_t)
@@ -687,9 +687,11 @@ def conv_strided_dgrad_bf16(dy_tok: torch.Tensor, batch: int, out_spatial: Seque
     taps = ks[0] * ks[1] * ks[2]
     Vo = batch * osp[0] * osp[1] * osp[2]
     with _lib.timed("conv_pertap_tcgen05", 2 * Vo * cout + 2 * V * cin + 2 * cin * cout * taps, 2 * Vo * cin * cout * taps):
-        check(_lib.lib().nextou_conv3d_ndhwc_strided_dgrad(ptr(dy_tok), ll(dy_tok.stride(0)), batch, *osp, cout, ptr(wpack_t), cin,
-                                                           *ks, *st, *pd, ptr(bias32), ptr(out), ll(out.stride(0)), *isp,
-                                                           dtype_code(out), cstream()), "nextou_conv3d_ndhwc_strided_dgrad")
+        cols = int(out.stride(0)) if store_cols is None else int(store_cols)
+        check(_lib.lib().nextou_conv3d_ndhwc_strided_dgrad_cols(ptr(dy_tok), ll(dy_tok.stride(0)), batch, *osp, cout, ptr(wpack_t),
+                                                                cin, *ks, *st, *pd, ptr(bias32), ptr(out), ll(out.stride(0)), cols,
+                                                                *isp, dtype_code(out), cstream()),
+              "nextou_conv3d_ndhwc_strided_dgrad")
     return out
 
 

@@ -138,6 +138,12 @@ def test_every_module_vs_oracle(fname, cfg, precision):
                 want = TO.ffn(xin, sd, name, dim, True)
             else:
                 want = xin
+                gap = getattr(mod.convs[0].conv, "in_gap", None)
+                if gap is not None and gap[1] > gap[0] and want.shape[1] == mod.convs[0].conv.in_channels + gap[1] - gap[0]:
+                    # decoder input in the product's concat layout [up | zero gap | skip] (nextou_b200.dense.up_cat):
+                    # the reference's torch.cat((up, skip), 1) is the same tensor without the gap channels
+                    assert float(want[:, gap[0]:gap[1]].abs().max()) == 0.0
+                    want = torch.cat([want[:, :gap[0]], want[:, gap[1]:]], 1)
                 for i in range(len(mod.convs)):
                     want = TO._conv_block(want, sd, f"{name}.convs.{i}", dim, tuple(mod.convs[i].conv.stride), True)
         got = out.float().cpu()
