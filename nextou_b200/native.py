@@ -18,6 +18,15 @@ def _f32(t):
     return None if t is None else t.detach().float()
 
 
+def _fork_wgrad(ctx, tensor):
+    """A side-stream launcher for the layer's weight-gradient kernel when its data gradient is computed as well (the two
+    kernels are independent: they become parallel branches of the step graph), else None."""
+    from ._lib import KernelTimers
+    if ops.OVERLAP_WGRAD and ctx.needs_input_grad[0] and ctx.needs_input_grad[1] and not KernelTimers.enabled:
+        return ops.side_launch(tensor.device)       # (per-kernel event timing wants every kernel alone on the GPU)
+    return None
+
+
 class _LinearTokens(torch.autograd.Function):
     """y[T, N] = x[T, K] @ w2d[N, K]^T + b  with w2d an fp32 / bf16 master weight."""
 
@@ -45,11 +54,17 @@ class _LinearTokens(torch.autograd.Function):
         K = w2d.shape[1] * g
         dyb = ops.tma_ready_bf16(dy)
         dx = dw = db = None
-        if ctx.needs_input_grad[0]:
-            dx = ops.gemm_bf16_tn(dyb, ctx.wt[:, :N], None, n=K)[:, :K]          # dX = dY W
+        side = _fork_wgrad(ctx, dyb)
         if ctx.needs_input_grad[1]:
             # dW = dY^T X through the MN-major tcgen05 weight-gradient kernel (a 1x1 "convolution" over T voxels)
-            dw = ops.conv_wgrad_bf16(dyb, xb, 1, (xb.shape[0],), K, N, (1,)).reshape(N, K)
+            dw = ops.conv_wgrad_bf16(dyb, xb, 1, (xb.shape[0],), K, N, (1,), side=side)
+        if ctx.needs_input_grad[0]:
+            dx = ops.gemm_bf16_tn(dyb, ctx.wt[:, :N], None, n=K)[:, :K]          # dX = dY W
+        if side is not None:
+            side.join()
+            dw = dw()
+        if ctx.needs_input_grad[1]:
+            dw = dw.reshape(N, K)
             if g > 1:   # diagonal blocks of the dense gradient -> (Cout, Cin / groups)
                 dw = dw.view(g, N // g, g, K // g).diagonal(dim1=0, dim2=2).permute(2, 0, 1).reshape(N, K // g)
             dw = dw.to(w2d.dtype)
@@ -91,10 +106,15 @@ class _ConvTokens(torch.autograd.Function):
         ks = tuple(weight.shape[2:])
         dyb = ops.tma_ready_bf16(dy)
         dx = dw = db = None
+        side = _fork_wgrad(ctx, dyb)
+        if ctx.needs_input_grad[1]:
+            dw = ops.conv_wgrad_bf16(dyb, xb, batch, spatial, cin, cout, ks, side=side)
         if ctx.needs_input_grad[0]:
             dx = ops.conv_ndhwc_bf16(dyb, batch, spatial, cout, ctx.wt, cin, ks, None)[:, :cin]
+        if side is not None:
+            side.join()
+            dw = dw()
         if ctx.needs_input_grad[1]:
-            dw = ops.conv_wgrad_bf16(dyb, xb, batch, spatial, cin, cout, ks)
             dw = dw.to(weight.dtype)
         if has_bias and ctx.needs_input_grad[2]:
             db = ops.colsum_tokens(dyb).to(bdt)
@@ -135,10 +155,15 @@ class _ConvStridedTokens(torch.autograd.Function):
         osp = _out_spatial(spatial, ks, stride, padding)
         dyb = ops.tma_ready_bf16(dy)
         dx = dw = db = None
+        side = _fork_wgrad(ctx, dyb)
+        if ctx.needs_input_grad[1]:
+            dw = ops.conv_strided_wgrad_bf16(dyb, xb, batch, osp, spatial, cin, cout, ks, stride, padding, side=side)
         if ctx.needs_input_grad[0]:
             dx = ops.conv_strided_dgrad_bf16(dyb, batch, osp, cout, ctx.wt, cin, ks, stride, padding, spatial)[:, :cin]
+        if side is not None:
+            side.join()
+            dw = dw()
         if ctx.needs_input_grad[1]:
-            dw = ops.conv_strided_wgrad_bf16(dyb, xb, batch, osp, spatial, cin, cout, ks, stride, padding)
             dw = dw.permute(0, 2, 1).reshape(cout, cin, *ks).to(weight.dtype)
         if has_bias and ctx.needs_input_grad[2]:
             db = ops.colsum_tokens(dyb).to(bdt)
@@ -235,11 +260,16 @@ class _UpCatTokens(torch.autograd.Function):
         zero = (0,) * len(ks)
         dyb = ops.tma_ready_bf16(g[:, :cout])
         dx = dw = db = dskip = None
+        side = _fork_wgrad(ctx, dyb)
+        if ctx.needs_input_grad[1]:
+            dw = ops.conv_strided_wgrad_bf16(xb, dyb, batch, spatial, osp, cout, cin, ks, ks, zero, side=side)
         if ctx.needs_input_grad[0]:
             dx, _ = ops.conv_strided_fwd_bf16(dyb, batch, osp, cout, ctx.wa, cin, ks, ks, zero, None)
             dx = dx[:, :cin]
+        if side is not None:
+            side.join()
+            dw = dw()
         if ctx.needs_input_grad[1]:
-            dw = ops.conv_strided_wgrad_bf16(xb, dyb, batch, spatial, osp, cout, cin, ks, ks, zero)
             dw = dw.permute(0, 2, 1).reshape(cin, cout, *ks).to(weight.dtype)
         if has_bias and ctx.needs_input_grad[2]:
             db = ops.colsum_tokens(dyb).to(bdt)

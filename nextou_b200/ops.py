@@ -697,8 +697,9 @@ def conv_strided_dgrad_bf16(dy_tok: torch.Tensor, batch: int, out_spatial: Seque
 
 def conv_strided_wgrad_bf16(dense_tok: torch.Tensor, strided_tok: torch.Tensor, batch: int, dense_spatial: Sequence[int],
                             strided_spatial: Sequence[int], c_strided: int, c_dense: int, ksize: Sequence[int],
-                            stride: Sequence[int], padding: Sequence[int]) -> torch.Tensor:
-    """fp32 [c_dense, taps, c_strided] = sum_i dense[i][m] * strided[i*s + tap - pad][n] (csrc/gemm_tcgen05.cu)."""
+                            stride: Sequence[int], padding: Sequence[int], side: Optional["side_launch"] = None):
+    """fp32 [c_dense, taps, c_strided] = sum_i dense[i][m] * strided[i*s + tap - pad][n] (csrc/gemm_tcgen05.cu).
+    With `side`: launched on the side stream, returns a finisher (see conv_wgrad_bf16)."""
     _need_cuda(dense_tok, strided_tok)
     assert dense_tok.dtype == torch.bfloat16 and strided_tok.dtype == torch.bfloat16
     dsp, ks, st, pd = _geom3(dense_spatial, ksize, stride, padding)
@@ -709,19 +710,62 @@ def conv_strided_wgrad_bf16(dense_tok: torch.Tensor, strided_tok: torch.Tensor, 
     cs = (c_strided + 3) // 4 * 4
     dw = torch.zeros((c_dense, taps, cs), device=dense_tok.device, dtype=torch.float32)
     V = batch * dsp[0] * dsp[1] * dsp[2]
-    with _lib.timed("wgrad_tcgen05", 2 * V * c_dense + 2 * batch * ssp[0] * ssp[1] * ssp[2] * c_strided + 4 * c_dense * c_strided * taps,
-                    2 * V * c_dense * c_strided * taps):
-        check(_lib.lib().nextou_conv3d_ndhwc_strided_wgrad(ptr(dense_tok), ll(dense_tok.stride(0)), ptr(strided_tok),
-                                                           ll(strided_tok.stride(0)), batch, *dsp, *ssp, c_strided, c_dense, *ks,
-                                                           *st, *pd, ptr(dw), cs, cstream()),
-              "nextou_conv3d_ndhwc_strided_wgrad")
-    return dw[:, :, :c_strided]
+    with (side if side is not None else _null_ctx()):
+        with _lib.timed("wgrad_tcgen05", 2 * V * c_dense + 2 * batch * ssp[0] * ssp[1] * ssp[2] * c_strided + 4 * c_dense * c_strided * taps,
+                        2 * V * c_dense * c_strided * taps):
+            check(_lib.lib().nextou_conv3d_ndhwc_strided_wgrad(ptr(dense_tok), ll(dense_tok.stride(0)), ptr(strided_tok),
+                                                               ll(strided_tok.stride(0)), batch, *dsp, *ssp, c_strided, c_dense,
+                                                               *ks, *st, *pd, ptr(dw), cs, cstream()),
+                  "nextou_conv3d_ndhwc_strided_wgrad")
+    finish = lambda: dw[:, :, :c_strided]
+    return finish if side is not None else finish()
+
+
+OVERLAP_WGRAD = True   # run a layer's weight-gradient kernel on a side stream, concurrently with its data-gradient kernel
+_SIDE_STREAMS = {}
+
+
+class side_launch:
+    """Fork / join helper: kernel launches inside the `with` block go to a per-device side stream that first waits for the
+    current stream; `join()` makes the current stream wait for them.  Nothing may be ALLOCATED inside the block (the
+    caching allocator ties a block to the stream it was allocated on): callers allocate outputs before entering.  Inside a
+    CUDA-graph capture the fork / join become graph edges, so the two kernels are parallel branches of the step graph."""
+
+    def __init__(self, device):
+        self.cur = torch.cuda.current_stream(device)
+        key = (device.index if device.index is not None else torch.cuda.current_device())
+        if key not in _SIDE_STREAMS:
+            _SIDE_STREAMS[key] = torch.cuda.Stream(device)
+        self.side = _SIDE_STREAMS[key]
+        self._ctx = None
+
+    def __enter__(self):
+        self.side.wait_stream(self.cur)
+        self._ctx = torch.cuda.stream(self.side)
+        self._ctx.__enter__()
+        return self
+
+    def __exit__(self, *exc):
+        self._ctx.__exit__(*exc)
+        return False
+
+    def join(self):
+        self.cur.wait_stream(self.side)
+
+
+class _null_ctx:
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *exc):
+        return False
 
 
 def conv_wgrad_bf16(dy_tok: torch.Tensor, x_tok: torch.Tensor, batch: int, spatial: Sequence[int], cin: int, cout: int,
-                    ksize: Sequence[int], halo: Optional[bool] = None) -> torch.Tensor:
+                    ksize: Sequence[int], halo: Optional[bool] = None, side: Optional[side_launch] = None):
     """fp32 weight gradient (Cout, Cin, *ksize) of a stride-1 'same' convolution (1x1: ksize of ones) from bf16
-    token-major dY [rows, Cout] and X [rows, Cin] (csrc/gemm_tcgen05.cu, MN-major tcgen05 operands)."""
+    token-major dY [rows, Cout] and X [rows, Cin] (csrc/gemm_tcgen05.cu, MN-major tcgen05 operands).
+    With `side` the kernel is launched on the side stream and a FINISHER is returned: call side.join(), then the finisher."""
     _need_cuda(dy_tok, x_tok)
     assert dy_tok.dtype == torch.bfloat16 and x_tok.dtype == torch.bfloat16
     sp = list(spatial)
@@ -735,11 +779,13 @@ def conv_wgrad_bf16(dy_tok: torch.Tensor, x_tok: torch.Tensor, batch: int, spati
     use_halo = (CONV_HALO if halo is None else halo) and ks[1] in (1, 3) and ks[2] in (1, 3) and taps > 1
     fn = _lib.lib().nextou_conv3d_ndhwc_halo_wgrad if use_halo else _lib.lib().nextou_conv3d_ndhwc_wgrad
     V = batch * D * H * W
-    with _lib.timed("wgrad_halo_tcgen05" if use_halo else "wgrad_tcgen05", 2 * V * (cin + cout) + 4 * cin * cout * taps,
-                    2 * V * cin * cout * taps):
-        check(fn(ptr(dy_tok), ll(dy_tok.stride(0)), ptr(x_tok), ll(x_tok.stride(0)), batch, D, H, W, cin, cout, ks[0], ks[1],
-                 ks[2], ptr(dw), cs, cstream()), "nextou_conv3d_ndhwc_wgrad")
-    return dw[:, :, :cin].permute(0, 2, 1).reshape(cout, cin, *ksize)
+    with (side if side is not None else _null_ctx()):
+        with _lib.timed("wgrad_halo_tcgen05" if use_halo else "wgrad_tcgen05", 2 * V * (cin + cout) + 4 * cin * cout * taps,
+                        2 * V * cin * cout * taps):
+            check(fn(ptr(dy_tok), ll(dy_tok.stride(0)), ptr(x_tok), ll(x_tok.stride(0)), batch, D, H, W, cin, cout, ks[0], ks[1],
+                     ks[2], ptr(dw), cs, cstream()), "nextou_conv3d_ndhwc_wgrad")
+    finish = lambda: dw[:, :, :cin].permute(0, 2, 1).reshape(cout, cin, *ksize)
+    return finish if side is not None else finish()
 
 
 # ----------------------------------------------------------------------------------------------
