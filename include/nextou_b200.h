@@ -206,6 +206,11 @@ int nextou_norm_stats_tracked(const void* x, int dtype, int C, int c_valid, long
  * _bwd_colsum: no padded copies of the module's parameters / buffers are needed. */
 int nextou_norm_apply_cv(const void* x, int dtype, int C, int c_valid, long long rows, int instances, const float* mean,
                          const float* invstd, const float* gamma, const float* beta, float slope, void* y, void* stream);
+/* Same with the block's residual shortcut fused in: y = lrelu(norm(x)) + residual (residual: same [instances][rows][C]
+ * layout, may be NULL) — `x + BN(fc2(...))` of FFN / SwinGrapher / PoolGrapher (NexToU_Encoder_Decoder.py:389, 817, 932). */
+int nextou_norm_apply_res(const void* x, int dtype, int C, int c_valid, long long rows, int instances, const float* mean,
+                          const float* invstd, const float* gamma, const float* beta, float slope, const void* residual,
+                          void* y, void* stream);
 /* y = lrelu((x - mean) * invstd * gamma + beta, slope); gamma / beta [C] fp32 or NULL */
 int nextou_norm_apply(const void* x, int dtype, int C, long long rows, int instances, const float* mean,
                       const float* invstd, const float* gamma, const float* beta, float slope, void* y,

@@ -81,10 +81,18 @@ def _residual(mod, out_tok, short_tok, B, spatial):
     return mod.drop_path(ops.from_tokens(out_tok, B, spatial)) + ops.from_tokens(short_tok, B, spatial)
 
 
-def _fc_bn(seq: nn.Sequential, tok: torch.Tensor, batch: int, act_slope=None) -> torch.Tensor:
+def _fc_bn(seq: nn.Sequential, tok: torch.Tensor, batch: int, act_slope=None, residual=None) -> torch.Tensor:
     """nn.Sequential(1x1 conv, norm) as used for fc1 / fc2 everywhere (ED:373-381, 710-720, 833-842), on token rows:
-    a GEMM followed by the fused norm (+ LeakyReLU) kernel."""
-    return dense.norm_tokens(dense.linear_tokens(tok, seq[0]), seq[1], batch, act_slope)
+    a GEMM followed by the fused norm (+ LeakyReLU) (+ residual shortcut) kernel."""
+    return dense.norm_tokens(dense.linear_tokens(tok, seq[0]), seq[1], batch, act_slope, residual)
+
+
+def _fc_bn_residual(mod, seq, tok, short_tok, B, spatial):
+    """x + drop_path(BN(fc2(.)))  (ED:389, 817, 932): with drop_path = identity (NexToU: rate 0) the shortcut add is fused
+    into the norm-apply kernel; a real DropPath goes through the logical view."""
+    if isinstance(mod.drop_path, nn.Identity):
+        return ops.from_tokens(_fc_bn(seq, tok, B, residual=short_tok), B, spatial)
+    return _residual(mod, _fc_bn(seq, tok, B), short_tok, B, spatial)
 
 
 class FFN(nn.Module):
@@ -110,7 +118,7 @@ class FFN(nn.Module):
             h = _fc_bn(self.fc1, tok, B, self.act.negative_slope)
         else:
             h = self.act(_fc_bn(self.fc1, tok, B))
-        return _residual(self, _fc_bn(self.fc2, h, B), short, B, spatial)
+        return _fc_bn_residual(self, self.fc2, h, short, B, spatial)
 
 
 # ------------------------------------------------------------------------------------------------------
@@ -394,8 +402,7 @@ class SwinGrapher(nn.Module):
         row_map = self._row_map(B, spatial, x.device)
         n_windows = B * _prod(spatial) // self.n
         g = self.graph_conv.forward_tokens(h, B, spatial, self.relative_pos, row_map=row_map, graphs=n_windows, n=self.n)
-        g = _fc_bn(self.fc2, g, B)
-        return _residual(self, g, short, B, spatial)
+        return _fc_bn_residual(self, self.fc2, g, short, B, spatial)
 
 
 class PoolGrapher(nn.Module):
@@ -430,8 +437,7 @@ class PoolGrapher(nn.Module):
         h = _fc_bn(self.fc1, tok, B)
         n_now = _prod([s // p for s, p in zip(spatial, self.pool_size)])
         rp = _resized_relative_pos(self.relative_pos, n_now, self.n, self.r, self.ndim)
-        h = _fc_bn(self.fc2, self.graph_conv.forward_tokens(h, B, spatial, rp), B)
-        return _residual(self, h, short, B, spatial)
+        return _fc_bn_residual(self, self.fc2, self.graph_conv.forward_tokens(h, B, spatial, rp), short, B, spatial)
 
 
 # ------------------------------------------------------------------------------------------------------

@@ -188,9 +188,11 @@ __global__ void __launch_bounds__(32 * FIN_SLICES)
 template <typename T>
 __global__ void norm_apply_kernel(const T* __restrict__ x, int C, int R, long long rows, const float* __restrict__ mean,
                                   const float* __restrict__ invstd, const float* __restrict__ gamma,
-                                  const float* __restrict__ beta, float slope, T* __restrict__ y, int c_valid) {
+                                  const float* __restrict__ beta, float slope, T* __restrict__ y, int c_valid,
+                                  const T* __restrict__ residual) {
   const long long total = rows * C;
   const T* base = x + (long long)blockIdx.y * total;
+  const T* rbase = residual ? residual + (long long)blockIdx.y * total : nullptr;
   T* obase = y + (long long)blockIdx.y * total;
   const long long S = (long long)C * R;
   float sc[NV], sh[NV];
@@ -209,6 +211,12 @@ __global__ void norm_apply_kernel(const T* __restrict__ x, int C, int R, long lo
     for (int e = 0; e < NV; ++e) {
       const float t = fmaf(v[e], sc[e], sh[e]);
       v[e] = t > 0.f ? t : t * slope;
+    }
+    if (rbase != nullptr) {   // fused residual add: y = T(act(norm(x))) + shortcut, rounded like the two separate ops
+      float r[NV];
+      load_guard(rbase, off, total, r);
+#pragma unroll
+      for (int e = 0; e < NV; ++e) v[e] = to_f(from_f<T>(v[e])) + r[e];
     }
     store_guard(obase, off, total, v);
   }
@@ -421,13 +429,19 @@ extern "C" int nextou_norm_apply(const void* x, int dtype, int C, long long rows
 extern "C" int nextou_norm_apply_cv(const void* x, int dtype, int C, int c_valid, long long rows, int instances,
                                     const float* mean, const float* invstd, const float* gamma, const float* beta,
                                     float slope, void* y, void* stream) {
+  return nextou_norm_apply_res(x, dtype, C, c_valid, rows, instances, mean, invstd, gamma, beta, slope, nullptr, y, stream);
+}
+
+extern "C" int nextou_norm_apply_res(const void* x, int dtype, int C, int c_valid, long long rows, int instances,
+                                     const float* mean, const float* invstd, const float* gamma, const float* beta,
+                                     float slope, const void* residual, void* y, void* stream) {
   NEXTOU_REQUIRE(x && y && mean && invstd, "norm_apply: null pointer");
   SweepPlan p;
   int rc = plan_sweep(C, rows, instances, p);
   if (rc) return rc;
   dim3 grid(p.nblk, instances);
   DISPATCH_T(dtype, norm_apply_kernel<T><<<grid, p.threads, 0, (cudaStream_t)stream>>>(
-                        (const T*)x, C, p.R, rows, mean, invstd, gamma, beta, slope, (T*)y, c_valid);)
+                        (const T*)x, C, p.R, rows, mean, invstd, gamma, beta, slope, (T*)y, c_valid, (const T*)residual);)
   return check_launch("norm_apply_kernel");
 }
 

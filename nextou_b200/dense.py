@@ -138,7 +138,8 @@ def _sync_world(bn) -> int:
     return dist.get_world_size(bn.process_group)
 
 
-def batch_norm_tokens(tok: torch.Tensor, bn: torch.nn.modules.batchnorm._BatchNorm, act_slope: Optional[float] = None):
+def batch_norm_tokens(tok: torch.Tensor, bn: torch.nn.modules.batchnorm._BatchNorm, act_slope: Optional[float] = None,
+                      residual: Optional[torch.Tensor] = None):
     """nn.BatchNorm semantics on token rows: batch statistics + running-stat update in training (or when the module
     tracks no running stats), running statistics in eval."""
     slope = 1.0 if act_slope is None else act_slope
@@ -152,9 +153,10 @@ def batch_norm_tokens(tok: torch.Tensor, bn: torch.nn.modules.batchnorm._BatchNo
             track = bn.track_running_stats and bn.running_mean is not None
             if bn.momentum is None:
                 raise NotImplementedError("SyncBatchNorm with cumulative moving average (momentum=None)")
-            return ops.sync_norm_act_tokens(tok, bn.weight, bn.bias, bn.running_mean if track else None,
-                                            bn.running_var if track else None, bn.momentum, bn.eps, slope,
-                                            bn.num_batches_tracked if track else None, bn.process_group, world)
+            y = ops.sync_norm_act_tokens(tok, bn.weight, bn.bias, bn.running_mean if track else None,
+                                         bn.running_var if track else None, bn.momentum, bn.eps, slope,
+                                         bn.num_batches_tracked if track else None, bn.process_group, world)
+            return y if residual is None else ops.add_tokens(y, residual)
         rm = rv = nbt = None
         momentum = 0.0
         if bn.training and bn.track_running_stats and bn.running_mean is not None:
@@ -164,14 +166,15 @@ def batch_norm_tokens(tok: torch.Tensor, bn: torch.nn.modules.batchnorm._BatchNo
             else:                                                        # cumulative average: the factor is needed on the host
                 bn.num_batches_tracked.add_(1)
                 momentum = 1.0 / float(bn.num_batches_tracked)
-        return ops.norm_act_tokens(tok, bn.weight, bn.bias, rm, rv, momentum, bn.eps, slope, 1, nbt)
+        return ops.norm_act_tokens(tok, bn.weight, bn.bias, rm, rv, momentum, bn.eps, slope, 1, nbt, residual)
     stats["native.affine_act"] += 1
     inv = torch.rsqrt(bn.running_var.float() + bn.eps)
     scale = inv if bn.weight is None else inv * bn.weight.float()
     shift = -bn.running_mean.float() * scale
     if bn.bias is not None:
         shift = shift + bn.bias.float()
-    return ops.affine_act_tokens(tok, scale, shift, slope)
+    y = ops.affine_act_tokens(tok, scale, shift, slope)
+    return y if residual is None else ops.add_tokens(y, residual)
 
 
 def instance_norm_tokens(tok: torch.Tensor, inorm: torch.nn.modules.instancenorm._InstanceNorm, batch: int,
@@ -184,9 +187,11 @@ def instance_norm_tokens(tok: torch.Tensor, inorm: torch.nn.modules.instancenorm
     return ops.norm_act_tokens(tok, inorm.weight, inorm.bias, None, None, 0.0, inorm.eps, slope, batch)
 
 
-def norm_tokens(tok, norm_mod, batch: int, act_slope: Optional[float] = None):
+def norm_tokens(tok, norm_mod, batch: int, act_slope: Optional[float] = None, residual: Optional[torch.Tensor] = None):
+    """norm (+ LeakyReLU) (+ residual shortcut: `x + BN(...)` of the graphers / FFN, fused into the apply kernel)."""
     if isinstance(norm_mod, torch.nn.modules.batchnorm._BatchNorm):
-        return batch_norm_tokens(tok, norm_mod, act_slope)
+        return batch_norm_tokens(tok, norm_mod, act_slope, residual)
     if isinstance(norm_mod, torch.nn.modules.instancenorm._InstanceNorm):
-        return instance_norm_tokens(tok, norm_mod, batch, act_slope)
+        y = instance_norm_tokens(tok, norm_mod, batch, act_slope)
+        return y if residual is None else ops.add_tokens(y, residual)
     raise NotImplementedError("normalisation module %s" % type(norm_mod).__name__)

@@ -854,7 +854,7 @@ class _NormAct(torch.autograd.Function):
     """Train-mode normalisation with batch statistics + optional LeakyReLU (slope 1.0 = none)."""
 
     @staticmethod
-    def forward(ctx, x, gamma, beta, running_mean, running_var, momentum, eps, slope, instances, tracked=None):
+    def forward(ctx, x, gamma, beta, running_mean, running_var, momentum, eps, slope, instances, tracked=None, residual=None):
         xf, C = _physical_rows(x)
         _need_cuda(xf)
         T, P = xf.shape                      # P = physical row pitch >= C
@@ -874,10 +874,16 @@ class _NormAct(torch.autograd.Function):
                                           ptr(invstd), ptr(rm), ptr(rv), cf(momentum if momentum is not None else 0.0),
                                           ptr(tracked), cstream()), "nextou_norm_stats_tracked")
         y = torch.empty_like(xf)
-        check(L.nextou_norm_apply_cv(ptr(xf), dtype_code(xf), P, C, ll(rows), instances, ptr(mean), ptr(invstd), ptr(g32),
-                                     ptr(b32), cf(slope), ptr(y), cstream()), "nextou_norm_apply")
+        rf = None
+        if residual is not None:      # shortcut of the residual block, in the same physical layout as x
+            rf = full_rows(_tok2d(residual))
+            if rf is None or rf.shape != xf.shape or rf.dtype != xf.dtype:
+                rf = _rows_like(residual, T, C, P, xf.dtype)
+        check(L.nextou_norm_apply_res(ptr(xf), dtype_code(xf), P, C, ll(rows), instances, ptr(mean), ptr(invstd), ptr(g32),
+                                      ptr(b32), cf(slope), ptr(rf), ptr(y), cstream()), "nextou_norm_apply")
         ctx.save_for_backward(xf, mean, invstd, g32, b32)
         ctx.meta = (C, P, rows, instances, slope, gamma is not None, None if gamma is None else gamma.dtype)
+        ctx.has_residual = residual is not None
         return y[:, :C]
 
     @staticmethod
@@ -899,7 +905,7 @@ class _NormAct(torch.autograd.Function):
             s = sums.view(instances, 2, P)
             s = s[0] if instances == 1 else s.sum(0)
             dbeta, dgamma = s[0, :C].to(pdt), s[1, :C].to(pdt)
-        return dx[:, :C], dgamma, dbeta, None, None, None, None, None, None, None
+        return dx[:, :C], dgamma, dbeta, None, None, None, None, None, None, None, (dy if ctx.has_residual else None)
 
 
 def sync_moments(sums: torch.Tensor, count: int, eps: float, group=None):
@@ -981,13 +987,13 @@ def sync_norm_act_tokens(x_tok, gamma, beta, running_mean, running_var, momentum
 
 
 def norm_act_tokens(x_tok, gamma, beta, running_mean=None, running_var=None, momentum=0.1, eps=1e-5, slope=1.0,
-                    instances=1, num_batches_tracked=None):
+                    instances=1, num_batches_tracked=None, residual=None):
     """Batch norm (instances=1) / instance norm (instances=batch) with batch statistics, + LeakyReLU(slope).
     num_batches_tracked (int64 0-d CUDA tensor) is incremented by the statistics kernel."""
     if num_batches_tracked is not None:
         assert num_batches_tracked.dtype == torch.int64 and num_batches_tracked.is_cuda
     return _NormAct.apply(x_tok, gamma, beta, running_mean, running_var, momentum, eps, float(slope), int(instances),
-                          num_batches_tracked)
+                          num_batches_tracked, residual)
 
 
 def affine_act_tokens(x_tok, scale, shift, slope=1.0):

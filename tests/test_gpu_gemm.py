@@ -214,3 +214,66 @@ def test_pack_weight_pair(R, Cc, ks, groups, conv, flip):
     if conv and groups == 1:        # same as the ATen reference packer
         assert torch.equal(a.cpu(), ops.pack_conv_weight(w))
         assert torch.equal(b.cpu(), ops.pack_conv_weight(w, transpose_flip=True) if flip else ops.pack_conv_weight(w, transpose=True))
+
+
+def test_fork_tokens_sums_gradients_in_padded_layout():
+    """ops.fork_tokens: two aliases whose gradients are summed by the package (padded pitch kept), equal to autograd's sum."""
+    from nextou_b200 import ops
+    g = torch.Generator().manual_seed(3)
+    rows, C = 500, 33
+    buf = torch.randn(rows, ops.pad8(C), generator=g).bfloat16().to(DEV)
+    x = buf[:, :C].requires_grad_(True)
+    a, b = ops.fork_tokens(x)
+    ga = torch.randn(rows, ops.pad8(C), generator=g).bfloat16().to(DEV)[:, :C]     # padded-pitch gradient (GEMM dgrad output)
+    gb = torch.randn(rows, C, generator=g).bfloat16().to(DEV)                      # dense gradient (autograd add output)
+    (a.float() * ga.float()).sum().backward(retain_graph=True)
+    assert torch.equal(x.grad, ga)                                                # single consumer: passed through
+    x.grad = None
+    seen = []
+    h = x.register_hook(lambda t: seen.append(t.stride(0)))                       # layout of the summed gradient itself
+    ((a.float() * ga.float()).sum() + (b.float() * gb.float()).sum()).backward()
+    h.remove()
+    assert torch.equal(x.grad.float(), (ga.float() + gb.float()).bfloat16().float())
+    assert seen and seen[0] % 8 == 0                                              # TMA-ready: no re-padding copy downstream
+    x.grad = None
+    a2, b2 = ops.fork_tokens(x)
+    ((a2.float() * ga.float()).sum() + (b2.float() * ga.float()).sum()).backward()   # both padded: vectorised full-row add
+    assert torch.equal(x.grad.float(), (2 * ga.float()).bfloat16().float())
+
+
+@pytest.mark.parametrize("B,spatial,cin,cskip,ks", [(1, (4, 7, 6), 324, 324, (2, 2, 2)), (1, (8, 12, 16), 132, 66, (2, 2, 2)),
+                                                    (2, (8, 12, 16), 66, 33, (1, 2, 2)), (1, (10, 12), 66, 33, (2, 2))])
+def test_up_cat_matches_transpose_conv_plus_cat(B, spatial, cin, cskip, ks):
+    """dense.up_cat == torch.cat((conv_transpose(low), skip), 1) up to the zero channel gap, forward and backward."""
+    from nextou_b200 import dense, ops
+    g = torch.Generator().manual_seed(cin + cskip)
+    dim = len(spatial)
+    osp = tuple(n * k for n, k in zip(spatial, ks))
+    low = torch.randn(B, cin, *spatial, generator=g).bfloat16()
+    skip = torch.randn(B, cskip, *osp, generator=g).bfloat16()
+    tc = (torch.nn.ConvTranspose3d if dim == 3 else torch.nn.ConvTranspose2d)(cin, cskip, ks, ks, bias=True)
+    with torch.no_grad():
+        tc.weight.copy_(tc.weight.bfloat16().float())
+    lr, sr = low.float().requires_grad_(True), skip.float().requires_grad_(True)
+    want = torch.cat((tc(lr), sr), 1)
+    dy = torch.randn(want.shape, generator=g).bfloat16()
+    want.backward(dy.float())
+    wg, bg = tc.weight.grad.clone(), tc.bias.grad.clone()
+    tc.zero_grad()
+    tcd = tc.to(DEV)
+    ld = ops.channels_last(low.to(DEV)).requires_grad_(True)
+    sd = ops.channels_last(skip.to(DEV)).requires_grad_(True)
+    with torch.autocast("cuda", dtype=torch.bfloat16):
+        got, gap = dense.up_cat(ld, tcd, sd)
+    ca, pa = gap
+    assert ca == cskip and pa == ops.pad8(cskip) and got.shape[1] == pa + cskip
+    gf = got.detach().float().cpu()
+    assert float(gf[:, ca:pa].abs().max()) == 0.0 if pa > ca else True
+    plain = torch.cat([gf[:, :ca], gf[:, pa:]], 1)
+    assert _rel(plain, want.detach()) < 6e-3
+    dyg = torch.zeros(B, pa + cskip, *osp)
+    dyg[:, :ca], dyg[:, pa:] = dy[:, :ca].float(), dy[:, ca:].float()
+    got.backward(dyg.to(DEV).to(got.dtype))
+    assert _rel(ld.grad.float().cpu(), lr.grad) < 6e-3
+    assert torch.equal(sd.grad.float().cpu(), dy[:, ca:].float())
+    assert _rel(tcd.weight.grad.cpu(), wg) < 1e-4 and _rel(tcd.bias.grad.cpu(), bg) < 1e-4
