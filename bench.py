@@ -311,11 +311,18 @@ def run_own(args):
             tensor_bound = name != "knn_topk"
             ach_tf = kt["flops"] / 1e12 / max(kt["ms"] * 1e-3, 1e-12)
             ach_gb = kt["bytes"] / 1e9 / max(kt["ms"] * 1e-3, 1e-12)
-            fams.append({"kernel": name, "launches_per_step": kt["launches"] / args.steps, "avg_launch_ms": per_launch_ms,
-                         "share_of_step": kt["ms"] / max(ms, 1e-9), "bound": "tensor" if tensor_bound else "hbm",
-                         "achieved": ach_tf if tensor_bound else ach_gb, "unit": "TFLOP/s" if tensor_bound else "GB/s",
-                         "frac": (ach_tf / tensor_peak) if tensor_bound else (ach_gb / hbm_peak),
-                         "hbm_gbs_algorithmic": ach_gb, "tflops_algorithmic": ach_tf})
+            fam = {"kernel": name, "launches_per_step": kt["launches"] / args.steps, "avg_launch_ms": per_launch_ms,
+                   "share_of_step": kt["ms"] / max(ms, 1e-9), "bound": "tensor" if tensor_bound else "hbm",
+                   "achieved": ach_tf if tensor_bound else ach_gb, "unit": "TFLOP/s" if tensor_bound else "GB/s",
+                   "frac": (ach_tf / tensor_peak) if tensor_bound else (ach_gb / hbm_peak),
+                   "hbm_gbs_algorithmic": ach_gb, "tflops_algorithmic": ach_tf}
+            if name == "knn_topk":
+                # the bit-exact contract keeps the distance GEMM on the fp32 FMA pipe: its own ceiling is
+                # 148 SMs x 128 FMA lanes x 2 x SM clock; `frac` above is SURVEY 8d's byte count over the HBM peak
+                fp32_peak = 148 * 128 * 2 * float(peaks.get("sm_max_mhz", 1965.0)) * 1e6 / 1e12
+                fam["fp32_fma_frac"] = ach_tf / fp32_peak
+                fam["mvox_per_s"] = 242256 * (kt["launches"] / args.steps / 14.0) / max(kt["ms"] / args.steps * 1e-3, 1e-12) / 1e6
+            fams.append(fam)
         fams.sort(key=lambda f: -f["share_of_step"])
         top = fams[0] if fams else {"kernel": None, "bound": "tensor", "achieved": 0.0, "unit": "TFLOP/s", "frac": 0.0,
                                     "avg_launch_ms": 0.0, "share_of_step": 0.0, "launches_per_step": 0}

@@ -299,6 +299,21 @@ int nextou_conv3d_ndhwc_strided_wgrad(const void* dy, long long ldy, const void*
 int nextou_pack_weight(const void* w, int dtype, int R, int Cc, int taps, int groups, int flip_b, void* A, int lda_c,
                        void* Bt, int ldb_c, void* stream);
 
+/* Inference forms: out = lrelu(acc * scale[N] + shift[N], slope).  An eval-mode BatchNorm (+ the
+ * LeakyReLU behind it) is folded into the epilogue of the layer that feeds it: scale = gamma * rsqrt(running_var + eps),
+ * shift = beta + (conv bias - running_mean) * scale — no statistics pass, no normalisation pass, no collective.
+ * scale == NULL means 1; slope == 1 disables the activation; the plain entry points are these with scale = NULL, slope = 1. */
+int nextou_gemm_bf16_tn_affine(const void* A, long long lda, const void* B, long long ldb, void* C, long long ldc, int M,
+                               int N, int K, const float* scale, const float* shift, float slope, int out_dtype,
+                               void* stream);
+int nextou_conv3d_ndhwc_halo_fwd_affine(const void* x, long long ldx, int B, int D, int H, int W, int Cin, const void* wpack,
+                                        int Cout, int kd, int kh, int kw, const float* scale, const float* shift, float slope,
+                                        void* out, long long ldo, int out_dtype, void* stream);
+int nextou_conv3d_ndhwc_strided_fwd_affine(const void* x, long long ldx, int B, int Di, int Hi, int Wi, int Cin,
+                                           const void* wpack, int Cout, int kd, int kh, int kw, int sd, int sh, int sw,
+                                           int pd, int ph, int pw, const float* scale, const float* shift, float slope,
+                                           void* out, long long ldo, int out_dtype, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -84,7 +84,7 @@ def _residual(mod, out_tok, short_tok, B, spatial):
 def _fc_bn(seq: nn.Sequential, tok: torch.Tensor, batch: int, act_slope=None, residual=None) -> torch.Tensor:
     """nn.Sequential(1x1 conv, norm) as used for fc1 / fc2 everywhere (ED:373-381, 710-720, 833-842), on token rows:
     a GEMM followed by the fused norm (+ LeakyReLU) (+ residual shortcut) kernel."""
-    return dense.norm_tokens(dense.linear_tokens(tok, seq[0]), seq[1], batch, act_slope, residual)
+    return dense.linear_norm_act_tokens(tok, seq[0], seq[1], batch, act_slope, residual)
 
 
 def _fc_bn_residual(mod, seq, tok, short_tok, B, spatial):

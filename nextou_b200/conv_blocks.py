@@ -97,7 +97,13 @@ class ConvDropoutNormReLU(nn.Module):
         while i < len(mods):
             m = mods[i]
             nxt = mods[i + 1] if i + 1 < len(mods) else None
-            if m is self.conv:
+            if m is self.conv and isinstance(nxt, (nn.modules.batchnorm._BatchNorm, nn.modules.instancenorm._InstanceNorm)):
+                # conv -> norm (-> LeakyReLU): one call, so that inference can fold the norm into the conv epilogue
+                act = mods[i + 2] if i + 2 < len(mods) else None
+                fuse = isinstance(act, nn.LeakyReLU)
+                tok, spatial = dense.conv_norm_act_tokens(tok, B, spatial, m, nxt, act.negative_slope if fuse else None)
+                i += 2 if fuse else 1
+            elif m is self.conv:
                 tok, spatial = dense.conv_tokens(tok, B, spatial, m)
             elif isinstance(m, (nn.modules.batchnorm._BatchNorm, nn.modules.instancenorm._InstanceNorm)):
                 fuse = isinstance(nxt, nn.LeakyReLU)

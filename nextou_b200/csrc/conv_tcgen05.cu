@@ -47,6 +47,8 @@ struct ConvParams {
   long long ldc;
   int out_dtype;
   const float* bias;
+  const float* scale;    // per-column scale [N] or NULL; out = lrelu(acc * scale + bias, slope)
+  float slope;
   int row32;             // every output row starts 32-byte aligned (256-bit stores)
   long long* dbg;        // optional [16] cycle counters written by CTA (0,0); NULL in production
 };
@@ -110,10 +112,10 @@ __global__ void __launch_bounds__(CV_THREADS, 1)
   uint64_t* tmem_empty = tmem_full + 2;        // [2]
   uint32_t* tmem_holder = reinterpret_cast<uint32_t*>(tmem_empty + 2);
 
-  __shared__ __align__(16) float sbias[256];
+  __shared__ __align__(16) float sbias[512];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int n0 = blockIdx.y * p.block_n;
-  stage_bias(sbias, p.bias, n0, p.N, p.block_n);
+  stage_bias(sbias, p.bias, n0, p.N, p.block_n, p.scale);
 
   if (warp == 0 && lane == 0) {
     prefetch_tmap(&tmA);
@@ -287,7 +289,7 @@ __global__ void __launch_bounds__(CV_THREADS, 1)
         __nv_bfloat16* dst = out_row >= 0 ? reinterpret_cast<__nv_bfloat16*>(p.C) + out_row * p.ldc + n0 : nullptr;
         const long long left = p.ldc - n0;
         epilogue_row_bf16(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * p.block_n), p.block_n, sbias, dst,
-                          (int)(left < p.block_n ? left : p.block_n), p.row32 != 0);
+                          (int)(left < p.block_n ? left : p.block_n), p.row32 != 0, p.slope);
       } else
       for (int c = 0; c < p.block_n; c += 16) {
         uint32_t raw[16];
@@ -298,8 +300,7 @@ __global__ void __launch_bounds__(CV_THREADS, 1)
 #pragma unroll
           for (int j = 0; j < 16; ++j) {
             const int col = n0 + c + j;
-            float x = __uint_as_float(raw[j]);
-            if (p.bias != nullptr && col < p.N) x += p.bias[col];
+            const float x = affine_act(raw[j], sbias[256 + c + j], sbias[c + j], p.slope);
             v[j] = col < p.N ? x : 0.f;
           }
           if (p.out_dtype == NEXTOU_BF16)
@@ -332,6 +333,15 @@ extern "C" void nextou_debug_set_conv_counters(long long* dev_buf) { g_conv_dbg 
 extern "C" int nextou_conv3d_ndhwc_halo_fwd(const void* x, long long ldx, int B, int D, int H, int W, int Cin,
                                             const void* wpack, int Cout, int kd, int kh, int kw, const float* bias,
                                             void* out, long long ldo, int out_dtype, void* stream) {
+  return nextou_conv3d_ndhwc_halo_fwd_affine(x, ldx, B, D, H, W, Cin, wpack, Cout, kd, kh, kw, nullptr, bias, 1.f, out, ldo,
+                                             out_dtype, stream);
+}
+
+// out = lrelu(conv(x) * scale[Cout] + shift[Cout], slope): inference form with the eval-mode norm (+ LeakyReLU) folded in
+extern "C" int nextou_conv3d_ndhwc_halo_fwd_affine(const void* x, long long ldx, int B, int D, int H, int W, int Cin,
+                                                   const void* wpack, int Cout, int kd, int kh, int kw, const float* scale,
+                                                   const float* bias, float slope, void* out, long long ldo, int out_dtype,
+                                                   void* stream) {
   NEXTOU_REQUIRE(x && wpack && out, "conv3d_ndhwc_halo_fwd: null pointer");
   NEXTOU_REQUIRE(B > 0 && D > 0 && H > 0 && W > 0 && Cin > 0 && Cout > 0, "conv3d_ndhwc_halo_fwd: bad shape");
   NEXTOU_REQUIRE((kh == 1 || kh == 3) && (kw == 1 || kw == 3) && kd % 2 == 1 && kd <= 7,
@@ -350,7 +360,7 @@ extern "C" int nextou_conv3d_ndhwc_halo_fwd(const void* x, long long ldx, int B,
   p.box_w = CV_TW + kw - 1;
   p.box_rows = p.box_w * (CV_TH + kh - 1);
   p.a_stage_bytes = (p.box_rows * 128 + 1023) / 1024 * 1024;
-  p.C = out; p.ldc = ldo; p.out_dtype = out_dtype; p.bias = bias; p.dbg = g_conv_dbg;
+  p.C = out; p.ldc = ldo; p.out_dtype = out_dtype; p.bias = bias; p.scale = scale; p.slope = slope; p.dbg = g_conv_dbg;
   p.row32 = (ldo % 16 == 0 && ((uintptr_t)out & 31) == 0) ? 1 : 0;
   const int taps = kd * kh * kw, inplane = kh * kw;
   const int cin_pad = p.kblocks * 64;

@@ -50,6 +50,8 @@ struct GemmParams {
   int zero_fill;       // no taps at all: write bias / zeros
   int row32;           // every output row starts 32-byte aligned (256-bit stores)
   int store_cols;      // columns [0, store_cols) of an output row are written (<= ldc: the row may continue with other data)
+  const float* scale;  // per-column scale [N] or NULL (= 1); out = lrelu(acc * scale + bias, slope)
+  float slope;
   signed char tap_dd[MAX_TAPS], tap_dh[MAX_TAPS], tap_dw[MAX_TAPS];
   short tap_wi[MAX_TAPS];
 };
@@ -69,10 +71,10 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1)
   uint64_t* tmem_full_bar = empty_bar + p.stages;
   uint32_t* tmem_base_holder = reinterpret_cast<uint32_t*>(tmem_full_bar + 1);
 
-  __shared__ __align__(16) float sbias[256];
+  __shared__ __align__(16) float sbias[512];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int n0 = blockIdx.y * p.block_n;
-  stage_bias(sbias, p.bias, n0, p.N, p.block_n);
+  stage_bias(sbias, p.bias, n0, p.N, p.block_n, p.scale);
 
   // output brick of this CTA
   int m0 = blockIdx.x * GEMM_BM;  // plain GEMM: first row
@@ -170,7 +172,7 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1)
       __nv_bfloat16* dst = out_row >= 0 ? reinterpret_cast<__nv_bfloat16*>(p.C) + out_row * p.ldc + n0 : nullptr;
       const long long left = p.store_cols - n0;
       epilogue_row_bf16(tmem_base + ((uint32_t)(q * 32) << 16), p.block_n, sbias, dst,
-                        (int)(left < p.block_n ? left : p.block_n), p.row32 != 0);
+                        (int)(left < p.block_n ? left : p.block_n), p.row32 != 0, p.slope);
     } else
     for (int c = 0; c < p.block_n; c += 16) {
       uint32_t raw[16];
@@ -186,8 +188,7 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1)
 #pragma unroll
         for (int j = 0; j < 16; ++j) {
           const int col = n0 + c + j;
-          float x = __uint_as_float(raw[j]);
-          if (p.bias != nullptr && col < p.N) x += p.bias[col];
+          const float x = affine_act(raw[j], sbias[256 + c + j], sbias[c + j], p.slope);
           v[j] = col < p.N ? x : 0.f;
         }
         if (n0 + c < p.store_cols) {
@@ -260,6 +261,8 @@ struct PGemmParams {
   int out_dtype;
   const float* bias;
   int row32;
+  const float* scale;
+  float slope;
 };
 
 __device__ __forceinline__ void mbar_arrive_cta(uint64_t* bar) {
@@ -283,10 +286,10 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1)
   uint64_t* tmem_empty = tmem_full + 2;   // [2]
   uint32_t* tmem_holder = reinterpret_cast<uint32_t*>(tmem_empty + 2);
 
-  __shared__ __align__(16) float sbias[256];
+  __shared__ __align__(16) float sbias[512];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int n0 = blockIdx.y * p.block_n;
-  stage_bias(sbias, p.bias, n0, p.N, p.block_n);
+  stage_bias(sbias, p.bias, n0, p.N, p.block_n, p.scale);
 
   if (warp == 0 && lane == 0) {
     prefetch_tmap(&tmA);
@@ -361,7 +364,7 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1)
         __nv_bfloat16* dst = row < p.M ? reinterpret_cast<__nv_bfloat16*>(p.C) + row * p.ldc + n0 : nullptr;
         const long long left = p.ldc - n0;
         epilogue_row_bf16(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * p.block_n), p.block_n, sbias, dst,
-                          (int)(left < p.block_n ? left : p.block_n), p.row32 != 0);
+                          (int)(left < p.block_n ? left : p.block_n), p.row32 != 0, p.slope);
       } else
       for (int c = 0; c < p.block_n; c += 16) {
         uint32_t raw[16];
@@ -372,8 +375,7 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1)
 #pragma unroll
           for (int j = 0; j < 16; ++j) {
             const int col = n0 + c + j;
-            float x = __uint_as_float(raw[j]);
-            if (p.bias != nullptr && col < p.N) x += p.bias[col];
+            const float x = affine_act(raw[j], sbias[256 + c + j], sbias[c + j], p.slope);
             v[j] = col < p.N ? x : 0.f;
           }
           if (p.out_dtype == NEXTOU_BF16)
@@ -398,6 +400,14 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1)
 // 16-byte aligned bases); C bf16 or fp32 with ldc % 8 == 0; columns [N, ldc) of C are zero-filled.
 extern "C" int nextou_gemm_bf16_tn(const void* A, long long lda, const void* B, long long ldb, void* C, long long ldc,
                                    int M, int N, int K, const float* bias, int out_dtype, void* stream) {
+  return nextou_gemm_bf16_tn_affine(A, lda, B, ldb, C, ldc, M, N, K, nullptr, bias, 1.f, out_dtype, stream);
+}
+
+// C = lrelu((A * B^T) * scale[N] + shift[N], slope): the inference form — an eval-mode BatchNorm (+ LeakyReLU) behind a
+// 1x1 convolution is folded into the epilogue (scale = gamma * rsqrt(var + eps), shift = beta + (bias - mean) * scale).
+extern "C" int nextou_gemm_bf16_tn_affine(const void* A, long long lda, const void* B, long long ldb, void* C, long long ldc,
+                                          int M, int N, int K, const float* scale, const float* bias, float slope,
+                                          int out_dtype, void* stream) {
   NEXTOU_REQUIRE(A && B && C, "gemm_bf16_tn: null pointer");
   NEXTOU_REQUIRE(M > 0 && N > 0 && K > 0, "gemm_bf16_tn: bad shape M=%d N=%d K=%d", M, N, K);
   NEXTOU_REQUIRE(lda % 8 == 0 && ldb % 8 == 0 && ldc % 8 == 0 && lda >= K && ldb >= K && ldc >= N,
@@ -411,7 +421,7 @@ extern "C" int nextou_gemm_bf16_tn(const void* A, long long lda, const void* B, 
   p.block_n = pick_block_n(N);
   p.tmem_cols = pow2_cols(2 * p.block_n);
   p.m_tiles = (M + GEMM_BM - 1) / GEMM_BM;
-  p.C = C; p.ldc = ldc; p.out_dtype = out_dtype; p.bias = bias;
+  p.C = C; p.ldc = ldc; p.out_dtype = out_dtype; p.bias = bias; p.scale = scale; p.slope = slope;
   p.row32 = (ldc % 16 == 0 && ((uintptr_t)C & 31) == 0) ? 1 : 0;
   const int a_bytes = GEMM_BM * GEMM_BK * 2, b_bytes = p.block_n * GEMM_BK * 2;
   const int budget = 200 * 1024;
@@ -471,9 +481,10 @@ static int launch_conv_general(const void* x, long long ldx, int B, int Di, int 
                                int w_taps_total, int Cout, const TapList& taps, int gd, int gh, int gw,   // i-grid
                                int es_d, int es_h, int es_w, int os_d, int os_h, int os_w, int oo_d, int oo_h, int oo_w,
                                int Do, int Ho, int Wo, const float* bias, void* out, long long ldo, int out_dtype,
-                               cudaStream_t stream, int store_cols = 0) {
+                               cudaStream_t stream, int store_cols = 0, const float* scale = nullptr, float slope = 1.f) {
   GemmParams p = {};
   p.store_cols = store_cols;
+  p.scale = scale; p.slope = slope;
   p.M = 0; p.N = Cout; p.kblocks = (Cin + GEMM_BK - 1) / GEMM_BK; p.taps = taps.n;
   p.last_ksteps = (Cin - (p.kblocks - 1) * GEMM_BK + 15) / 16;
   p.zero_fill = taps.n == 0 ? 1 : 0;
@@ -543,6 +554,15 @@ extern "C" int nextou_conv3d_ndhwc_strided_fwd(const void* x, long long ldx, int
                                                const void* wpack, int Cout, int kd, int kh, int kw, int sd, int sh, int sw,
                                                int pd, int ph, int pw, const float* bias, void* out, long long ldo,
                                                int out_dtype, void* stream) {
+  return nextou_conv3d_ndhwc_strided_fwd_affine(x, ldx, B, Di, Hi, Wi, Cin, wpack, Cout, kd, kh, kw, sd, sh, sw, pd, ph, pw, nullptr,
+                                                bias, 1.f, out, ldo, out_dtype, stream);
+}
+
+// out = lrelu(conv(x) * scale[Cout] + shift[Cout], slope): inference form with the eval-mode norm (+ LeakyReLU) folded in
+extern "C" int nextou_conv3d_ndhwc_strided_fwd_affine(const void* x, long long ldx, int B, int Di, int Hi, int Wi, int Cin,
+                                                      const void* wpack, int Cout, int kd, int kh, int kw, int sd, int sh,
+                                                      int sw, int pd, int ph, int pw, const float* scale, const float* bias,
+                                                      float slope, void* out, long long ldo, int out_dtype, void* stream) {
   int rc = conv_common_checks("conv3d_ndhwc_strided_fwd", x, wpack, out, ldx, Cin, ldo, Cout, out_dtype);
   if (rc) return rc;
   NEXTOU_REQUIRE(B > 0 && Di > 0 && Hi > 0 && Wi > 0, "conv3d_ndhwc_strided_fwd: bad shape");
@@ -559,7 +579,7 @@ extern "C" int nextou_conv3d_ndhwc_strided_fwd(const void* x, long long ldx, int
         taps.dd[t] = a - pd; taps.dh[t] = b - ph; taps.dw[t] = c - pw; taps.wi[t] = t;
       }
   return launch_conv_general(x, ldx, B, Di, Hi, Wi, Cin, wpack, kd * kh * kw, Cout, taps, Do, Ho, Wo, sd, sh, sw, 1, 1, 1, 0, 0,
-                             0, Do, Ho, Wo, bias, out, ldo, out_dtype, (cudaStream_t)stream);
+                             0, Do, Ho, Wo, bias, out, ldo, out_dtype, (cudaStream_t)stream, 0, scale, slope);
 }
 
 // Stride-1 'same' convolution (odd kernels): the per-tap variant of nextou_conv3d_ndhwc_halo_fwd.

@@ -188,23 +188,35 @@ __device__ __forceinline__ void st_global_128(void* p, uint32_t a, uint32_t b, u
 
 // The CTA's bias slice in shared memory: sbias[i] = bias[n0 + i] for n0 + i < N, else 0 (so padded columns come out as
 // exact zeros: their accumulators are zero because the weight rows beyond N are zero-filled by TMA).
-__device__ __forceinline__ void stage_bias(float* sbias, const float* bias, int n0, int N, int block_n) {
-  for (int i = threadIdx.x; i < block_n; i += blockDim.x) sbias[i] = (bias != nullptr && n0 + i < N) ? bias[n0 + i] : 0.f;
+// sbias is float[512]: [0, 256) the additive term, [256, 512) the per-column scale (1 unless an inference-time norm is folded in)
+__device__ __forceinline__ void stage_bias(float* sbias, const float* bias, int n0, int N, int block_n,
+                                           const float* scale = nullptr) {
+  for (int i = threadIdx.x; i < block_n; i += blockDim.x) {
+    sbias[i] = (bias != nullptr && n0 + i < N) ? bias[n0 + i] : 0.f;
+    sbias[256 + i] = (scale != nullptr && n0 + i < N) ? scale[n0 + i] : 1.f;
+  }
 }
 
 // bf16 epilogue of ONE accumulator row (this thread's TMEM lane): columns [0, block_n) of the CTA's N tile are read
 // 32 at a time, biased, rounded and stored with 128/256-bit stores.  All lanes must call it (the TMEM loads are
 // warp-collective); dst == nullptr skips the stores (row outside the volume).  ncols = number of columns that exist in
 // the output row from n0 on (min(block_n, ldc - n0), a multiple of 8); row32 = every row start is 32-byte aligned.
+// out = lrelu(acc * scale[col] + shift[col], slope): scale = 1, slope = 1 is the plain "+ bias" epilogue of training; an
+// eval-mode BatchNorm (+ LeakyReLU) behind the layer is folded in through scale / shift / slope (inference path)
+__device__ __forceinline__ float affine_act(uint32_t acc, float scale, float shift, float slope) {
+  const float t = fmaf(__uint_as_float(acc), scale, shift);
+  return t > 0.f ? t : t * slope;
+}
 template <int CHUNK>
 __device__ __forceinline__ void epilogue_store_chunk(const uint32_t* raw, const float* sb, __nv_bfloat16* dst, int c, int ncols,
-                                                     bool row32) {
+                                                     bool row32, float slope) {
   uint32_t w[CHUNK / 2];
 #pragma unroll
   for (int g = 0; g < CHUNK / 4; ++g) {
     const float4 b4 = *reinterpret_cast<const float4*>(sb + c + 4 * g);
-    w[2 * g] = pack_bf16x2(__uint_as_float(raw[4 * g]) + b4.x, __uint_as_float(raw[4 * g + 1]) + b4.y);
-    w[2 * g + 1] = pack_bf16x2(__uint_as_float(raw[4 * g + 2]) + b4.z, __uint_as_float(raw[4 * g + 3]) + b4.w);
+    const float4 s4 = *reinterpret_cast<const float4*>(sb + 256 + c + 4 * g);
+    w[2 * g] = pack_bf16x2(affine_act(raw[4 * g], s4.x, b4.x, slope), affine_act(raw[4 * g + 1], s4.y, b4.y, slope));
+    w[2 * g + 1] = pack_bf16x2(affine_act(raw[4 * g + 2], s4.z, b4.z, slope), affine_act(raw[4 * g + 3], s4.w, b4.w, slope));
   }
   if (dst == nullptr) return;
   if (c + CHUNK <= ncols) {
@@ -228,19 +240,19 @@ __device__ __forceinline__ void epilogue_store_chunk(const uint32_t* raw, const 
 }
 
 __device__ __forceinline__ void epilogue_row_bf16(uint32_t tmem_row, int block_n, const float* sbias, __nv_bfloat16* dst,
-                                                  int ncols, bool row32) {
+                                                  int ncols, bool row32, float slope) {
   int c = 0;
   for (; c + 32 <= block_n; c += 32) {
     uint32_t raw[32];
     tmem_ld32(tmem_row + (uint32_t)c, raw);
     tmem_ld_wait();
-    epilogue_store_chunk<32>(raw, sbias, dst, c, ncols, row32);
+    epilogue_store_chunk<32>(raw, sbias, dst, c, ncols, row32, slope);
   }
   if (c < block_n) {   // block_n is a multiple of 16
     uint32_t raw[16];
     tmem_ld16(tmem_row + (uint32_t)c, raw);
     tmem_ld_wait();
-    epilogue_store_chunk<16>(raw, sbias, dst, c, ncols, row32);
+    epilogue_store_chunk<16>(raw, sbias, dst, c, ncols, row32, slope);
   }
 }
 

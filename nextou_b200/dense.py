@@ -126,6 +126,70 @@ def conv_transpose_nd(x, weight, bias, stride):
 
 
 # ------------------------------------------------------------------------------------------------------
+# inference: eval-mode BatchNorm (+ LeakyReLU) folded into the epilogue of the layer that feeds it
+# ------------------------------------------------------------------------------------------------------
+FOLD_EVAL_NORM = True
+
+
+def _foldable(tok: torch.Tensor, layer: torch.nn.Module, norm_mod) -> bool:
+    """True when `norm_mod` is a BatchNorm that normalises with its RUNNING statistics and nothing needs a gradient: then
+    y = lrelu(layer(x) * scale + shift) in one kernel, without a statistics or a normalisation pass (and without collectives)."""
+    return (FOLD_EVAL_NORM and isinstance(norm_mod, torch.nn.modules.batchnorm._BatchNorm) and not norm_mod.training
+            and norm_mod.running_mean is not None and not torch.is_grad_enabled() and _bf16_path(tok)
+            and getattr(layer, "padding_mode", "zeros") == "zeros")
+
+
+def _folded_affine(layer, bn):
+    inv = torch.rsqrt(bn.running_var.float() + bn.eps)
+    scale = inv if bn.weight is None else inv * bn.weight.float()
+    shift = -bn.running_mean.float() * scale
+    if layer.bias is not None:
+        shift = shift + layer.bias.float() * scale
+    if bn.bias is not None:
+        shift = shift + bn.bias.float()
+    return scale, shift
+
+
+def linear_norm_act_tokens(tok, conv, norm_mod, batch: int, act_slope: Optional[float] = None, residual=None):
+    """1x1 conv (plain or grouped) -> norm (-> LeakyReLU) (-> + residual) on token rows; one GEMM launch in inference."""
+    if _foldable(tok, conv, norm_mod):
+        stats["tcgen05.linear_folded_norm"] += 1
+        scale, shift = _folded_affine(conv, norm_mod)
+        xb = ops.tma_ready_bf16(tok)
+        w2d = conv.weight.reshape(conv.weight.shape[0], -1)
+        N, K = w2d.shape[0], w2d.shape[1] * conv.groups
+        wp, _ = ops.pack_weight_pair(w2d, conv=False, groups=conv.groups, want_b=False)
+        y = ops.gemm_bf16_tn(xb, wp[:, :K], shift, n=N, scale=scale, slope=1.0 if act_slope is None else act_slope)[:, :N]
+        return y if residual is None else ops.add_tokens(y, residual)
+    h = grouped_linear_tokens(tok, conv) if conv.groups > 1 else linear_tokens(tok, conv)
+    return norm_tokens(h, norm_mod, batch, act_slope, residual)
+
+
+def conv_norm_act_tokens(tok, batch: int, spatial: Sequence[int], conv, norm_mod, act_slope: Optional[float] = None):
+    """k x k (x k) conv -> norm (-> LeakyReLU) of a StackedConvBlocks block; one conv launch in inference."""
+    stride, ks = tuple(conv.stride), tuple(conv.kernel_size)
+    plain = all(d == 1 for d in conv.dilation) and conv.groups == 1 and not isinstance(conv.padding, str) \
+        and all(1 <= s <= 4 for s in stride) and len(ks) in (2, 3) and int(torch.tensor(ks).prod()) <= 64 \
+        and getattr(conv, "in_gap", None) is None
+    if plain and _foldable(tok, conv, norm_mod):
+        stats["tcgen05.conv_folded_norm"] += 1
+        scale, shift = _folded_affine(conv, norm_mod)
+        slope = 1.0 if act_slope is None else act_slope
+        xb = ops.tma_ready_bf16(tok)
+        cout, cin = conv.weight.shape[:2]
+        wp, _ = ops.pack_weight_pair(conv.weight, conv=True, want_b=False)
+        same = all(s == 1 for s in stride) and all(k % 2 == 1 for k in ks) and tuple(conv.padding) == tuple(k // 2 for k in ks)
+        if same:
+            y = ops.conv_ndhwc_bf16(xb, batch, spatial, cin, wp, cout, ks, shift, scale=scale, slope=slope)
+            return y[:, :cout], tuple(spatial)
+        y, osp = ops.conv_strided_fwd_bf16(xb, batch, spatial, cin, wp, cout, ks, stride, tuple(conv.padding), shift,
+                                           scale=scale, slope=slope)
+        return y[:, :cout], osp
+    h, osp = conv_tokens(tok, batch, spatial, conv)
+    return norm_tokens(h, norm_mod, batch, act_slope), osp
+
+
+# ------------------------------------------------------------------------------------------------------
 # normalisation (+ LeakyReLU), csrc/norm.cu
 # ------------------------------------------------------------------------------------------------------
 def _sync_world(bn) -> int:

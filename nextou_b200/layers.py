@@ -92,7 +92,13 @@ class BasicConv(Seq):
         while i < len(mods):
             m = mods[i]
             nxt = mods[i + 1] if i + 1 < len(mods) else None
-            if isinstance(m, (nn.Conv2d, nn.Conv3d)):
+            if isinstance(m, (nn.Conv2d, nn.Conv3d)) and isinstance(nxt, (nn.modules.batchnorm._BatchNorm,
+                                                                          nn.modules.instancenorm._InstanceNorm)):
+                act = mods[i + 2] if i + 2 < len(mods) else None
+                slope = act.negative_slope if isinstance(act, nn.LeakyReLU) else None
+                tok = dense.linear_norm_act_tokens(tok, m, nxt, batch, slope)
+                i += 2 if slope is not None else 1
+            elif isinstance(m, (nn.Conv2d, nn.Conv3d)):
                 tok = dense.grouped_linear_tokens(tok, m) if m.groups > 1 else dense.linear_tokens(tok, m)
             elif isinstance(m, (nn.modules.batchnorm._BatchNorm, nn.modules.instancenorm._InstanceNorm)):
                 slope = nxt.negative_slope if isinstance(nxt, nn.LeakyReLU) else None

@@ -555,7 +555,8 @@ def seg_loss(logits, target, w_ce, w_dice, w_ti, batch_dice, do_bg, smooth, ddp,
 # tcgen05 GEMM engine (csrc/gemm_tcgen05.cu)
 # ----------------------------------------------------------------------------------------------
 def gemm_bf16_tn(a: torch.Tensor, b: torch.Tensor, bias: Optional[torch.Tensor] = None, n: Optional[int] = None,
-                 out_dtype=torch.bfloat16, out: Optional[torch.Tensor] = None) -> torch.Tensor:
+                 out_dtype=torch.bfloat16, out: Optional[torch.Tensor] = None, scale: Optional[torch.Tensor] = None,
+                 slope: float = 1.0) -> torch.Tensor:
     """out[M, ldc] = a[M, K] @ b[N, K]^T (+ bias); a, b bf16 with unit inner stride and row pitches that are multiples of
     8 elements; returns the PADDED [M, pad8(N)] matrix (columns >= N are zero), or writes into `out`."""
     _need_cuda(a, b)
@@ -565,9 +566,11 @@ def gemm_bf16_tn(a: torch.Tensor, b: torch.Tensor, bias: Optional[torch.Tensor] 
     if out is None:
         out = torch.empty((M, pad8(N)), device=a.device, dtype=out_dtype)
     bias32 = None if bias is None else bias.detach().float().contiguous()
+    scale32 = None if scale is None else scale.detach().float().contiguous()
     with _lib.timed("gemm_tcgen05", 2 * M * (K + N) + 2 * N * K, 2 * M * N * K):
-        check(_lib.lib().nextou_gemm_bf16_tn(ptr(a), ll(a.stride(0)), ptr(b), ll(b.stride(0)), ptr(out), ll(out.stride(0)), M,
-                                             N, K, ptr(bias32), dtype_code(out), cstream()), "nextou_gemm_bf16_tn")
+        check(_lib.lib().nextou_gemm_bf16_tn_affine(ptr(a), ll(a.stride(0)), ptr(b), ll(b.stride(0)), ptr(out), ll(out.stride(0)),
+                                                    M, N, K, ptr(scale32), ptr(bias32), cf(slope), dtype_code(out), cstream()),
+              "nextou_gemm_bf16_tn")
     return out
 
 
@@ -615,7 +618,7 @@ CONV_HALO = True  # use the halo-reuse kernel (csrc/conv_tcgen05.cu) whenever kh
 
 def conv_ndhwc_bf16(x_tok: torch.Tensor, batch: int, spatial: Sequence[int], cin: int, wpack: torch.Tensor, cout: int,
                     ksize: Sequence[int], bias: Optional[torch.Tensor] = None, out_dtype=torch.bfloat16,
-                    halo: Optional[bool] = None) -> torch.Tensor:
+                    halo: Optional[bool] = None, scale: Optional[torch.Tensor] = None, slope: float = 1.0) -> torch.Tensor:
     """Stride-1 'same' convolution on a token-major bf16 volume [B*prod(spatial), ldx] -> padded [.., pad8(cout)]."""
     _need_cuda(x_tok, wpack)
     assert x_tok.dtype == torch.bfloat16 and x_tok.stride(1) == 1 and wpack.dtype == torch.bfloat16
@@ -626,15 +629,24 @@ def conv_ndhwc_bf16(x_tok: torch.Tensor, batch: int, spatial: Sequence[int], cin
     D, H, W = sp
     out = torch.empty((batch * D * H * W, pad8(cout)), device=x_tok.device, dtype=out_dtype)
     bias32 = None if bias is None else bias.detach().float().contiguous()
+    scale32 = None if scale is None else scale.detach().float().contiguous()
     use_halo = (CONV_HALO if halo is None else halo) and ks[1] in (1, 3) and ks[2] in (1, 3)
-    fn = _lib.lib().nextou_conv3d_ndhwc_halo_fwd if use_halo else _lib.lib().nextou_conv3d_ndhwc_fwd
     V = batch * D * H * W
     # algorithmic work / traffic: 2*V*Cin*Cout*taps flops; input + output + weights once, bf16
     flops = 2 * V * cin * cout * ks[0] * ks[1] * ks[2]
     nbytes = 2 * V * (cin + cout) + 2 * cin * cout * ks[0] * ks[1] * ks[2]
+    L = _lib.lib()
     with _lib.timed("conv_halo_tcgen05" if use_halo else "conv_pertap_tcgen05", nbytes, flops):
-        check(fn(ptr(x_tok), ll(x_tok.stride(0)), batch, D, H, W, cin, ptr(wpack), cout, ks[0], ks[1], ks[2], ptr(bias32),
-                 ptr(out), ll(out.stride(0)), dtype_code(out), cstream()), "nextou_conv3d_ndhwc_fwd")
+        if use_halo:
+            check(L.nextou_conv3d_ndhwc_halo_fwd_affine(ptr(x_tok), ll(x_tok.stride(0)), batch, D, H, W, cin, ptr(wpack), cout,
+                                                        ks[0], ks[1], ks[2], ptr(scale32), ptr(bias32), cf(slope), ptr(out),
+                                                        ll(out.stride(0)), dtype_code(out), cstream()),
+                  "nextou_conv3d_ndhwc_halo_fwd")
+        else:
+            check(L.nextou_conv3d_ndhwc_strided_fwd_affine(ptr(x_tok), ll(x_tok.stride(0)), batch, D, H, W, cin, ptr(wpack), cout,
+                                                           ks[0], ks[1], ks[2], 1, 1, 1, ks[0] // 2, ks[1] // 2, ks[2] // 2,
+                                                           ptr(scale32), ptr(bias32), cf(slope), ptr(out), ll(out.stride(0)),
+                                                           dtype_code(out), cstream()), "nextou_conv3d_ndhwc_fwd")
     return out
 
 
@@ -650,7 +662,8 @@ def _geom3(spatial, *lists):
 
 def conv_strided_fwd_bf16(x_tok: torch.Tensor, batch: int, spatial: Sequence[int], cin: int, wpack: torch.Tensor, cout: int,
                           ksize: Sequence[int], stride: Sequence[int], padding: Sequence[int],
-                          bias: Optional[torch.Tensor] = None, out_dtype=torch.bfloat16):
+                          bias: Optional[torch.Tensor] = None, out_dtype=torch.bfloat16,
+                          scale: Optional[torch.Tensor] = None, slope: float = 1.0):
     """Strided convolution on a token-major bf16 volume -> (padded [rows_out, pad8(cout)] matrix, output spatial shape)."""
     _need_cuda(x_tok, wpack)
     assert x_tok.dtype == torch.bfloat16 and x_tok.stride(1) == 1 and wpack.dtype == torch.bfloat16
@@ -662,9 +675,11 @@ def conv_strided_fwd_bf16(x_tok: torch.Tensor, batch: int, spatial: Sequence[int
     taps = ks[0] * ks[1] * ks[2]
     with _lib.timed("conv_pertap_tcgen05", 2 * batch * sp[0] * sp[1] * sp[2] * cin + 2 * V * cout + 2 * cin * cout * taps,
                     2 * V * cin * cout * taps):
-        check(_lib.lib().nextou_conv3d_ndhwc_strided_fwd(ptr(x_tok), ll(x_tok.stride(0)), batch, *sp, cin, ptr(wpack), cout, *ks,
-                                                         *st, *pd, ptr(bias32), ptr(out), ll(out.stride(0)), dtype_code(out),
-                                                         cstream()), "nextou_conv3d_ndhwc_strided_fwd")
+        scale32 = None if scale is None else scale.detach().float().contiguous()
+        check(_lib.lib().nextou_conv3d_ndhwc_strided_fwd_affine(ptr(x_tok), ll(x_tok.stride(0)), batch, *sp, cin, ptr(wpack), cout,
+                                                                *ks, *st, *pd, ptr(scale32), ptr(bias32), cf(slope), ptr(out),
+                                                                ll(out.stride(0)), dtype_code(out), cstream()),
+              "nextou_conv3d_ndhwc_strided_fwd")
     return out, tuple(osp[3 - len(spatial):])
 
 

@@ -277,3 +277,51 @@ def test_up_cat_matches_transpose_conv_plus_cat(B, spatial, cin, cskip, ks):
     assert _rel(ld.grad.float().cpu(), lr.grad) < 6e-3
     assert torch.equal(sd.grad.float().cpu(), dy[:, ca:].float())
     assert _rel(tcd.weight.grad.cpu(), wg) < 1e-4 and _rel(tcd.bias.grad.cpu(), bg) < 1e-4
+
+
+@pytest.mark.parametrize("kind", ["conv3", "conv_strided", "linear", "grouped"])
+def test_folded_eval_norm_matches_fp32_reference(kind):
+    """Inference path: an eval-mode BatchNorm (+ LeakyReLU) folded into the conv / GEMM epilogue equals
+    lrelu(bn_eval(layer(x))) in fp32 on the same bf16-valued operands (only the final bf16 rounding differs)."""
+    from nextou_b200 import dense, ops
+    g = torch.Generator().manual_seed(11)
+    B, spatial = 1, (6, 10, 12)
+    if kind == "conv3":
+        layer = torch.nn.Conv3d(33, 66, 3, 1, 1, bias=True)
+    elif kind == "conv_strided":
+        layer = torch.nn.Conv3d(33, 66, 3, 2, 1, bias=True)
+    elif kind == "linear":
+        layer = torch.nn.Conv3d(132, 264, 1, bias=True)
+    else:
+        layer = torch.nn.Conv3d(264, 264, 1, bias=True, groups=6)
+    cin, cout = layer.in_channels, layer.out_channels
+    bn = torch.nn.BatchNorm3d(cout)
+    with torch.no_grad():
+        layer.weight.copy_(layer.weight.bfloat16().float())
+        bn.weight.uniform_(0.5, 1.5, generator=g); bn.bias.uniform_(-0.5, 0.5, generator=g)
+        bn.running_mean.uniform_(-0.3, 0.3, generator=g); bn.running_var.uniform_(0.5, 2.0, generator=g)
+    bn.eval()
+    x = torch.randn(B, cin, *spatial, generator=g).bfloat16()
+    with torch.no_grad():
+        want = F.leaky_relu(bn(layer(x.float())), 0.01)
+    layer, bn = layer.to(DEV), bn.to(DEV)
+    tok = _tok_of(x).to(DEV)[:, :cin]
+    dense.stats.clear()
+    with torch.no_grad(), torch.autocast("cuda", dtype=torch.bfloat16):
+        if kind.startswith("conv"):
+            y, osp = dense.conv_norm_act_tokens(tok, B, spatial, layer, bn, 0.01)
+        else:
+            y, osp = dense.linear_norm_act_tokens(tok, layer, bn, B, 0.01), spatial
+    assert dense.stats["tcgen05.conv_folded_norm"] + dense.stats["tcgen05.linear_folded_norm"] == 1
+    assert tuple(osp) == tuple(want.shape[2:])
+    got = _vol_of(y, B, cout, osp)
+    assert _rel(got, want) < 4e-3, _rel(got, want)
+    # training mode (or autograd on) must NOT fold
+    dense.stats.clear()
+    bn.train()
+    with torch.no_grad(), torch.autocast("cuda", dtype=torch.bfloat16):
+        if kind.startswith("conv"):
+            dense.conv_norm_act_tokens(tok, B, spatial, layer, bn, 0.01)
+        else:
+            dense.linear_norm_act_tokens(tok, layer, bn, B, 0.01)
+    assert dense.stats["tcgen05.conv_folded_norm"] + dense.stats["tcgen05.linear_folded_norm"] == 0

@@ -210,3 +210,49 @@ def test_full_size_3d_forward_backward_smoke():
         assert int(idx.min()) >= 0 and int(idx.max()) < m
         srt = idx.sort(-1).values
         assert bool((srt[..., 1:] != srt[..., :-1]).all())
+
+
+def test_inference_forward_folds_batch_norm():
+    """Eval-mode forward under bf16 autocast (what nnU-Net's sliding-window predictor calls, deep supervision off): every
+    BatchNorm is folded into the producing conv / GEMM epilogue (no statistics / normalisation pass).  A randomly
+    initialised NexToU is chaotic end to end in bf16 (neighbour lists and max-unpool positions flip on rounding, see
+    DESIGN.md 5), so numerical parity is asserted where it is well defined: each conv stack against the oracle's eval-mode
+    blocks on the SAME input (per-layer folding parity: test_gpu_gemm.py::test_folded_eval_norm_matches_fp32_reference)."""
+    from nextou_b200 import dense
+    from nextou_b200.conv_blocks import StackedConvBlocks
+    cfg = H.MINI3D
+    npz = H.golden_model("model_mini3d_reference.npz")
+    model = H.build_product(cfg)
+    H.load_golden_into(model, npz)
+    model = model.to(DEV).train()
+    g = torch.Generator().manual_seed(42)
+    x = torch.randn(1, 1, *cfg["patch"], generator=g)
+    # give the running statistics the batch statistics of this input (momentum 1), as a trained network would have: with
+    # the defaults (0, 1) a random network amplifies its input ~3000x in eval mode
+    for m in model.modules():
+        if isinstance(m, torch.nn.modules.batchnorm._BatchNorm):
+            m.momentum = 1.0
+    with torch.no_grad():
+        model(x.to(DEV))
+    sd = H.full_state_dict_for_oracle(model)
+    model.eval()
+    model.decoder.deep_supervision = False
+    caps = []
+    for name, mod in model.named_modules():
+        if name.startswith("encoder.stages") and isinstance(mod, StackedConvBlocks):
+            mod.register_forward_hook(lambda m, i, o, name=name: caps.append((name, m, i[0].detach(), o.detach())))
+    dense.stats.clear()
+    with torch.no_grad(), torch.autocast("cuda", dtype=torch.bfloat16):
+        y = model(x.to(DEV))
+    assert tuple(y.shape) == (1, cfg["num_classes"], *cfg["patch"]) and bool(torch.isfinite(y).all())
+    assert dense.stats["tcgen05.conv_folded_norm"] >= 10 and dense.stats["tcgen05.linear_folded_norm"] >= 30
+    assert dense.stats["native.batch_norm"] == 0                     # no statistics / normalisation pass for BatchNorm
+    dim = len(cfg["patch"])
+    assert len(caps) >= 4
+    for name, mod, inp, out in caps:
+        want = inp.float().cpu()
+        with torch.no_grad():
+            for i in range(len(mod.convs)):
+                want = TO._conv_block(want, sd, f"{name}.convs.{i}", dim, tuple(mod.convs[i].conv.stride), False)
+        rel = ((out.float().cpu() - want).norm() / want.norm()).item()
+        assert rel <= 1e-2, (name, rel)
