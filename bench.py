@@ -308,7 +308,11 @@ def run_own(args):
             if kt["launches"] == 0:
                 continue
             per_launch_ms = kt["ms"] / kt["launches"]
-            tensor_bound = name != "knn_topk"
+            # roofline side by arithmetic intensity of the family's ALGORITHMIC work: tensor-bound above the
+            # ridge (measured bf16 peak / measured HBM peak ~ 209 FLOP/B), HBM-bound below; the kNN is classed by its byte
+            # count as 8d asks (its fp32-FMA fraction is reported next to it)
+            ridge = tensor_peak * 1e12 / (hbm_peak * 1e9)
+            tensor_bound = name != "knn_topk" and kt["flops"] >= ridge * max(kt["bytes"], 1)
             ach_tf = kt["flops"] / 1e12 / max(kt["ms"] * 1e-3, 1e-12)
             ach_gb = kt["bytes"] / 1e9 / max(kt["ms"] * 1e-3, 1e-12)
             fam = {"kernel": name, "launches_per_step": kt["launches"] / args.steps, "avg_launch_ms": per_launch_ms,
