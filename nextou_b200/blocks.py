@@ -304,10 +304,10 @@ class Grapher(nn.Module):
 
     def forward(self, x):
         B, spatial = x.shape[0], tuple(x.shape[2:])
-        h = _fc_bn(self.fc1, ops.as_tokens(x), B)
+        tok, short = ops.fork_tokens(ops.as_tokens(x))
+        h = _fc_bn(self.fc1, tok, B)
         rp = _resized_relative_pos(self.relative_pos, _prod(spatial), self.n, self.r, self.ndim)
-        h = _fc_bn(self.fc2, self.graph_conv.forward_tokens(h, B, spatial, rp), B)
-        return _residual(self, h, x, B, spatial)
+        return _fc_bn_residual(self, self.fc2, self.graph_conv.forward_tokens(h, B, spatial, rp), short, B, spatial)
 
 
 # ------------------------------------------------------------------------------------------------------

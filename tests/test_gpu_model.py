@@ -256,3 +256,19 @@ def test_inference_forward_folds_batch_norm():
                 want = TO._conv_block(want, sd, f"{name}.convs.{i}", dim, tuple(mod.convs[i].conv.stride), False)
         rel = ((out.float().cpu() - want).norm() / want.norm()).item()
         assert rel <= 1e-2, (name, rel)
+
+
+@pytest.mark.parametrize("precision", ["fp32", "bf16"])
+def test_plain_grapher_api_smoke(precision):
+    """The reference's plain `Grapher` (ED:553-632) is never built by NexToU but is part of the module surface: it must run
+    forward + backward (fc1 -> kNN graph conv -> fc2 + residual) and return finite values of the input's shape."""
+    from nextou_b200.blocks import Grapher
+    torch.manual_seed(0)
+    m = Grapher(12, kernel_size=5, dilation=1, conv="mr", act="leakyrelu", norm="batch", n=64).to(DEV).train()
+    x = torch.randn(2, 12, 4, 4, 4, device=DEV, requires_grad=True)
+    with torch.autocast("cuda", dtype=torch.bfloat16, enabled=precision == "bf16"):
+        y = m(x)
+    assert y.shape == x.shape
+    y.float().square().mean().backward()
+    assert bool(torch.isfinite(y).all()) and x.grad is not None and bool(torch.isfinite(x.grad).all())
+    assert all(p.grad is not None and bool(torch.isfinite(p.grad).all()) for p in m.parameters() if p.requires_grad)
