@@ -157,3 +157,33 @@ def test_error_conventions_match_reference():
         NexToU_Encoder(1, [32, 32], 5, 8, nn.Conv1d, 3, [[1]] + [[2]] * 4, 2)
     with pytest.raises(AssertionError):
         H.build_product(dict(H.MINI2D, kernels=[[3, 3]] * 4))
+
+
+def test_fork_tokens_gradient_sum_cpu():
+    """ops.fork_tokens is pure tensor plumbing (no kernel): the two aliases' gradients are summed by the package, in the
+    padded token layout when both arrive in it, and the result equals autograd's own accumulation."""
+    import torch
+    from nextou_b200 import ops
+    g = torch.Generator().manual_seed(0)
+    rows, C = 64, 33
+    x = torch.randn(rows, ops.pad8(C), generator=g)[:, :C].requires_grad_(True)
+    w1 = torch.randn(rows, ops.pad8(C), generator=g)[:, :C]          # padded-pitch gradient
+    w2 = torch.randn(rows, C, generator=g)                           # dense gradient
+    a, b = ops.fork_tokens(x)
+    seen = []
+    h = x.register_hook(lambda t: seen.append(tuple(t.stride())))
+    ((a * w1).sum() + (b * w2).sum()).backward()
+    h.remove()
+    assert torch.allclose(x.grad, w1 + w2)
+    assert seen and seen[0][0] % 8 == 0 and seen[0][1] == 1          # summed into a channel-padded buffer
+    x.grad = None
+    a, b = ops.fork_tokens(x)
+    ((a * w1).sum() + (b * w1).sum()).backward()                     # both padded: one pass over the physical rows
+    assert torch.allclose(x.grad, 2 * w1)
+    x.grad = None
+    a, b = ops.fork_tokens(x)
+    (a * w1).sum().backward()                                        # unused alias: its gradient is None, not zeros
+    assert torch.equal(x.grad, w1)
+    with torch.no_grad():
+        p, q = ops.fork_tokens(x)
+    assert p is x and q is x                                         # no autograd: no-op
