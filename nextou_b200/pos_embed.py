@@ -56,11 +56,47 @@ def get_3d_relative_pos_embed(embed_dim, grid_size):
     return _relative(get_3d_sincos_pos_embed(embed_dim, grid_size))
 
 
+_TABLE_MEMO = {}
+
+
+def _relative_pos_table(channels: int, n: int, n_reduced: int, ndim: int) -> torch.Tensor:
+    """The (1, n, n_reduced) fp32 table of ED:731-742 / 869-880, computed with the reference's own arithmetic (float64
+    numpy matmul -> fp32 -> bicubic resize -> negate).  The Pool-GNN tables of 3d_fullres_nextou need a 10 648 x 10 648
+    float64 matmul each (0.9 GB, ~2 s): identical (channels, n, n_reduced) requests — encoder and decoder graphers of the
+    same stage — share one computation in-process, and NEXTOU_RELPOS_CACHE=<dir> keeps the tables on disk across runs
+    (init cost).  The cached bytes are the computed bytes, so the tables stay bit-identical."""
+    import os
+    key = (int(channels), int(n), int(n_reduced), int(ndim))
+    if key in _TABLE_MEMO:
+        return _TABLE_MEMO[key]
+    cache_dir = os.environ.get("NEXTOU_RELPOS_CACHE")
+    path = os.path.join(cache_dir, "relpos_c%d_n%d_m%d_d%d.pt" % key) if cache_dir else None
+    t = None
+    if path and os.path.exists(path):
+        try:
+            t = torch.load(path, map_location="cpu")
+            if tuple(t.shape) != (1, n, n_reduced) or t.dtype != torch.float32:
+                t = None
+        except Exception:
+            t = None
+    if t is None:
+        grid = int(n ** (1 / ndim))
+        fn = get_3d_relative_pos_embed if ndim == 3 else get_2d_relative_pos_embed
+        t = torch.from_numpy(np.float32(fn(channels, grid))).unsqueeze(0).unsqueeze(1)
+        t = -F.interpolate(t, size=(n, n_reduced), mode="bicubic", align_corners=False).squeeze(1)
+        if path:
+            try:
+                os.makedirs(cache_dir, exist_ok=True)
+                tmp = path + ".tmp%d" % os.getpid()
+                torch.save(t, tmp)
+                os.replace(tmp, path)
+            except OSError:
+                pass
+    _TABLE_MEMO[key] = t
+    return t
+
+
 def relative_pos_parameter(channels: int, n: int, n_reduced: int, ndim: int) -> torch.nn.Parameter:
     """Frozen (1, n, n_reduced) table, already negated: it is ADDED to the distances (ED:731-742, 869-880).
     The base grid is int(n ** (1/ndim)) per axis — a reference quirk kept on purpose (int(343 ** (1/3)) == 6)."""
-    grid = int(n ** (1 / ndim))
-    fn = get_3d_relative_pos_embed if ndim == 3 else get_2d_relative_pos_embed
-    t = torch.from_numpy(np.float32(fn(channels, grid))).unsqueeze(0).unsqueeze(1)
-    t = F.interpolate(t, size=(n, n_reduced), mode="bicubic", align_corners=False)
-    return torch.nn.Parameter(-t.squeeze(1), requires_grad=False)
+    return torch.nn.Parameter(_relative_pos_table(channels, n, n_reduced, ndim).clone(), requires_grad=False)

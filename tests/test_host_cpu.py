@@ -187,3 +187,29 @@ def test_fork_tokens_gradient_sum_cpu():
     with torch.no_grad():
         p, q = ops.fork_tokens(x)
     assert p is x and q is x                                         # no autograd: no-op
+
+
+def test_relative_pos_table_memo_and_disk_cache(tmp_path, monkeypatch):
+    """In-process memo and NEXTOU_RELPOS_CACHE return the very bytes of a fresh computation (tables stay bit-identical)."""
+    import numpy as np
+    import torch
+    import torch.nn.functional as F
+    from nextou_b200 import pos_embed as PE
+    def fresh(c, n, m, d):
+        grid = int(n ** (1 / d))
+        fn = PE.get_3d_relative_pos_embed if d == 3 else PE.get_2d_relative_pos_embed
+        t = torch.from_numpy(np.float32(fn(c, grid))).unsqueeze(0).unsqueeze(1)
+        return -F.interpolate(t, size=(n, m), mode="bicubic", align_corners=False).squeeze(1)
+    PE._TABLE_MEMO.clear()
+    monkeypatch.setenv("NEXTOU_RELPOS_CACHE", str(tmp_path))
+    a = PE.relative_pos_parameter(12, 168, 168, 3)
+    assert torch.equal(a.data, fresh(12, 168, 168, 3)) and not a.requires_grad
+    assert (tmp_path / "relpos_c12_n168_m168_d3.pt").exists()
+    b = PE.relative_pos_parameter(12, 168, 168, 3)                    # memo hit: equal values, independent storage
+    assert torch.equal(a, b) and a.data_ptr() != b.data_ptr()
+    PE._TABLE_MEMO.clear()
+    c = PE.relative_pos_parameter(12, 168, 168, 3)                    # disk hit
+    assert torch.equal(a, c)
+    d2 = PE.relative_pos_parameter(8, 64, 16, 2)
+    assert torch.equal(d2.data, fresh(8, 64, 16, 2))
+    PE._TABLE_MEMO.clear()
