@@ -193,6 +193,46 @@ def gen_model(r, cfg, fname, dim):
     np.savez_compressed(os.path.join(OUT, fname), **out)
 
 
+def gen_model_eval(r, cfg, fname):
+    """Inference fixture: the reference in eval mode (deep supervision off) on the same seeded input.  With the default
+    running statistics (0, 1) a randomly initialised NexToU amplifies its input ~3000x in eval mode and is chaotic, so the
+    running statistics are first set to the batch statistics of this input (momentum 1, one train-mode forward), as a
+    trained network would have.  Weights are the seed-0 initialisation of model_mini3d_reference.npz (not stored again):
+    only the running statistics, the eval-mode neighbour lists and the (sub-sampled) logits are saved."""
+    m = ref_shims.build_ref_3d(patch=cfg["patch"], feats=cfg["feats"], num_classes=cfg["num_classes"], seed=0)
+    for mod in m.modules():
+        if isinstance(mod, nn.modules.batchnorm._BatchNorm):
+            mod.momentum = 1.0
+    g = torch.Generator().manual_seed(42)
+    x = torch.randn(1, 1, *cfg["patch"], generator=g)
+    m.train()
+    with torch.no_grad():
+        torch.manual_seed(0)
+        m(x)
+    m.eval()
+    m.decoder.deep_supervision = False
+    caps = []
+    _hook_modules(m, r, caps)
+    with torch.no_grad():
+        torch.manual_seed(0)
+        y = m(x)
+    out = {}
+    for k, v in m.state_dict().items():
+        if k.startswith("decoder.encoder.") or ".all_modules." in k:
+            continue
+        if k.endswith(("running_mean", "running_var")):
+            out["sd/" + k] = v.detach().numpy()
+    knn_i = 0
+    for kind, mod, inp, o in caps:
+        if kind == "knn":
+            out[f"knn/{knn_i}"] = o[0].numpy().astype(np.int16)
+            knn_i += 1
+    y = y.detach()
+    out["out/0"] = y.reshape(-1)[::97].numpy()
+    out["out_shape"] = np.asarray(y.shape)
+    np.savez_compressed(os.path.join(OUT, fname), **out)
+
+
 def main():
     os.makedirs(OUT, exist_ok=True)
     r = ref_shims.load_reference()
@@ -201,6 +241,7 @@ def main():
     gen_bti(r)
     gen_model(r, MINI, "model_mini3d_reference.npz", 3)
     gen_model(r, MINI2D, "model_mini2d_reference.npz", 2)
+    gen_model_eval(r, MINI, "model_mini3d_reference_eval.npz")
     for f in sorted(os.listdir(OUT)):
         print(f, os.path.getsize(os.path.join(OUT, f)) // 1024, "KiB")
 

@@ -128,3 +128,45 @@ def test_torch_oracle_model_matches_reference_golden(fname, cfg):
             assert (gmine - gref).abs().max().item() <= 2e-2 * scale + 1e-6, (k, (gmine - gref).abs().max(), scale)
             checked += 1
     assert checked > 20
+
+
+def test_torch_oracle_eval_forward_matches_reference_golden():
+    """Inference path of the oracle (eval-mode BatchNorm with running statistics, deep supervision off) against the
+    UNMODIFIED reference in eval mode (tests/golden/model_mini3d_reference_eval.npz, generated by
+    oracle/make_golden.py::gen_model_eval): this pins the checker the GPU inference tests compare with."""
+    cfg = H.MINI3D
+    base = H.golden_model("model_mini3d_reference.npz")
+    ev = H.golden_model("model_mini3d_reference_eval.npz")
+    sd = H.golden_state_dict(base)
+    n_stats = 0
+    for k in ev.files:
+        if k.startswith("sd/"):
+            assert k[3:] in sd, k
+            sd[k[3:]] = torch.from_numpy(ev[k])            # running statistics after the momentum-1 forward
+            n_stats += 1
+    assert n_stats > 100
+    dim = len(cfg["patch"])
+    plan = TO.derive_plan(cfg["patch"], cfg["strides"])
+    for s in range(plan["gnn_from"], len(cfg["feats"])):
+        st = plan["stages"][s]
+        C = cfg["feats"][s]
+        n_pool = int(np.prod(st["shape"])) // int(np.prod(st["pool_size"]))
+        n_win = int(np.prod(st["window"]))
+        prefixes = [f"encoder.stages.{s}.0"]
+        j = len(cfg["feats"]) - 2 - s
+        if j >= 0:
+            prefixes.append(f"decoder.stages.{j}")
+        for p in prefixes:
+            sd[f"{p}.1.blocks.0.0.relative_pos"] = TO.relative_pos_table(C, n_pool, n_pool // st["r"] ** dim, dim)
+            sd[f"{p}.2.blocks.0.0.relative_pos"] = TO.relative_pos_table(C, n_win, n_win, dim)
+    g = torch.Generator().manual_seed(42)
+    x = torch.randn(1, 1, *cfg["patch"], generator=g)
+    replay = TO.ReplayKnn(H.golden_knn_list(ev), tol=1e-4)
+    with torch.no_grad():
+        y = TO.nextou_forward(sd, x, cfg["patch"], cfg["strides"], deep_supervision=False, training=False, knn=replay)
+    assert replay.pos == len(replay.recorded) == 14
+    assert tuple(y.shape) == tuple(int(v) for v in ev["out_shape"])
+    ref = torch.from_numpy(ev["out/0"])
+    got = y.reshape(-1)[::97]
+    # same bound as the train-mode fixture: teacher-forced graphs, the max-unpool positions may still flip on 1e-7
+    assert torch.allclose(got, ref, rtol=1e-3, atol=2e-3), (got - ref).abs().max()
