@@ -60,7 +60,11 @@ def check(lib):
 
 if __name__ == "__main__":
     import os
+    import sys
     here = os.path.dirname(os.path.abspath(__file__))
-    lib = ctypes.CDLL(os.path.join(here, "..", "..", "lib", "libnextou_b200.so"))
+    # default: the product library once the kernel has been moved into csrc/; or a standalone draft build given on the command
+    # line:  nvcc -gencode arch=compute_100a,code=sm_100a -O3 -std=c++17 --expt-relaxed-constexpr -Xcompiler -fPIC
+    #        -I include -shared nextou_b200/csrc/drafts/conv_fold_tcgen05.cu nextou_b200/csrc/core.cu -o _libdraft.so
+    lib = ctypes.CDLL(sys.argv[1] if len(sys.argv) > 1 else os.path.join(here, "..", "..", "lib", "libnextou_b200.so"))
     lib.nextou_last_error.restype = ctypes.c_char_p
     check(lib)
