@@ -18,7 +18,7 @@
 
 namespace nextou {
 
-constexpr int BTI_MAX_INTER = 32;
+constexpr int BTI_MAX_INTER = 128;   // interactions per LAUNCH (by-value table); longer lists run in chunks that OR into the map
 struct BtiTable {
   uint32_t a[BTI_MAX_INTER];
   uint32_t c[BTI_MAX_INTER];
@@ -47,13 +47,21 @@ __global__ void bti_argmax_ce_kernel(const T* __restrict__ logits, long long sb,
   if (v >= V) return;
   const T* p = logits + (long long)b * sb + v * sv;
   float best = to_f(p[0]);
+  for (int c = 1; c < NC; ++c) best = fmaxf(best, to_f(p[(long long)c * sc]));
+  // The reference takes argmax(softmax(x)) (bti_loss.py:132-134), not argmax(x): fp32 softmax is not injective — logits
+  // closer than ~3e-8 to the maximum get the same exp(x - max) = 1.0f, and torch.argmax then returns the LOWEST such
+  // index.  Evaluate the same fp32 expression (exp(x - max) / sum in class order, first maximum wins).
+  float e[32];
+  float s = 0.f;
+  for (int c = 0; c < NC; ++c) {
+    e[c] = expf(to_f(p[(long long)c * sc]) - best);
+    s += e[c];
+  }
+  float pbest = -1.f;
   int bi = 0;
-  for (int c = 1; c < NC; ++c) {
-    const float x = to_f(p[(long long)c * sc]);
-    if (x > best) {  // first maximum wins, like torch.argmax on the (monotone) softmax, bti_loss.py:132-134
-      best = x;
-      bi = c;
-    }
+  for (int c = 0; c < NC; ++c) {
+    const float pc = __fdiv_rn(e[c], s);
+    if (pc > pbest) { pbest = pc; bi = c; }
   }
   labels[(long long)b * V + v] = (uint8_t)bi;
   if (ce) {
@@ -66,7 +74,7 @@ __global__ void bti_argmax_ce_kernel(const T* __restrict__ logits, long long sb,
 }
 
 __global__ void bti_critical_kernel(const uint8_t* __restrict__ labels, int D, int H, int W, int rd, int r, int cross,
-                                    BtiTable tab, uint8_t* __restrict__ crit) {
+                                    BtiTable tab, int accumulate, uint8_t* __restrict__ crit) {
   const int x = blockIdx.x * blockDim.x + threadIdx.x;
   const int y = blockIdx.y * blockDim.y + threadIdx.y;
   const int bz = blockIdx.z;  // b * D + z
@@ -95,7 +103,12 @@ __global__ void bti_critical_kernel(const uint8_t* __restrict__ labels, int D, i
     const bool nearA = (nb & tab.a[t]) != 0, nearC = (nb & tab.c[t]) != 0;
     c = c || (nearC && inA) || (nearA && inC);
   }
-  crit[(long long)bz * H * W + (long long)y * W + x] = c ? 1 : 0;
+  uint8_t* out = crit + (long long)bz * H * W + (long long)y * W + x;
+  if (accumulate) {           // later chunk of a long interaction list: OR into the map of the earlier chunks
+    if (c) *out = 1;
+  } else {
+    *out = c ? 1 : 0;
+  }
 }
 
 constexpr int SUM_THREADS = 256;
@@ -177,25 +190,39 @@ extern "C" int nextou_bti_critical_map(const uint8_t* labels, int B, int D, int 
                                        uint8_t* crit, void* stream) {
   NEXTOU_REQUIRE(labels && crit, "bti_critical_map: null pointer");
   NEXTOU_REQUIRE(B > 0 && D > 0 && H > 0 && W > 0 && (long long)B * D <= 65535, "bti_critical_map: bad shape");
-  NEXTOU_REQUIRE(n_inter >= 0 && n_inter <= BTI_MAX_INTER, "bti_critical_map: %d interactions (max %d)", n_inter, BTI_MAX_INTER);
+  NEXTOU_REQUIRE(n_inter >= 0 && (n_inter == 0 || (mask_a_host && mask_c_host && inclusion_host)), "bti_critical_map: bad interaction table");
   NEXTOU_REQUIRE(dim == 2 || dim == 3, "bti_critical_map: dim=%d", dim);
   NEXTOU_REQUIRE(dim == 3 || D == 1, "bti_critical_map: dim=2 needs D=1");
   const bool box = (dim == 3 && connectivity == 26) || (dim == 2 && connectivity == 8);
   const bool cross = (dim == 3 && connectivity == 6) || (dim == 2 && connectivity == 4);
   NEXTOU_REQUIRE(box || cross, "bti_critical_map: connectivity %d invalid for dim %d (bti_loss.py:57-71)", connectivity, dim);
   NEXTOU_REQUIRE(min_thick >= 1, "bti_critical_map: min_thick=%d", min_thick);
-  BtiTable tab;
-  tab.n = n_inter;
-  for (int t = 0; t < n_inter; ++t) {
-    tab.a[t] = mask_a_host[t];
-    tab.c[t] = inclusion_host[t] ? ~(mask_c_host[t] | mask_a_host[t]) : mask_c_host[t];  // bti_loss.py:91-95
-  }
   const int r = box ? min_thick : 1;
   dim3 block(32, 8);
   dim3 grid((W + 31) / 32, (H + 7) / 8, B * D);
-  bti_critical_kernel<<<grid, block, 0, (cudaStream_t)stream>>>(labels, D, H, W, dim == 3 ? r : 0, r, cross ? 1 : 0,
-                                                                tab, crit);
-  return check_launch("bti_critical_kernel");
+  // The reference has no limit on the number of interactions (nnUNetTrainer_NexToU_TI builds all C(n, 2) label pairs: 78 for
+  // the 13 Synapse organs).  Duplicate (A, C) pairs cannot change the OR; the rest goes out in chunks of BTI_MAX_INTER.
+  BtiTable tab;
+  tab.n = 0;
+  int launched = 0;
+  for (int t = 0; t <= n_inter; ++t) {
+    if (t < n_inter) {
+      const uint32_t a = mask_a_host[t];
+      const uint32_t c = inclusion_host[t] ? ~(mask_c_host[t] | mask_a_host[t]) : mask_c_host[t];  // bti_loss.py:91-95
+      bool dup = false;
+      for (int j = 0; j < tab.n && !dup; ++j) dup = tab.a[j] == a && tab.c[j] == c;
+      if (!dup) { tab.a[tab.n] = a; tab.c[tab.n] = c; ++tab.n; }
+    }
+    if (tab.n == BTI_MAX_INTER || (t == n_inter && (tab.n > 0 || launched == 0))) {
+      bti_critical_kernel<<<grid, block, 0, (cudaStream_t)stream>>>(labels, D, H, W, dim == 3 ? r : 0, r, cross ? 1 : 0,
+                                                                    tab, launched > 0 ? 1 : 0, crit);
+      int rc = check_launch("bti_critical_kernel");
+      if (rc) return rc;
+      ++launched;
+      tab.n = 0;
+    }
+  }
+  return NEXTOU_OK;
 }
 
 extern "C" size_t nextou_bti_masked_sum_workspace_bytes(int B) { return sizeof(double) * (size_t)B * 296; }

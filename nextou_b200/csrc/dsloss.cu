@@ -41,15 +41,23 @@ __global__ void __launch_bounds__(DSL_THREADS)
     const T* p = logits + (long long)b * sb + v * sv;
     float x[NC];
     float mx = -INFINITY;
-    int arg = 0;
 #pragma unroll
     for (int c = 0; c < NC; ++c) {
       x[c] = to_f(p[(long long)c * sc]);
-      if (x[c] > mx) { mx = x[c]; arg = c; }
+      mx = fmaxf(mx, x[c]);
     }
     float s = 0.f;
 #pragma unroll
-    for (int c = 0; c < NC; ++c) { x[c] = __expf(x[c] - mx); s += x[c]; }
+    for (int c = 0; c < NC; ++c) { x[c] = expf(x[c] - mx); s += x[c]; }
+    // label = argmax(softmax(x)) like the reference (bti_loss.py:132-134): fp32 softmax ties (logits within ~3e-8 of the
+    // maximum) resolve to the lowest index — same expression as csrc/bti.cu::bti_argmax_ce_kernel
+    float pbest = -1.f;
+    int arg = 0;
+#pragma unroll
+    for (int c = 0; c < NC; ++c) {
+      const float pc = __fdiv_rn(x[c], s);
+      if (pc > pbest) { pbest = pc; arg = c; }
+    }
     const float inv = 1.f / s;
     const int t = dsl_target(target, tcode, (long long)b * V + v);
     float pt = 0.f;

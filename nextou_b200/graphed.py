@@ -61,6 +61,7 @@ class GraphedTrainStep:
         self.model, self.loss_fn, self.optimizer, self.reducer = model, loss_fn, optimizer, reducer
         self.clip, self.autocast_dtype = clip_grad_norm, autocast_dtype
         self.params = [p for g in optimizer.param_groups for p in g["params"] if p.requires_grad]
+        self._pin_hyper_parameters(device)
         self.static_x = torch.empty(example_input.shape, dtype=example_input.dtype, device=device)
         self.static_t = [torch.empty(t.shape, dtype=t.dtype, device=device) for t in example_targets]
         self._load(example_input, example_targets)
@@ -83,6 +84,45 @@ class GraphedTrainStep:
                 reducer.zero_grad()
             self.static_loss = self._body()
         self.launches_per_step = launch_count() - n0   # kernels of libnextou_b200.so recorded in the graph
+
+    # ---- optimizer hyper-parameters vs. a captured step ----------------------------------------------------------
+    # A CUDA graph bakes every host scalar of optimizer.step() into its kernels.  nnU-Net's PolyLRScheduler assigns
+    # `param_groups[i]['lr'] = new_lr` every epoch, so the learning rate must not be such a scalar: it is turned into a
+    # 1-element device tensor (torch's fused SGD / Adam and nextou_b200.optim.FusedSGD read it on the device) that is
+    # re-filled whenever the scheduler has put a new number into the group.  Any other hyper-parameter that changes after
+    # the capture (momentum, weight decay, ...) cannot be patched into the graph: that raises instead of silently training
+    # with the old value.
+    def _pin_hyper_parameters(self, device):
+        self._lr_tensors, self._hyper = [], []
+        for g in self.optimizer.param_groups:
+            lr = g.get("lr")
+            dev_lr_ok = bool(g.get("fused")) or getattr(self.optimizer, "device_lr", False)
+            if isinstance(lr, torch.Tensor):
+                t = lr if lr.is_cuda else None
+            elif dev_lr_ok and lr is not None:
+                t = torch.tensor(float(lr), device=device, dtype=torch.float32)
+                g["lr"] = t
+            else:
+                t = None
+            self._lr_tensors.append(t)
+            self._hyper.append({k: v for k, v in g.items() if k not in ("params", "lr") and isinstance(v, (int, float, bool, type(None)))})
+        self._lr_baked = [None if t is not None else g.get("lr") for t, g in zip(self._lr_tensors, self.optimizer.param_groups)]
+
+    def _sync_hyper_parameters(self):
+        for i, g in enumerate(self.optimizer.param_groups):
+            t, lr = self._lr_tensors[i], g.get("lr")
+            if t is not None:
+                if lr is not t:                       # a scheduler assigned a new value: move it into the captured tensor
+                    t.fill_(float(lr))
+                    g["lr"] = t
+            elif lr != self._lr_baked[i]:
+                raise NextouError(f"param group {i}: lr changed from {self._lr_baked[i]} to {lr} after the step was captured, and "
+                                  f"{type(self.optimizer).__name__} bakes a host-scalar lr into the CUDA graph; use a fused "
+                                  "optimizer (device-tensor lr) or build a new GraphedTrainStep")
+            for k, v in self._hyper[i].items():
+                if g.get(k) != v:
+                    raise NextouError(f"param group {i}: {k} changed from {v} to {g.get(k)} after the step was captured; "
+                                      "build a new GraphedTrainStep")
 
     def _zero(self):
         if self.reducer is not None:
@@ -112,6 +152,7 @@ class GraphedTrainStep:
                 s.copy_(t, non_blocking=True)
 
     def __call__(self, x: torch.Tensor, targets: Sequence[torch.Tensor]) -> torch.Tensor:
+        self._sync_hyper_parameters()
         self._load(x, targets)
         self.graph.replay()
         return self.static_loss

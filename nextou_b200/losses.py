@@ -58,7 +58,7 @@ class _InteractionLoss(nn.Module):
             self.interaction_list.append([True, inc[0], inc[1]])
         for exc in exclusion:
             self.interaction_list.append([False, exc[0], exc[1]])
-        self._table = None
+        self._bits_memo = {}
 
     def set_kernel(self):
         """Connectivity structuring element (BTI:52-73); only its shape parameters reach the CUDA kernel."""
@@ -81,12 +81,23 @@ class _InteractionLoss(nn.Module):
 
     def interaction_table(self):
         """(maskA, maskC, inclusion flag) lists, one entry per interaction, bit c = class c."""
-        if self._table is None or len(self._table[0]) != len(self.interaction_list):
-            ma = [_class_bits(it[1], self._singleton) for it in self.interaction_list]
-            mc = [_class_bits(it[2], self._singleton) for it in self.interaction_list]
-            inc = [1 if it[0] else 0 for it in self.interaction_list]
-            self._table = (ma, mc, inc)
-        return self._table
+        # rebuilt from the public `interaction_list` on every call, like the reference re-reads it (BTI:84-98): a few
+        # dozen small ints; label tensors are converted once and remembered by identity (they may live on the device)
+        memo = self._bits_memo
+        def bits(v):
+            if not isinstance(v, torch.Tensor):
+                return _class_bits(v, self._singleton)
+            key = (id(v), v._version)
+            hit = memo.get(key)
+            if hit is None or hit[0] is not v:
+                hit = memo[key] = (v, _class_bits(v, self._singleton))
+            return hit[1]
+        ma = [bits(it[1]) for it in self.interaction_list]
+        mc = [bits(it[2]) for it in self.interaction_list]
+        inc = [1 if it[0] else 0 for it in self.interaction_list]
+        if len(memo) > 4 * max(len(self.interaction_list), 8):
+            memo.clear()
+        return (ma, mc, inc)
 
     def critical_voxels_map(self, P: torch.Tensor) -> torch.Tensor:
         """P: discrete segmentation (b, 1, *spatial) or (b, *spatial) -> double map like the reference (BTI:76-117)."""

@@ -508,11 +508,16 @@ class _SegLoss(torch.autograd.Function):
             check(L.nextou_bti_masked_sum(ptr(ce), ptr(crit), B, ll(V), ptr(ws), ptr(ti), cstream()), "nextou_bti_masked_sum")
         # per-class algebra on [B, NC] doubles (MemoryEfficientSoftDiceLoss.forward; CrossEntropyLoss mean reduction)
         P, I, G = sums[:, :NC], sums[:, NC:2 * NC], sums[:, 2 * NC:3 * NC]
+        grad_world = 1.0
         if batch_dice:
             if ddp and torch.distributed.is_available() and torch.distributed.is_initialized():
                 pig = sums[:, :3 * NC].sum(0, keepdim=True)
-                torch.distributed.all_reduce(pig)  # AllGatherGrad + sum: gradients stay with the local voxels
+                torch.distributed.all_reduce(pig)
                 P, I, G = pig[:, :NC], pig[:, NC:2 * NC], pig[:, 2 * NC:]
+                # upstream gathers with AllGatherGrad, whose backward all-reduces (SUM) the incoming gradient: every rank's
+                # loss depends on every rank's sums, so the local derivative is world_size x d(dice)/d(sums); DDP's gradient
+                # averaging then yields the gradient of the global-batch Dice (same as torch.distributed.nn all_gather)
+                grad_world = float(torch.distributed.get_world_size())
             else:
                 P, I, G = P.sum(0, keepdim=True), I.sum(0, keepdim=True), G.sum(0, keepdim=True)
         first = 0 if do_bg else 1
@@ -523,8 +528,8 @@ class _SegLoss(torch.autograd.Function):
         total = sums[:, 3 * NC].sum() * (w_ce / (B * V)) - (num / den)[:, first:].sum() * (w_dice / n_terms)
         if ti is not None:
             total = total + w_ti * ti
-        dI = -2.0 * w_dice / n_terms / den
-        dP = torch.where(raw >= 1e-8, w_dice / n_terms * num / (den * den), torch.zeros_like(den))
+        dI = -2.0 * w_dice * grad_world / n_terms / den
+        dP = torch.where(raw >= 1e-8, w_dice * grad_world / n_terms * num / (den * den), torch.zeros_like(den))
         coef = torch.stack([dI, dP]).expand(2, B, NC).clone()
         coef[:, :, :first] = 0
         ctx.save_for_backward(x, y, crit if crit is not None else labels, coef)
@@ -940,6 +945,25 @@ def sync_moments(sums: torch.Tensor, count: int, eps: float, group=None):
     return mean.float(), invstd.float(), unbiased.float(), n
 
 
+_EQUAL_ROWS = {}
+
+
+def _equal_rows(rows: int, group, world: int) -> bool:
+    """True when every rank of `group` normalises the same number of rows (nnU-Net DDP splits the batch unevenly when the
+    batch size is not divisible by the world size).  One tiny all-gather per (group, rows), remembered afterwards."""
+    import torch.distributed as dist
+    key = (id(group), rows, world)
+    hit = _EQUAL_ROWS.get(key)
+    if hit is None:
+        if torch.cuda.is_current_stream_capturing():
+            raise NextouError("SyncBatchNorm: run one eager step before capturing (row counts are compared across ranks once)")
+        mine = torch.tensor([rows], device="cuda", dtype=torch.int64)
+        every = [torch.empty_like(mine) for _ in range(world)]
+        dist.all_gather(every, mine, group=group)
+        hit = _EQUAL_ROWS[key] = all(int(t) == rows for t in every)
+    return hit
+
+
 class _SyncNormAct(torch.autograd.Function):
     """Train-mode SyncBatchNorm (+ LeakyReLU): statistics over the rows of ALL ranks.  Forward: local (sum x, sum x^2) ->
     all-reduce -> normalise; backward: local (sum dy', sum dy' xhat) -> all-reduce -> dx with the global sums and row count
@@ -965,14 +989,17 @@ class _SyncNormAct(torch.autograd.Function):
         y = torch.empty_like(xf)
         check(L.nextou_norm_apply_cv(ptr(xf), dtype_code(xf), P, C, ll(T), 1, ptr(mean), ptr(invstd), ptr(g32), ptr(b32),
                                      cf(slope), ptr(y), cstream()), "nextou_norm_apply")
-        ctx.save_for_backward(xf, mean, invstd, g32, b32)
+        # backward divides the all-reduced sums by the number of rows normalised together.  Equal row counts on every rank
+        # (one patch each: checked ONCE per (group, rows) on the host) -> T * world; else the true count from the all-reduce
+        fix = None if _equal_rows(T, group, world) else ((T * world) / n).float().reshape(1)
+        ctx.save_for_backward(xf, mean, invstd, g32, b32, fix)
         ctx.meta = (C, P, T, slope, gamma is not None, None if gamma is None else gamma.dtype, group, world)
         return y[:, :C]
 
     @staticmethod
     def backward(ctx, dy):
         import torch.distributed as dist
-        xf, mean, invstd, g32, b32 = ctx.saved_tensors
+        xf, mean, invstd, g32, b32, fix = ctx.saved_tensors
         C, P, T, slope, affine, pdt, group, world = ctx.meta
         L = _lib.lib()
         dyf = _rows_like(dy, T, C, P, xf.dtype)
@@ -985,6 +1012,8 @@ class _SyncNormAct(torch.autograd.Function):
         if affine:
             dbeta, dgamma = local[0, :C].clone().to(pdt), local[1, :C].clone().to(pdt)   # `sums` is reduced in place below
         dist.all_reduce(sums, op=dist.ReduceOp.SUM, group=group)
+        if fix is not None:
+            sums.mul_(fix)      # uneven batch split: sums / n_true == (sums * T * world / n_true) / (T * world)
         dx = torch.empty_like(xf)
         dxsum = torch.empty((1, P), device=xf.device, dtype=torch.float32)
         check(L.nextou_norm_bwd_apply(ptr(xf), ptr(dyf), dtype_code(xf), P, C, ll(T), 1, ll(T * world), ptr(mean), ptr(invstd),

@@ -120,7 +120,7 @@ int oracle_bti_critical(const uint8_t* labels, int B, int D, int H, int W, int d
   const int rd = dim == 3 ? r : 0;
   const long V = (long)D * H * W;
   memset(out, 0, (size_t)B * V);
-  if (n_inter > 32 || n_inter < 0) return -2;
+  if (n_inter < 0) return -2;   /* no upper bound: the reference loops over a python list (bti_loss.py:84) */
 #pragma omp parallel for schedule(static)
   for (long bz = 0; bz < (long)B * D; ++bz) {
     const int b = (int)(bz / D), z = (int)(bz % D);

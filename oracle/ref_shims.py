@@ -1,9 +1,10 @@
-"""TEST INFRASTRUCTURE — loads the UNMODIFIED reference files from /root/reference.
+"""TEST INFRASTRUCTURE — loads the UNMODIFIED reference files from /root/reference, or from the byte-identical
+archive that oracle/stage_ref.py stages under oracle/_ref/ (git-ignored; it travels to the GPU box, where /root/reference
+does not exist, so that `bench.py --impl reference` times the reference's own code there).
 
-Only usable in the build container (the GPU box has no /root/reference).  It is
-used by `oracle/make_golden.py` (to generate the committed fixtures under
-tests/golden/) and by the `-m "not gpu"` tests that pin the `oracle/` restatement
-against the real reference.  Product code (nextou_b200/) never imports this.
+It is used by `oracle/make_golden.py` (to generate the committed fixtures under
+tests/golden/), by the `-m "not gpu"` tests that pin the `oracle/` restatement
+against the real reference, and by bench.py's reference arm.  Product code (nextou_b200/) never imports this.
 
 The reference is an overlay on nnU-Net v2 and imports un-vendored packages
 (`nnunetv2`, `dynamic_network_architectures`, `timm`).  We register stand-ins for
@@ -22,11 +23,21 @@ import types
 import torch
 from torch import nn
 
-REF_ROOT = os.environ.get("NEXTOU_REFERENCE_ROOT", "/root/reference")
+def _resolve_root():
+    env = os.environ.get("NEXTOU_REFERENCE_ROOT")
+    if env:
+        return env
+    if os.path.isfile("/root/reference/network_architecture/NexToU.py"):
+        return "/root/reference"
+    from . import stage_ref
+    return stage_ref.unpack()          # byte-identical archive staged by oracle/stage_ref.py (hash-checked), or None
+
+
+REF_ROOT = _resolve_root()
 
 
 def reference_available() -> bool:
-    return os.path.isfile(os.path.join(REF_ROOT, "network_architecture", "NexToU.py"))
+    return REF_ROOT is not None and os.path.isfile(os.path.join(REF_ROOT, "network_architecture", "NexToU.py"))
 
 
 # --------------------------------------------------------------------------------------
@@ -135,6 +146,49 @@ class _InitWeights_He:
                 module.bias = nn.init.constant_(module.bias, 0)
 
 
+class _RobustCrossEntropyLoss(nn.CrossEntropyLoss):
+    def forward(self, input, target):
+        if target.ndim == input.ndim:
+            assert target.shape[1] == 1
+            target = target[:, 0]
+        return super().forward(input, target.long())
+
+
+class _SoftDiceLoss(nn.Module):
+    def __init__(self, apply_nonlin=None, batch_dice=False, do_bg=True, smooth=1., ddp=True, clip_tp=None):
+        super().__init__()
+        self.do_bg, self.batch_dice, self.apply_nonlin, self.smooth, self.ddp = do_bg, batch_dice, apply_nonlin, smooth, ddp
+
+    def forward(self, x, y, loss_mask=None):
+        if self.apply_nonlin is not None:
+            x = self.apply_nonlin(x)
+        axes = tuple(range(2, x.ndim))
+        with torch.no_grad():
+            y_onehot = torch.zeros(x.shape, device=x.device, dtype=torch.bool)
+            y_onehot.scatter_(1, y.long(), 1)
+            if not self.do_bg:
+                y_onehot = y_onehot[:, 1:]
+            sum_gt = y_onehot.sum(axes)
+        if not self.do_bg:
+            x = x[:, 1:]
+        intersect = (x * y_onehot).sum(axes)
+        sum_pred = x.sum(axes)
+        if self.batch_dice:
+            intersect, sum_pred, sum_gt = intersect.sum(0), sum_pred.sum(0), sum_gt.sum(0)
+        dc = (2 * intersect + self.smooth) / torch.clip(sum_gt + sum_pred + self.smooth, 1e-8)
+        return -dc.mean()
+
+
+class _DeepSupervisionWrapper(nn.Module):
+    def __init__(self, loss, weight_factors=None):
+        super().__init__()
+        self.weight_factors = tuple(weight_factors)
+        self.loss = loss
+
+    def forward(self, *args):
+        return sum(w * self.loss(*inputs) for w, inputs in zip(self.weight_factors, zip(*args)) if w != 0.0)
+
+
 def _pkg(name):
     m = sys.modules.get(name)
     if m is None:
@@ -169,8 +223,20 @@ def _install_standins():
     for p in ("nnunetv2", "nnunetv2.training", "nnunetv2.training.nnUNetTrainer",
               "nnunetv2.training.nnUNetTrainer.variants",
               "nnunetv2.training.nnUNetTrainer.variants.network_architecture",
-              "nnunetv2.training.loss"):
+              "nnunetv2.training.loss", "nnunetv2.utilities"):
         _pkg(p)
+    # upstream nnU-Net loss pieces the reference's compound losses import (compound_bti_loss.py:2-5) — un-vendored, so
+    # restated from their public behaviour (parity unpinned for these): softmax over dim 1, CE on (b, 1, ...)
+    # targets, memory-efficient soft Dice (batch_dice / do_bg / smooth), weighted deep-supervision sum
+    helpers = _pkg("nnunetv2.utilities.helpers")
+    helpers.softmax_helper_dim1 = lambda x: torch.softmax(x, 1)
+    rce = _pkg("nnunetv2.training.loss.robust_ce_loss")
+    rce.RobustCrossEntropyLoss = _RobustCrossEntropyLoss
+    dice = _pkg("nnunetv2.training.loss.dice")
+    dice.SoftDiceLoss = _SoftDiceLoss
+    dice.MemoryEfficientSoftDiceLoss = _SoftDiceLoss
+    ds = _pkg("nnunetv2.training.loss.deep_supervision")
+    ds.DeepSupervisionWrapper = _DeepSupervisionWrapper
 
 
 def _load(dotted, relpath):
@@ -198,7 +264,7 @@ def load_reference() -> Ref:
     if _REF is not None:
         return _REF
     if not reference_available():
-        raise RuntimeError(f"reference not found under {REF_ROOT}")
+        raise RuntimeError(f"reference not found under {REF_ROOT} (stage it with `python -m oracle.stage_ref` where /root/reference exists)")
     _install_standins()
     na = "nnunetv2.training.nnUNetTrainer.variants.network_architecture."
     r = Ref()
@@ -209,6 +275,10 @@ def load_reference() -> Ref:
     r.NX = _load(na + "NexToU", "network_architecture/NexToU.py")
     r.bti = _load("nnunetv2.training.loss.bti_loss", "loss/bti_loss.py")
     r.ti = _load("nnunetv2.training.loss.ti_loss", "loss/ti_loss.py")
+    r.compound_bti = _load("nnunetv2.training.loss.compound_bti_loss", "loss/compound_bti_loss.py")
+    r.compound_ti = _load("nnunetv2.training.loss.compound_ti_loss", "loss/compound_ti_loss.py")
+    r.DeepSupervisionWrapper = _DeepSupervisionWrapper
+    r.SoftDiceLoss = _SoftDiceLoss
     r.InitWeights_He = _InitWeights_He
     _REF = r
     return r

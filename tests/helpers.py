@@ -10,27 +10,12 @@ from torch import nn
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 GOLDEN = os.path.join(ROOT, "tests", "golden")
 
-MINI3D = dict(patch=(32, 96, 128), feats=(6, 12, 24, 36, 48, 48), num_classes=5,
-              strides=[[1, 1, 1], [1, 2, 2]] + [[2, 2, 2]] * 4, kernels=[[1, 3, 3]] + [[3, 3, 3]] * 5)
-MINI2D = dict(patch=(64, 64), feats=(8, 16, 32, 32, 32), num_classes=3,
-              strides=[[1, 1]] + [[2, 2]] * 4, kernels=[[3, 3]] * 5)
-FULL3D = dict(patch=(64, 224, 192), feats=(33, 66, 132, 264, 324, 324), num_classes=14,
-              strides=[[1, 1, 1], [1, 2, 2]] + [[2, 2, 2]] * 4, kernels=[[1, 3, 3]] + [[3, 3, 3]] * 5)
+from nextou_b200.factory import FULL3D, MINI2D, MINI3D, build_nextou  # noqa: E402  (configs + constructor live in the package)
 
 
 def build_product(cfg, deep_supervision=True, in_ch=1, seed=0):
     """nextou_b200.NexToU with the kwargs nnUNetTrainer_NexToU.build_network_architecture passes (TR:52-58, 74-87)."""
-    from nextou_b200.conv_blocks import InitWeights_He
-    from nextou_b200.model import NexToU
-    dim = len(cfg["patch"])
-    conv = nn.Conv3d if dim == 3 else nn.Conv2d
-    bn = nn.BatchNorm3d if dim == 3 else nn.BatchNorm2d
-    torch.manual_seed(seed)
-    m = NexToU(in_ch, list(cfg["patch"]), len(cfg["feats"]), list(cfg["feats"]), conv, cfg["kernels"], cfg["strides"], 2,
-               cfg["num_classes"], 2, conv_bias=True, norm_op=bn, norm_op_kwargs={"eps": 1e-5, "affine": True},
-               nonlin=nn.LeakyReLU, nonlin_kwargs={"inplace": True}, deep_supervision=deep_supervision)
-    m.apply(InitWeights_He(1e-2))
-    return m
+    return build_nextou(cfg, deep_supervision, in_ch, seed)
 
 
 def golden_model(name):

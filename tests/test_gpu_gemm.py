@@ -325,3 +325,74 @@ def test_folded_eval_norm_matches_fp32_reference(kind):
         else:
             dense.linear_norm_act_tokens(tok, layer, bn, B, 0.01)
     assert dense.stats["tcgen05.conv_folded_norm"] + dense.stats["tcgen05.linear_folded_norm"] == 0
+
+
+# ------------------------------------------------------------------------------------------------------
+# full-resolution layers of 3d_fullres_nextou: the shapes bench.py runs — 21 504 bricks over the
+# persistent CTAs, 80-byte row pitch at 33 channels, the [up | gap | skip] concat layout — against fp32 cuDNN (TF32 off)
+# on the same bf16-valued operands, all on the GPU (the CPU would need minutes)
+# ------------------------------------------------------------------------------------------------------
+def _gpu_tok(x, pitch=None):
+    """(B, C, *sp) bf16 CUDA tensor -> [rows, C] view over a [rows, pitch] buffer whose padding lanes hold NaN."""
+    from nextou_b200 import ops
+    B, C = x.shape[:2]
+    dim = x.dim() - 2
+    pitch = ops.pad8(C) if pitch is None else pitch
+    t = torch.full((B * x[0, 0].numel(), pitch), float("nan"), dtype=torch.bfloat16, device=x.device)
+    t[:, :C] = x.permute(0, *range(2, 2 + dim), 1).reshape(-1, C)
+    return t[:, :C]
+
+
+def _gpu_vol(tok, B, C, spatial):
+    dim = len(spatial)
+    return tok[:, :C].float().reshape(B, *spatial, C).permute(0, dim + 1, *range(1, dim + 1))
+
+
+@pytest.mark.parametrize("spatial,cin,cout,ks,gap", [
+    ((64, 224, 192), 33, 33, (1, 3, 3), False),     # enc s0 conv1 / dec st4 conv1
+    ((64, 224, 192), 66, 33, (1, 3, 3), True),      # dec st4 conv0 on the [up 33 | zero gap 7 | skip 33] concat layout
+    ((64, 112, 96), 66, 66, (3, 3, 3), False),      # enc s1 conv1 / dec st3 conv1
+], ids=["s0_33to33_1x3x3", "dec4_66to33_gap_layout", "s1_66to66_3x3x3"])
+def test_full_resolution_conv_layer_fwd_dgrad_wgrad(spatial, cin, cout, ks, gap):
+    from nextou_b200 import native, ops
+    old = (torch.backends.cudnn.allow_tf32, torch.backends.cuda.matmul.allow_tf32)
+    torch.backends.cudnn.allow_tf32 = False
+    torch.backends.cuda.matmul.allow_tf32 = False
+    try:
+        g = torch.Generator(device=DEV).manual_seed(cin * 131 + cout)
+        x = torch.randn(1, cin, *spatial, generator=g, device=DEV).bfloat16()
+        w = (torch.randn(cout, cin, *ks, generator=g, device=DEV) / (cin * 9) ** 0.5).bfloat16().float()
+        bias = torch.randn(cout, generator=g, device=DEV)
+        dy = torch.randn(1, cout, *spatial, generator=g, device=DEV).bfloat16()
+        xr, wr = x.float().requires_grad_(True), w.clone().requires_grad_(True)
+        want = F.conv3d(xr, wr, bias, padding=[k // 2 for k in ks])
+        want.backward(dy.float())
+        if gap:
+            # physical input: the decoder's concatenation buffer (native.up_cat_tokens): up-sampled half, zero-filled gap up
+            # to the next multiple of 8 channels, skip half; the weight gets matching zero columns (dense.conv_tokens)
+            ca, pa = cin // 2, ops.pad8(cin // 2)
+            xcat = torch.cat([x[:, :ca], torch.zeros(1, pa - ca, *spatial, device=DEV, dtype=torch.bfloat16), x[:, ca:]], 1)
+            xt = _gpu_tok(xcat).requires_grad_(True)
+            wd = w.clone().requires_grad_(True)
+            wfull = torch.cat([wd[:, :ca], wd.new_zeros(cout, pa - ca, *ks), wd[:, ca:]], 1)
+        else:
+            xt = _gpu_tok(x).requires_grad_(True)
+            wd = w.clone().requires_grad_(True)
+            wfull = wd
+        bd = bias.clone().requires_grad_(True)
+        y = native.conv_tokens(xt, wfull, bd, 1, spatial)
+        y.backward(_gpu_tok(dy))
+        torch.cuda.synchronize()
+        got = _gpu_vol(y.detach(), 1, cout, spatial)
+        assert _rel(got, want.detach()) < 4e-3, _rel(got, want.detach())                    # bf16 output rounding (2^-9 rms)
+        assert (got - want.detach()).abs().max().item() <= 2 ** -7 * want.abs().max().item()
+        gx = _gpu_vol(xt.grad, 1, xt.shape[1], spatial)
+        if gap:
+            assert torch.count_nonzero(gx[:, ca:pa]) == 0             # gap lanes: data gradient through zero weight columns
+            gx = torch.cat([gx[:, :ca], gx[:, pa:]], 1)
+        assert _rel(gx, xr.grad) < 4e-3, _rel(gx, xr.grad)
+        assert _rel(wd.grad, wr.grad) < 2e-4, _rel(wd.grad, wr.grad)                         # fp32 accumulation over 0.7-2.75 M voxels
+        bias_ref = dy.float().sum((0, 2, 3, 4))
+        assert _rel(bd.grad, bias_ref) < 1e-4
+    finally:
+        torch.backends.cudnn.allow_tf32, torch.backends.cuda.matmul.allow_tf32 = old

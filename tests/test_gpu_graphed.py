@@ -88,3 +88,37 @@ def test_graph_refuses_host_random_dilation():
     opt = torch.optim.SGD(model.parameters(), lr=1e-2)
     with pytest.raises(NextouError):
         GraphedTrainStep(model, loss_fn, opt, x.to(DEV), [t.to(DEV) for t in targets])
+
+
+def test_graph_replay_follows_learning_rate_schedule():
+    """nnU-Net's PolyLRScheduler assigns param_groups[i]['lr'] every epoch.  A captured step must follow it: with a fused
+    optimizer the learning rate lives in a device tensor that is re-filled when the group holds a new number (lr = 0 must
+    freeze the weights); an optimizer that bakes a host-scalar lr into the graph must raise instead of training on."""
+    from nextou_b200._lib import NextouError
+    from nextou_b200.graphed import GraphedTrainStep
+    model, loss_fn, x, targets = _setup()
+    xd, td = x.to(DEV), [t.to(DEV) for t in targets]
+    params = [p for p in model.parameters() if p.requires_grad]
+    opt = torch.optim.SGD(params, lr=1e-2, momentum=0.0, weight_decay=3e-5, fused=True)
+    step = GraphedTrainStep(model, loss_fn, opt, xd, td, clip_grad_norm=12, warmup=1)
+    assert isinstance(opt.param_groups[0]["lr"], torch.Tensor) and opt.param_groups[0]["lr"].is_cuda
+    step(xd, td)
+    w0 = [p.detach().clone() for p in params]
+    opt.param_groups[0]["lr"] = 0.0                      # what a scheduler does
+    step(xd, td)
+    assert all(torch.equal(a, b.detach()) for a, b in zip(w0, params)), "replay ignored the new learning rate"
+    opt.param_groups[0]["lr"] = 1e-2
+    step(xd, td)
+    assert any(not torch.equal(a, b.detach()) for a, b in zip(w0, params))
+    opt.param_groups[0]["weight_decay"] = 0.0            # cannot be patched into a captured graph
+    with pytest.raises(NextouError):
+        step(xd, td)
+    opt.param_groups[0]["weight_decay"] = 3e-5
+    del step
+    # host-scalar lr baked into the capture: changing it must be detected
+    opt2 = torch.optim.SGD(params, lr=1e-2, momentum=0.0)
+    step2 = GraphedTrainStep(model, loss_fn, opt2, xd, td, clip_grad_norm=12, warmup=1)
+    step2(xd, td)
+    opt2.param_groups[0]["lr"] = 5e-3
+    with pytest.raises(NextouError):
+        step2(xd, td)

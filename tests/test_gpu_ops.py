@@ -315,7 +315,7 @@ def test_bti_loss_matches_reference_golden_and_oracle(case, layout, bti_gold):
     ref = float(bti_gold[f"{name}.bti.loss"])
     assert abs(val.item() - ref) <= 1e-9 * max(1.0, abs(ref))               # fp64 scalar vs the reference
     labels = ops.bti_labels(lg.detach())
-    assert np.array_equal(labels.cpu().numpy(), logits.argmax(1).numpy().astype(np.uint8))
+    assert np.array_equal(labels.cpu().numpy(), torch.softmax(logits, 1).argmax(1).numpy().astype(np.uint8))   # BTI:132-134
     crit = mod.binary_topological_interaction_module(labels.unsqueeze(1))
     ref_crit = np.unpackbits(bti_gold[f"{name}.bti.crit"])[: labels.numel()].reshape(labels.shape)
     assert np.array_equal(crit[:, 0].cpu().numpy().astype(np.uint8), ref_crit)  # bit-exact critical map
@@ -345,7 +345,7 @@ def test_bti_full_size_properties():
     lg = logits.to(DEV).bfloat16()
     val = mod(lg, target.to(DEV))
     labels = ops.bti_labels(lg)
-    lab_cpu = lg.float().cpu().argmax(1)
+    lab_cpu = torch.softmax(lg.float().cpu(), 1).argmax(1)      # BTI:132-134
     assert np.array_equal(labels.cpu().numpy(), lab_cpu.numpy().astype(np.uint8))
     ma, mc, flags = mod.interaction_table()
     crit = ops.bti_critical_map(labels, ma, mc, flags, 26, 1)
@@ -357,6 +357,104 @@ def test_bti_full_size_properties():
     assert torch.equal(swapped, crit)
     const = ops.bti_critical_map(torch.full_like(labels, 3), ma, mc, flags, 26, 1)
     assert int(const.sum()) == 0
+
+
+def _near_tie_logits(shape, nc, seed, scale=0.05):
+    """fp32 logits whose two largest classes per voxel are closer than fp32 softmax can resolve: gaps of 0, 1 or 2 ulp at
+    |x| ~ 0.15 (0 / 1.5e-8 / 3e-8 <= 2^-25), with the LARGER logit at the HIGHER class index half of the time, so that
+    argmax(logits) != argmax(softmax(logits)) there (the reference takes the latter, bti_loss.py:132-134)."""
+    g = torch.Generator().manual_seed(seed)
+    x = torch.randn(shape[0], nc, *shape[1:], generator=g) * scale
+    mx = x.max(1, keepdim=True).values
+    vs = (shape[0], 1, *shape[1:])
+    i1 = torch.randint(0, nc, vs, generator=g)
+    i2 = (i1 + torch.randint(1, nc, vs, generator=g)) % nc
+    top = mx + 0.01
+    ulps = torch.randint(0, 3, vs, generator=g)
+    hi = top.clone()
+    for _ in range(2):
+        hi = torch.where(ulps > 0, torch.nextafter(hi, torch.full_like(hi, 10.0)), hi)
+        ulps = ulps - 1
+    x.scatter_(1, i1, top)
+    x.scatter_(1, i2, hi)
+    return x
+
+
+@pytest.mark.parametrize("fused", [False, True], ids=["bti_kernel", "dsloss_kernel"])
+def test_bti_labels_are_argmax_of_softmax_on_near_ties(fused):
+    """The discrete map of the reference is argmax(softmax(x)) (bti_loss.py:132-134).  fp32 softmax maps logits within
+    2^-25 of the maximum to the same probability and torch.argmax then returns the lowest index — which is NOT
+    argmax(x).  Inside that clear-tie zone the result does not depend on the exp / sum implementation, and the kernels
+    must equal torch bit for bit.  (One to four ulp further out, torch's own CPU kernels disagree with each other —
+    softmax over dim 1 of NCDHW vs. the last dim of channels-last gave different arg-maxima on 4 % of crafted voxels —
+    so no implementation-independent answer exists there; the kernels evaluate exp(x - max) / sum in class order, fp32.)"""
+    from nextou_b200 import ops
+    shape, nc = (2, 6, 40, 48), 14
+    x = _near_tie_logits(shape, nc, 11)
+    want = torch.softmax(x, 1).argmax(1)
+    naive = x.argmax(1)
+    assert (want != naive).float().mean().item() > 0.15           # the case really separates the two definitions
+    target = torch.randint(0, nc, (shape[0], 1, *shape[1:])).float()
+    for layout in ("ncdhw", "channels_last"):
+        lg = x.to(DEV)
+        if layout == "channels_last":
+            lg = ops.channels_last(lg)
+        if not fused:
+            got = ops.bti_labels(lg)
+        else:
+            from nextou_b200 import _lib
+            import ctypes
+            xx, (sb, sc, sv) = ops._prep_logits(lg)
+            y = ops._prep_target(target.to(DEV))
+            B, V = shape[0], xx[0, 0].numel()
+            nblk = ctypes.c_int(0)
+            ops.check(_lib.lib().nextou_dsloss_plan(ops.ll(V), B, ctypes.byref(nblk)), "plan")
+            got = torch.empty((B, *shape[1:]), device=DEV, dtype=torch.uint8)
+            ce = torch.empty((B, V), device=DEV, dtype=torch.float64)
+            partial = torch.empty((B, nblk.value, 3 * nc + 1), device=DEV, dtype=torch.float64)
+            sums = torch.empty((B, 3 * nc + 1), device=DEV, dtype=torch.float64)
+            ops.check(_lib.lib().nextou_dsloss_stats(ops.ptr(xx), ops.dtype_code(xx), ops.ll(sb), ops.ll(sc), ops.ll(sv), B, nc,
+                                                     ops.ll(V), ops.ptr(y), ops._TGT_CODE[y.dtype], ops.ptr(got), ops.ptr(ce),
+                                                     ops.ptr(partial), ops.ptr(sums), ops.cstream()), "stats")
+        assert np.array_equal(got.cpu().numpy(), want.numpy().astype(np.uint8)), layout
+    # and the loss built on those labels equals the oracle's (which calls torch.softmax + argmax like the reference)
+    from nextou_b200.losses import BTI_Loss
+    _, exc = bti_interactions("synapse", nc)
+    mod = BTI_Loss(dim=3, connectivity=26, inclusion=[], exclusion=exc, min_thick=1)
+    val = mod(x.to(DEV), target.to(DEV))
+    ref = TO.bti_loss(x, target, [], exc, 3, 26, 1)
+    assert abs(val.item() - ref.item()) <= 1e-9 * max(1.0, abs(ref.item()))
+
+
+def test_ti_loss_all_pairs_of_13_organs_78_interactions():
+    """nnUNetTrainer_NexToU_TI builds every C(13, 2) = 78 pairwise exclusion of the Synapse organs (generate_combinations);
+    the reference has no limit on the list length.  Map bit-exact vs the C oracle, loss vs the torch oracle."""
+    from itertools import combinations
+    from nextou_b200 import ops
+    from nextou_b200.losses import TI_Loss
+    nc = 14
+    exc = [[torch.tensor(a), torch.tensor(b)] for a, b in combinations(range(1, nc), 2)]
+    assert len(exc) == 78
+    logits, target = bti_case((2, 12, 40, 36), nc, 9)
+    mod = TI_Loss(dim=3, connectivity=26, inclusion=[], exclusion=exc, min_thick=1)
+    val = mod(logits.to(DEV), target.to(DEV))
+    ref = TO.bti_loss(logits, target, [], exc, 3, 26, 1)
+    assert abs(val.item() - ref.item()) <= 1e-9 * max(1.0, abs(ref.item()))
+    labels = ops.bti_labels(logits.to(DEV))
+    ma, mc, flags = mod.interaction_table()
+    crit = ops.bti_critical_map(labels, ma, mc, flags, 26, 1)
+    want = c_oracle.bti_critical(labels.cpu().numpy(), ma, mc, flags, 26, 1)
+    assert np.array_equal(crit.cpu().numpy(), want)
+    # more than one launch chunk (> 128 distinct interactions): ordered pairs of 20 labels = 190, OR-accumulated
+    ma2 = [1 << a for a, b in combinations(range(20), 2)]
+    mc2 = [1 << b for a, b in combinations(range(20), 2)]
+    lab20 = torch.randint(0, 20, (1, 8, 24, 32), dtype=torch.uint8)
+    crit2 = ops.bti_critical_map(lab20.to(DEV), ma2, mc2, [0] * len(ma2), 26, 1)
+    want2 = c_oracle.bti_critical(lab20.numpy(), ma2, mc2, [0] * len(ma2), 26, 1)
+    assert np.array_equal(crit2.cpu().numpy(), want2)
+    # editing an entry of the public interaction_list in place takes effect (the reference re-reads the list every call)
+    mod.interaction_list[0][2] = torch.tensor(13)
+    assert mod.interaction_table()[1][0] == 1 << 13
 
 
 # ------------------------------------------------------------------------------------------------
