@@ -14,48 +14,53 @@
 
 namespace nextou {
 
-constexpr int NV = 4;  // elements per thread per sweep (8-byte bf16 / 16-byte fp32 loads)
-
-template <typename T> struct VecIO;
-template <> struct VecIO<float> {
-  static __device__ __forceinline__ void load(const float* p, float (&v)[NV]) {
-    const float4 t = *reinterpret_cast<const float4*>(p);
-    v[0] = t.x; v[1] = t.y; v[2] = t.z; v[3] = t.w;
-  }
-  static __device__ __forceinline__ void store(float* p, const float (&v)[NV]) {
+// NV elements per thread per sweep (8-byte bf16 / 16-byte fp32 loads).  Measured on B200 (tools/norm_ab.py): 16-byte bf16
+// loads (NV = 8) are no faster in the forward kernels and 40 % slower in the backward ones (108 registers: one CTA per SM).
+template <typename T, int NV> struct VecIO;
+template <> struct VecIO<float, 4> {
+  typedef float4 raw_t;
+  static __device__ __forceinline__ raw_t load_raw(const float* p) { return *reinterpret_cast<const float4*>(p); }
+  static __device__ __forceinline__ void unpack(const raw_t& t, float (&v)[4]) { v[0] = t.x; v[1] = t.y; v[2] = t.z; v[3] = t.w; }
+  static __device__ __forceinline__ void store(float* p, const float (&v)[4]) {
     *reinterpret_cast<float4*>(p) = make_float4(v[0], v[1], v[2], v[3]);
   }
 };
-template <> struct VecIO<__nv_bfloat16> {
-  static __device__ __forceinline__ void load(const __nv_bfloat16* p, float (&v)[NV]) {
-    const uint2 u = *reinterpret_cast<const uint2*>(p);
-    const float2 a = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&u.x));
-    const float2 b = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&u.y));
-    v[0] = a.x; v[1] = a.y; v[2] = b.x; v[3] = b.y;
+__device__ __forceinline__ void bf16x2_to_f32(unsigned u, float& a, float& b) {
+  a = __uint_as_float(u << 16);          // bf16 -> fp32 is a 16-bit shift
+  b = __uint_as_float(u & 0xffff0000u);
+}
+__device__ __forceinline__ unsigned f32x2_to_bf16x2(float a, float b) {
+  __nv_bfloat162 t = __floats2bfloat162_rn(a, b);
+  return *reinterpret_cast<unsigned*>(&t);
+}
+template <> struct VecIO<__nv_bfloat16, 4> {
+  typedef uint2 raw_t;
+  static __device__ __forceinline__ raw_t load_raw(const __nv_bfloat16* p) { return *reinterpret_cast<const uint2*>(p); }
+  static __device__ __forceinline__ void unpack(const raw_t& u, float (&v)[4]) {
+    bf16x2_to_f32(u.x, v[0], v[1]);
+    bf16x2_to_f32(u.y, v[2], v[3]);
   }
-  static __device__ __forceinline__ void store(__nv_bfloat16* p, const float (&v)[NV]) {
-    __nv_bfloat162 lo = __floats2bfloat162_rn(v[0], v[1]), hi = __floats2bfloat162_rn(v[2], v[3]);
+  static __device__ __forceinline__ void store(__nv_bfloat16* p, const float (&v)[4]) {
     uint2 u;
-    u.x = *reinterpret_cast<unsigned*>(&lo);
-    u.y = *reinterpret_cast<unsigned*>(&hi);
+    u.x = f32x2_to_bf16x2(v[0], v[1]);
+    u.y = f32x2_to_bf16x2(v[2], v[3]);
     *reinterpret_cast<uint2*>(p) = u;
   }
 };
-
 // guarded load / store for the ragged tail of an instance (total not a multiple of the sweep)
-template <typename T>
+template <typename T, int NV>
 __device__ __forceinline__ void load_guard(const T* base, long long off, long long total, float (&v)[NV]) {
   if (off + NV <= total) {
-    VecIO<T>::load(base + off, v);
+    VecIO<T, NV>::unpack(VecIO<T, NV>::load_raw(base + off), v);
   } else {
 #pragma unroll
     for (int e = 0; e < NV; ++e) v[e] = (off + e < total) ? to_f(base[off + e]) : 0.f;
   }
 }
-template <typename T>
+template <typename T, int NV>
 __device__ __forceinline__ void store_guard(T* base, long long off, long long total, const float (&v)[NV]) {
   if (off + NV <= total) {
-    VecIO<T>::store(base + off, v);
+    VecIO<T, NV>::store(base + off, v);
   } else {
 #pragma unroll
     for (int e = 0; e < NV; ++e)
@@ -63,10 +68,51 @@ __device__ __forceinline__ void store_guard(T* base, long long off, long long to
   }
 }
 
+// The sweep loop shared by every streaming kernel.  A CTA owns the sweeps s = blockIdx.x, blockIdx.x + gridDim.x, ...; sweeps
+// that lie completely inside the instance need no bounds check, so U of them are fetched back to back (U * NIN independent
+// vector loads in flight per thread: the HBM pipe needs ~50 bytes in flight per thread at this occupancy) before any
+// arithmetic; only the instance's last, ragged sweep takes the guarded path.  f(off, v0, v1) consumes one sweep of this
+// thread (v1 is unused when NIN == 1) and may store its result.
+template <typename T, int NV, int U, int NIN, typename F>
+__device__ __forceinline__ void for_each_sweep(const T* __restrict__ in0, const T* __restrict__ in1, long long total, long long S,
+                                               F&& f) {
+  typedef typename VecIO<T, NV>::raw_t raw_t;
+  const long long nfull = total / S, stride = gridDim.x, toff = (long long)NV * threadIdx.x;
+  long long s = blockIdx.x;
+  for (; s + (U - 1) * stride < nfull; s += U * stride) {
+    raw_t r0[U], r1[U];
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      r0[u] = VecIO<T, NV>::load_raw(in0 + (s + u * stride) * S + toff);
+      if (NIN > 1) r1[u] = VecIO<T, NV>::load_raw(in1 + (s + u * stride) * S + toff);
+    }
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      float v0[NV], v1[NV];
+      VecIO<T, NV>::unpack(r0[u], v0);
+      if (NIN > 1) VecIO<T, NV>::unpack(r1[u], v1);
+      f((s + u * stride) * S + toff, v0, v1);
+    }
+  }
+  for (; s < nfull; s += stride) {
+    float v0[NV], v1[NV];
+    VecIO<T, NV>::unpack(VecIO<T, NV>::load_raw(in0 + s * S + toff), v0);
+    if (NIN > 1) VecIO<T, NV>::unpack(VecIO<T, NV>::load_raw(in1 + s * S + toff), v1);
+    f(s * S + toff, v0, v1);
+  }
+  if (s == nfull && nfull * S + toff < total) {   // the ragged last sweep (owned by exactly one CTA)
+    float v0[NV], v1[NV];
+    load_guard<T, NV>(in0, s * S + toff, total, v0);
+    if (NIN > 1) load_guard<T, NV>(in1, s * S + toff, total, v1);
+    f(s * S + toff, v0, v1);
+  }
+}
+
 __device__ __forceinline__ float lrelu_grad(float pre, float slope) { return pre > 0.f ? 1.f : slope; }
 
 // ---- two-value per-channel reduction shared by the statistics and the backward-reduce kernels ---------------
 // acc[e][0..1] are this thread's partial sums for channel (NV*tid + e) % C.  Writes partial[blk][2][C].
+template <int NV>
 __device__ __forceinline__ void block_channel_reduce(float (&acc)[NV][2], int C, int R, float* smem,
                                                      float* __restrict__ out) {
   const int tid = threadIdx.x;
@@ -86,6 +132,7 @@ __device__ __forceinline__ void block_channel_reduce(float (&acc)[NV][2], int C,
 }
 
 // one-value variant: acc[e] is this thread's partial for channel (NV*tid + e) % C.  Writes partial[blk][C].
+template <int NV>
 __device__ __forceinline__ void block_channel_reduce1(float (&acc)[NV], int C, int R, float* smem, float* __restrict__ out) {
   const int tid = threadIdx.x;
 #pragma unroll
@@ -99,24 +146,20 @@ __device__ __forceinline__ void block_channel_reduce1(float (&acc)[NV], int C, i
 }
 
 // grid (nblk, instances); block C*R/NV threads; dynamic smem 2*C*R floats
-template <typename T>
+template <typename T, int NV>
 __global__ void norm_stats_kernel(const T* __restrict__ x, int C, int R, long long rows, float* __restrict__ partial) {
   extern __shared__ float smem[];
   const long long total = rows * C;
   const T* base = x + (long long)blockIdx.y * total;
-  const long long S = (long long)C * R;
   float acc[NV][2] = {};
-#pragma unroll 4
-  for (long long off = (long long)blockIdx.x * S + NV * threadIdx.x; off < total; off += (long long)gridDim.x * S) {
-    float v[NV];
-    load_guard(base, off, total, v);
+  for_each_sweep<T, NV, 6, 1>(base, base, total, (long long)C * R, [&](long long, const float (&v)[NV], const float (&)[NV]) {
 #pragma unroll
     for (int e = 0; e < NV; ++e) {
       acc[e][0] += v[e];
       acc[e][1] = fmaf(v[e], v[e], acc[e][1]);
     }
-  }
-  block_channel_reduce(acc, C, R, smem, partial + ((long long)blockIdx.y * gridDim.x + blockIdx.x) * 2 * C);
+  });
+  block_channel_reduce<NV>(acc, C, R, smem, partial + ((long long)blockIdx.y * gridDim.x + blockIdx.x) * 2 * C);
 }
 
 // Fixed-order fp64 sum of the CTA partial rows: block = 32 columns x FIN_SLICES slices; slice s adds rows s, s+8, ...
@@ -185,7 +228,7 @@ __global__ void __launch_bounds__(32 * FIN_SLICES)
 }
 
 // y = lrelu((x - mean) * invstd * gamma + beta); slope == 1 -> no activation
-template <typename T>
+template <typename T, int NV>
 __global__ void norm_apply_kernel(const T* __restrict__ x, int C, int R, long long rows, const float* __restrict__ mean,
                                   const float* __restrict__ invstd, const float* __restrict__ gamma,
                                   const float* __restrict__ beta, float slope, T* __restrict__ y, int c_valid,
@@ -194,7 +237,6 @@ __global__ void norm_apply_kernel(const T* __restrict__ x, int C, int R, long lo
   const T* base = x + (long long)blockIdx.y * total;
   const T* rbase = residual ? residual + (long long)blockIdx.y * total : nullptr;
   T* obase = y + (long long)blockIdx.y * total;
-  const long long S = (long long)C * R;
   float sc[NV], sh[NV];
 #pragma unroll
   for (int e = 0; e < NV; ++e) {
@@ -203,27 +245,36 @@ __global__ void norm_apply_kernel(const T* __restrict__ x, int C, int R, long lo
     sc[e] = invstd[blockIdx.y * C + ch] * g;
     sh[e] = b - mean[blockIdx.y * C + ch] * sc[e];
   }
-#pragma unroll 2
-  for (long long off = (long long)blockIdx.x * S + NV * threadIdx.x; off < total; off += (long long)gridDim.x * S) {
-    float v[NV];
-    load_guard(base, off, total, v);
+  auto act = [&](float (&v)[NV]) {
 #pragma unroll
     for (int e = 0; e < NV; ++e) {
       const float t = fmaf(v[e], sc[e], sh[e]);
       v[e] = t > 0.f ? t : t * slope;
     }
-    if (rbase != nullptr) {   // fused residual add: y = T(act(norm(x))) + shortcut, rounded like the two separate ops
-      float r[NV];
-      load_guard(rbase, off, total, r);
+  };
+  if (rbase == nullptr) {
+    for_each_sweep<T, NV, 4, 1>(base, base, total, (long long)C * R, [&](long long off, const float (&x0)[NV], const float (&)[NV]) {
+      float v[NV];
+#pragma unroll
+      for (int e = 0; e < NV; ++e) v[e] = x0[e];
+      act(v);
+      store_guard<T, NV>(obase, off, total, v);
+    });
+  } else {   // fused residual add: y = T(act(norm(x))) + shortcut, rounded like the two separate ops
+    for_each_sweep<T, NV, 2, 2>(base, rbase, total, (long long)C * R, [&](long long off, const float (&x0)[NV], const float (&r)[NV]) {
+      float v[NV];
+#pragma unroll
+      for (int e = 0; e < NV; ++e) v[e] = x0[e];
+      act(v);
 #pragma unroll
       for (int e = 0; e < NV; ++e) v[e] = to_f(from_f<T>(v[e])) + r[e];
-    }
-    store_guard(obase, off, total, v);
+      store_guard<T, NV>(obase, off, total, v);
+    });
   }
 }
 
 // backward pass 1: per channel  s1 = sum dy',  s2 = sum dy' * xhat,  dy' = dy * lrelu'(pre-activation)
-template <typename T>
+template <typename T, int NV>
 __global__ void norm_bwd_reduce_kernel(const T* __restrict__ x, const T* __restrict__ dy, int C, int R, long long rows,
                                        const float* __restrict__ mean, const float* __restrict__ invstd,
                                        const float* __restrict__ gamma, const float* __restrict__ beta, float slope,
@@ -232,7 +283,6 @@ __global__ void norm_bwd_reduce_kernel(const T* __restrict__ x, const T* __restr
   const long long total = rows * C;
   const T* xb = x + (long long)blockIdx.y * total;
   const T* db = dy + (long long)blockIdx.y * total;
-  const long long S = (long long)C * R;
   float mu[NV], is[NV], g[NV], b[NV];
 #pragma unroll
   for (int e = 0; e < NV; ++e) {
@@ -243,11 +293,7 @@ __global__ void norm_bwd_reduce_kernel(const T* __restrict__ x, const T* __restr
     b[e] = (beta && ch < c_valid) ? beta[ch] : 0.f;
   }
   float acc[NV][2] = {};
-#pragma unroll 2
-  for (long long off = (long long)blockIdx.x * S + NV * threadIdx.x; off < total; off += (long long)gridDim.x * S) {
-    float v[NV], d[NV];
-    load_guard(xb, off, total, v);
-    load_guard(db, off, total, d);
+  for_each_sweep<T, NV, 3, 2>(xb, db, total, (long long)C * R, [&](long long, const float (&v)[NV], const float (&d)[NV]) {
 #pragma unroll
     for (int e = 0; e < NV; ++e) {
       const float xh = (v[e] - mu[e]) * is[e];
@@ -255,8 +301,8 @@ __global__ void norm_bwd_reduce_kernel(const T* __restrict__ x, const T* __restr
       acc[e][0] += dd;
       acc[e][1] = fmaf(dd, xh, acc[e][1]);
     }
-  }
-  block_channel_reduce(acc, C, R, smem, partial + ((long long)blockIdx.y * gridDim.x + blockIdx.x) * 2 * C);
+  });
+  block_channel_reduce<NV>(acc, C, R, smem, partial + ((long long)blockIdx.y * gridDim.x + blockIdx.x) * 2 * C);
 }
 
 // sums[inst][cols] (fp32) from the CTA partial rows [inst][nblk][cols], fixed order, fp64 accumulation;
@@ -273,7 +319,7 @@ __global__ void __launch_bounds__(32 * FIN_SLICES)
 }
 
 // backward pass 2: dx = gamma * invstd * (dy' - s1/n - xhat * s2/n)
-template <typename T>
+template <typename T, int NV>
 __global__ void norm_bwd_apply_kernel(const T* __restrict__ x, const T* __restrict__ dy, int C, int R, long long rows,
                                       const float* __restrict__ mean, const float* __restrict__ invstd,
                                       const float* __restrict__ gamma, const float* __restrict__ beta, float slope,
@@ -284,7 +330,6 @@ __global__ void norm_bwd_apply_kernel(const T* __restrict__ x, const T* __restri
   const T* xb = x + (long long)blockIdx.y * total;
   const T* db = dy + (long long)blockIdx.y * total;
   T* ob = dx + (long long)blockIdx.y * total;
-  const long long S = (long long)C * R;
   float mu[NV], is[NV], g[NV], b[NV], m1[NV], m2[NV];
 #pragma unroll
   for (int e = 0; e < NV; ++e) {
@@ -297,30 +342,26 @@ __global__ void norm_bwd_apply_kernel(const T* __restrict__ x, const T* __restri
     m2[e] = sums[(long long)blockIdx.y * 2 * C + C + ch] * inv_n;
   }
   float csum[NV] = {};
-#pragma unroll 2
-  for (long long off = (long long)blockIdx.x * S + NV * threadIdx.x; off < total; off += (long long)gridDim.x * S) {
-    float v[NV], d[NV];
-    load_guard(xb, off, total, v);
-    load_guard(db, off, total, d);
+  for_each_sweep<T, NV, 3, 2>(xb, db, total, (long long)C * R, [&](long long off, const float (&v)[NV], const float (&d)[NV]) {
+    float o[NV];
 #pragma unroll
     for (int e = 0; e < NV; ++e) {
       const float xh = (v[e] - mu[e]) * is[e];
       const float dd = d[e] * lrelu_grad(fmaf(xh, g[e], b[e]), slope);
-      v[e] = g[e] * is[e] * (dd - m1[e] - xh * m2[e]);
-      csum[e] += to_f(from_f<T>(v[e]));   // column sums of dx as stored (= bias gradient of the producing conv / linear)
+      o[e] = g[e] * is[e] * (dd - m1[e] - xh * m2[e]);
+      csum[e] += to_f(from_f<T>(o[e]));   // column sums of dx as stored (= bias gradient of the producing conv / linear)
     }
-    store_guard(ob, off, total, v);
-  }
+    store_guard<T, NV>(ob, off, total, o);
+  });
   if (dx_partial != nullptr)
-    block_channel_reduce1(csum, C, R, smem, dx_partial + ((long long)blockIdx.y * gridDim.x + blockIdx.x) * C);
+    block_channel_reduce1<NV>(csum, C, R, smem, dx_partial + ((long long)blockIdx.y * gridDim.x + blockIdx.x) * C);
 }
 
 // eval-mode affine: y = lrelu(x * scale[c] + shift[c])  (running statistics folded by the caller)
-template <typename T>
+template <typename T, int NV>
 __global__ void affine_act_kernel(const T* __restrict__ x, int C, int R, long long rows, const float* __restrict__ scale,
                                   const float* __restrict__ shift, float slope, T* __restrict__ y) {
   const long long total = rows * C;
-  const long long S = (long long)C * R;
   float sc[NV], sh[NV];
 #pragma unroll
   for (int e = 0; e < NV; ++e) {
@@ -328,17 +369,15 @@ __global__ void affine_act_kernel(const T* __restrict__ x, int C, int R, long lo
     sc[e] = scale[ch];
     sh[e] = shift[ch];
   }
-#pragma unroll 2
-  for (long long off = (long long)blockIdx.x * S + NV * threadIdx.x; off < total; off += (long long)gridDim.x * S) {
+  for_each_sweep<T, NV, 4, 1>(x, x, total, (long long)C * R, [&](long long off, const float (&x0)[NV], const float (&)[NV]) {
     float v[NV];
-    load_guard(x, off, total, v);
 #pragma unroll
     for (int e = 0; e < NV; ++e) {
-      const float t = fmaf(v[e], sc[e], sh[e]);
+      const float t = fmaf(x0[e], sc[e], sh[e]);
       v[e] = t > 0.f ? t : t * slope;
     }
-    store_guard(y, off, total, v);
-  }
+    store_guard<T, NV>(y, off, total, v);
+  });
 }
 
 struct SweepPlan {
@@ -352,22 +391,23 @@ static int plan_sweep(int C, long long rows, int instances, SweepPlan& p) {
     set_error("norm: unsupported shape C=%d rows=%lld instances=%d (C <= 4096)", C, rows, instances);
     return NEXTOU_ERR_INVALID;
   }
-  if (instances > 1 && (rows * C) % NV) {
-    set_error("norm: rows*C=%lld must be a multiple of %d when instances > 1 (vector alignment)", rows * C, NV);
+  if (instances > 1 && (rows * C) % 4) {
+    set_error("norm: rows*C=%lld must be a multiple of 4 when instances > 1 (vector alignment)", rows * C);
     return NEXTOU_ERR_INVALID;
   }
+  constexpr int NVp = 4;
   int r0 = 1;
-  while ((C * r0) % NV) ++r0;
+  while ((C * r0) % NVp) ++r0;
   int R = r0;
-  while ((long long)C * (R + r0) / NV <= 512) R += r0;
-  if ((long long)C * R / NV > 1024) {
+  while ((long long)C * (R + r0) / NVp <= 512) R += r0;
+  if ((long long)C * R / NVp > 1024) {
     set_error("norm: C=%d needs more than 1024 threads per sweep", C);
     return NEXTOU_ERR_INVALID;
   }
   p.R = R;
-  p.threads = C * R / NV;
+  p.threads = C * R / NVp;
   const long long sweeps = (rows + R - 1) / R;
-  long long nblk = (8LL * num_sms() + instances - 1) / instances;   // 4 resident CTAs / SM x 2 waves
+  long long nblk = (4LL * num_sms() + instances - 1) / instances;   // one wave at 4 resident CTAs / SM (grid-stride sweeps)
   // small (L2-resident) tensors: fewer, fatter CTAs -> fewer partial rows for the latency-bound finalize (>= 16 sweeps each)
   const long long fat = (sweeps + 15) / 16;
   const long long floor_blk = (2LL * num_sms() + instances - 1) / instances;
@@ -382,6 +422,18 @@ static int plan_sweep(int C, long long rows, int instances, SweepPlan& p) {
 }  // namespace nextou
 
 using namespace nextou;
+
+#define DISPATCH_TV(dtype, ...)                                       \
+  if ((dtype) == NEXTOU_F32) {                                        \
+    using T = float; constexpr int NV = 4;                            \
+    __VA_ARGS__                                                       \
+  } else if ((dtype) == NEXTOU_BF16) {                                \
+    using T = __nv_bfloat16; constexpr int NV = 4;                    \
+    __VA_ARGS__                                                       \
+  } else {                                                            \
+    ::nextou::set_error("bad dtype %d", (dtype));                     \
+    return NEXTOU_ERR_INVALID;                                        \
+  }
 
 extern "C" int nextou_norm_plan(int C, long long rows, int instances, int* nblk_out) {
   SweepPlan p;
@@ -407,10 +459,10 @@ extern "C" int nextou_norm_stats_tracked(const void* x, int dtype, int C, int c_
   if (rc) return rc;
   cudaStream_t st = (cudaStream_t)stream;
   dim3 grid(p.nblk, instances);
-  DISPATCH_T(dtype, {
-    rc = ensure_smem(norm_stats_kernel<T>, p.smem);
+  DISPATCH_TV(dtype, {
+    rc = ensure_smem(norm_stats_kernel<T, NV>, p.smem);
     if (rc) return rc;
-    norm_stats_kernel<T><<<grid, p.threads, p.smem, st>>>((const T*)x, C, p.R, rows, partial);
+    norm_stats_kernel<T, NV><<<grid, p.threads, p.smem, st>>>((const T*)x, C, p.R, rows, partial);
   })
   rc = check_launch("norm_stats_kernel");
   if (rc) return rc;
@@ -440,8 +492,8 @@ extern "C" int nextou_norm_apply_res(const void* x, int dtype, int C, int c_vali
   int rc = plan_sweep(C, rows, instances, p);
   if (rc) return rc;
   dim3 grid(p.nblk, instances);
-  DISPATCH_T(dtype, norm_apply_kernel<T><<<grid, p.threads, 0, (cudaStream_t)stream>>>(
-                        (const T*)x, C, p.R, rows, mean, invstd, gamma, beta, slope, (T*)y, c_valid, (const T*)residual);)
+  DISPATCH_TV(dtype, norm_apply_kernel<T, NV><<<grid, p.threads, 0, (cudaStream_t)stream>>>(
+                               (const T*)x, C, p.R, rows, mean, invstd, gamma, beta, slope, (T*)y, c_valid, (const T*)residual);)
   return check_launch("norm_apply_kernel");
 }
 
@@ -472,11 +524,11 @@ extern "C" int nextou_norm_bwd_reduce(const void* x, const void* dy, int dtype, 
   if (rc) return rc;
   cudaStream_t st = (cudaStream_t)stream;
   dim3 grid(p.nblk, instances);
-  DISPATCH_T(dtype, {
-    rc = ensure_smem(norm_bwd_reduce_kernel<T>, p.smem);
+  DISPATCH_TV(dtype, {
+    rc = ensure_smem(norm_bwd_reduce_kernel<T, NV>, p.smem);
     if (rc) return rc;
-    norm_bwd_reduce_kernel<T><<<grid, p.threads, p.smem, st>>>((const T*)x, (const T*)dy, C, p.R, rows, mean, invstd,
-                                                              gamma, beta, slope, partial, c_valid);
+    norm_bwd_reduce_kernel<T, NV><<<grid, p.threads, p.smem, st>>>((const T*)x, (const T*)dy, C, p.R, rows, mean, invstd,
+                                                                  gamma, beta, slope, partial, c_valid);
   })
   rc = check_launch("norm_bwd_reduce_kernel");
   if (rc) return rc;
@@ -500,12 +552,12 @@ extern "C" int nextou_norm_bwd_apply(const void* x, const void* dy, int dtype, i
   dim3 grid(p.nblk, instances);
   float* dx_partial = dx_colsum ? partial : nullptr;
   const size_t smem2 = dx_colsum ? p.smem / 2 : 0;
-  DISPATCH_T(dtype, {
-    rc = ensure_smem(norm_bwd_apply_kernel<T>, smem2);
+  DISPATCH_TV(dtype, {
+    rc = ensure_smem(norm_bwd_apply_kernel<T, NV>, smem2);
     if (rc) return rc;
-    norm_bwd_apply_kernel<T><<<grid, p.threads, smem2, st>>>((const T*)x, (const T*)dy, C, p.R, rows, mean, invstd, gamma,
-                                                            beta, slope, sums, (T*)dx, dx_partial, c_valid,
-                                                            1.f / (float)n_total);
+    norm_bwd_apply_kernel<T, NV><<<grid, p.threads, smem2, st>>>((const T*)x, (const T*)dy, C, p.R, rows, mean, invstd, gamma,
+                                                                beta, slope, sums, (T*)dx, dx_partial, c_valid,
+                                                                1.f / (float)n_total);
   })
   rc = check_launch("norm_bwd_apply_kernel");
   if (rc || !dx_colsum) return rc;
@@ -520,8 +572,8 @@ extern "C" int nextou_affine_act(const void* x, int dtype, int C, long long rows
   SweepPlan p;
   int rc = plan_sweep(C, rows, 1, p);
   if (rc) return rc;
-  DISPATCH_T(dtype, affine_act_kernel<T><<<p.nblk, p.threads, 0, (cudaStream_t)stream>>>((const T*)x, C, p.R, rows,
-                                                                                        scale, shift, slope, (T*)y);)
+  DISPATCH_TV(dtype, affine_act_kernel<T, NV><<<p.nblk, p.threads, 0, (cudaStream_t)stream>>>((const T*)x, C, p.R, rows,
+                                                                                               scale, shift, slope, (T*)y);)
   return check_launch("affine_act_kernel");
 }
 
@@ -534,10 +586,10 @@ extern "C" int nextou_colsum(const void* x, int dtype, int C, long long rows, fl
   int rc = plan_sweep(C, rows, 1, p);
   if (rc) return rc;
   cudaStream_t st = (cudaStream_t)stream;
-  DISPATCH_T(dtype, {
-    rc = ensure_smem(norm_stats_kernel<T>, p.smem);
+  DISPATCH_TV(dtype, {
+    rc = ensure_smem(norm_stats_kernel<T, NV>, p.smem);
     if (rc) return rc;
-    norm_stats_kernel<T><<<dim3(p.nblk, 1), p.threads, p.smem, st>>>((const T*)x, C, p.R, rows, partial);
+    norm_stats_kernel<T, NV><<<dim3(p.nblk, 1), p.threads, p.smem, st>>>((const T*)x, C, p.R, rows, partial);
   })
   rc = check_launch("norm_stats_kernel");
   if (rc) return rc;

@@ -25,8 +25,7 @@ def build(force: bool = False) -> str:
 def lib():
     global _lib
     if _lib is None:
-        if not os.path.exists(LIB):
-            build()
+        build()          # no-op unless the library is missing or older than its source
         _lib = ctypes.CDLL(LIB)
         _lib.oracle_knn_topk.restype = ctypes.c_int
         _lib.oracle_bti_critical.restype = ctypes.c_int
