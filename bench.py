@@ -186,6 +186,7 @@ def run_own(args):
     import torch.distributed as dist
     from nextou_b200 import _lib, dense
     from nextou_b200.losses import DC_and_CE_and_BTI_Loss, DeepSupervisionWrapper, MemoryEfficientSoftDiceLoss
+    from nextou_b200.optim import FusedSGD
     from nextou_b200.parallel import GradientAllReducer
     from nextou_b200.factory import build_nextou
 
@@ -215,8 +216,12 @@ def run_own(args):
     w[-1] = 0
     loss_fn = DeepSupervisionWrapper(inner, (w / w.sum()).tolist())
     params = [p for p in model.parameters() if p.requires_grad]
-    opt = torch.optim.SGD(params, lr=1e-2, momentum=0.99, nesterov=True, weight_decay=3e-5, fused=True)
     reducer = GradientAllReducer(params, world) if world > 1 else None
+    if args.torch_sgd:
+        opt = torch.optim.SGD(params, lr=1e-2, momentum=0.99, nesterov=True, weight_decay=3e-5, fused=True)
+    else:
+        # csrc/optim.cu: gradient-norm clip + SGD-Nesterov + refresh of the bf16 operand packs, four launches per step
+        opt = FusedSGD(params, lr=1e-2, momentum=0.99, nesterov=True, weight_decay=3e-5, max_grad_norm=12)
 
     x_host, t_host = synthetic_batch(rank)
     x_host = x_host.pin_memory()
@@ -236,7 +241,8 @@ def run_own(args):
         loss.backward()
         if reducer is not None:
             reducer.all_reduce()
-        torch.nn.utils.clip_grad_norm_(params, 12)
+        if args.torch_sgd:
+            torch.nn.utils.clip_grad_norm_(params, 12)
         opt.step()
         return loss
 
@@ -374,7 +380,8 @@ def run_own(args):
                 "config": {"workload": WORKLOAD, "global_batch": world, "parallelism": f"dp{world}",
                            "batch_norm": "per-GPU batch statistics" if world == 1 else "SyncBatchNorm over all ranks (as upstream DDP)",
                            "loss": "DeepSupervision(Dice+CE+1e-6*BTI, Synapse interactions)",
-                           "optimizer": "SGD nesterov 0.99 wd 3e-5 (torch fused=True), clip 12",
+                           "optimizer": "clip 12 + SGD nesterov 0.99 wd 3e-5: " + ("torch.optim.SGD(fused=True) + clip_grad_norm_" if args.torch_sgd
+                                         else "nextou_b200.optim.FusedSGD (csrc/optim.cu: norm, clip, update, operand packs in 4 launches)"),
                            "execution": "eager" if gstep is None else "whole-step CUDA graph replay (fwd+loss+bwd+clip+SGD)",
                            "l2": "no flush needed: per-step working set (activations, several GB) >> 126 MB L2",
                            "library_calls_per_step": {k: v / args.steps for k, v in lib_calls.items()}},
@@ -422,6 +429,7 @@ def main():
     ap.add_argument("--impl", default="own", choices=["own", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-graph", action="store_true", help="issue every kernel from Python instead of replaying the step graph")
+    ap.add_argument("--torch-sgd", action="store_true", help="torch.optim.SGD(fused=True) + clip_grad_norm_ instead of FusedSGD (A/B)")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)

@@ -298,6 +298,47 @@ int nextou_conv3d_ndhwc_strided_wgrad(const void* dy, long long ldy, const void*
  * groups > 1 expands a grouped 1x1 convolution (torch_nn.py:85) to its block-diagonal dense operand. */
 int nextou_pack_weight(const void* w, int dtype, int R, int Cc, int taps, int groups, int flip_b, void* A, int lda_c,
                        void* Bt, int ldb_c, void* stream);
+/* Same with a zero channel gap [gap_lo, gap_hi) inserted into the INPUT-channel axis of both packs (lda_c >= Cc + gap width,
+ * Bt has Cc + gap width rows): the first convolution of a decoder stage reads the concatenation buffer [up | gap | skip]
+ * (NexToU_Encoder_Decoder.py:321-322) whose up-sampled half is padded to a multiple of 8 channels. */
+int nextou_pack_weight_gap(const void* w, int dtype, int R, int Cc, int taps, int groups, int flip_b, int gap_lo, int gap_hi,
+                           void* A, int lda_c, void* Bt, int ldb_c, void* stream);
+
+/* ------------------------------------------------------------------------------------------
+ * Optimizer side of the training step: upstream nnUNetTrainer.train_step runs
+ * torch.nn.utils.clip_grad_norm_(network.parameters(), 12) and torch.optim.SGD(momentum 0.99, nesterov, weight_decay 3e-5)
+ * .step() after backward; the next forward re-derives the bf16 operand packs of every weight.  Here: all parameter tensors
+ * in three launches + all packs in a fourth.  The tables live in device memory and are built once by the caller.
+ * ------------------------------------------------------------------------------------------ */
+typedef struct {
+  float* param;      /* fp32 master weights, updated in place */
+  float* grad;       /* fp32 gradient (optionally overwritten with the clipped gradient) */
+  float* momentum;   /* fp32 momentum buffer (zero-initialised by the caller) or NULL when momentum == 0 */
+  long long numel;
+} NextouOptTensor;
+typedef struct {
+  int tensor;        /* index into the tensor / pack-job table */
+  int count;         /* elements of this chunk (<= nextou_opt_chunk_elems()) */
+  long long start;   /* first element */
+} NextouOptChunk;
+typedef struct {
+  const void* w;     /* master weight [R][Cc/groups][taps] */
+  void* A;           /* bf16 [R][taps][lda_c] */
+  void* Bt;          /* bf16 [Cc + gap][taps][ldb_c] or NULL */
+  int R, Cc, taps, groups, flip_b, lda_c, ldb_c, gap_lo, gap_hi;
+} NextouPackJob;
+int nextou_opt_chunk_elems(void);
+/* state[0] = 2-norm of all gradients, state[1] = min(1, max_norm / (state[0] + 1e-6)) (1 when max_norm <= 0);
+ * partial: n_partial doubles of workspace.  No host synchronisation. */
+int nextou_opt_grad_norm(const NextouOptTensor* tensors, const NextouOptChunk* chunks, int n_chunks, float max_norm,
+                         double* partial, int n_partial, float* state, void* stream);
+/* g' = state[1]*g + weight_decay*p;  buf = momentum*buf + (1-dampening)*g';  p -= lr[0] * (nesterov ? g' + momentum*buf : buf)
+ * (torch.optim.SGD.step on clipped gradients; state == NULL: no clipping; lr is read on the device). */
+int nextou_opt_sgd_step(const NextouOptTensor* tensors, const NextouOptChunk* chunks, int n_chunks, const float* lr,
+                        const float* state, float momentum, float dampening, float weight_decay, int nesterov,
+                        int write_clipped_grad, void* stream);
+/* every pack job (fp32 master weights) in one launch; chunks index the concatenated A | Bt element range of a job */
+int nextou_opt_pack_weights(const NextouPackJob* jobs, const NextouOptChunk* chunks, int n_chunks, void* stream);
 
 /* Inference forms: out = lrelu(acc * scale[N] + shift[N], slope).  An eval-mode BatchNorm (+ the
  * LeakyReLU behind it) is folded into the epilogue of the layer that feeds it: scale = gamma * rsqrt(running_var + eps),

@@ -77,6 +77,39 @@ template <> __device__ __forceinline__ float from_f<float>(float v) { return v; 
 template <> __device__ __forceinline__ __nv_bfloat16 from_f<__nv_bfloat16>(float v) { return __float2bfloat16_rn(v); }
 
 
+// Weight packing, one output element: master weight w[R][Cc/groups][taps] (nn.Conv / nn.ConvTranspose layout) ->
+//   A[r][t][c]   (row pitch taps*lda_c) = w[r][c][t]     forward operand        ([Cout][taps][Cin pad])
+//   Bt[c][t'][r] (row pitch taps*ldb_c) = w[r][c][t]     data-gradient operand  ([Cin][taps][Cout pad]), t' = flipped t
+// i indexes the A elements first, then the Bt elements.  Zero where c / r are channel padding, outside the diagonal blocks of
+// a grouped layer, and inside the channel gap [gap_lo, gap_hi) that the decoder's concatenation layout [up | gap | skip]
+// inserts into the INPUT channel axis (physical channel c -> logical channel c - (gap_hi - gap_lo) behind the gap).
+template <typename T>
+__device__ __forceinline__ void pack_element(const NextouPackJob& j, const T* __restrict__ w, long long i) {
+  const int gapw = j.gap_hi - j.gap_lo;
+  const int Cp = j.Cc + gapw;
+  const long long na = (long long)j.R * j.taps * j.lda_c;
+  const int cpg = j.Cc / j.groups, rpg = j.R / j.groups;
+  int r, c, t;
+  if (i < na) {
+    c = (int)(i % j.lda_c);
+    t = (int)((i / j.lda_c) % j.taps);
+    r = (int)(i / ((long long)j.lda_c * j.taps));
+  } else {
+    const long long q = i - na;
+    r = (int)(q % j.ldb_c);
+    const int tf = (int)((q / j.ldb_c) % j.taps);
+    t = j.flip_b ? j.taps - 1 - tf : tf;
+    c = (int)(q / ((long long)j.ldb_c * j.taps));
+  }
+  float v = 0.f;
+  if (r < j.R && c < Cp && !(c >= j.gap_lo && c < j.gap_hi)) {
+    const int cl = c < j.gap_lo ? c : c - gapw;
+    if (j.groups == 1 || cl / cpg == r / rpg) v = to_f(w[((long long)r * cpg + (j.groups == 1 ? cl : cl % cpg)) * j.taps + t]);
+  }
+  if (i < na) reinterpret_cast<__nv_bfloat16*>(j.A)[i] = __float2bfloat16_rn(v);
+  else reinterpret_cast<__nv_bfloat16*>(j.Bt)[i - na] = __float2bfloat16_rn(v);
+}
+
 inline int num_sms() {
   static int n = 0;
   if (!n) {

@@ -300,41 +300,33 @@ extern "C" int nextou_maxunpool3d_bwd(const void* dout, int dtype, long long ldo
 // ------------------------------------------------------------------------------------------------------
 namespace nextou {
 template <typename T>
-__global__ void pack_weight_kernel(const T* __restrict__ w, int R, int Cc, int taps, int groups, int flip_b,
-                                   __nv_bfloat16* __restrict__ A, int lda_c, __nv_bfloat16* __restrict__ Bt, int ldb_c) {
-  const long long na = (long long)R * taps * lda_c, nb = Bt ? (long long)Cc * taps * ldb_c : 0;
-  const int cpg = Cc / groups, rpg = R / groups;
-  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < na + nb; i += (long long)gridDim.x * blockDim.x) {
-    int r, c, t;
-    if (i < na) {
-      c = (int)(i % lda_c);
-      t = (int)((i / lda_c) % taps);
-      r = (int)(i / ((long long)lda_c * taps));
-    } else {
-      const long long j = i - na;
-      r = (int)(j % ldb_c);
-      int tf = (int)((j / ldb_c) % taps);
-      t = flip_b ? taps - 1 - tf : tf;
-      c = (int)(j / ((long long)ldb_c * taps));
-    }
-    float v = 0.f;
-    if (r < R && c < Cc && (groups == 1 || c / cpg == r / rpg))
-      v = to_f(w[((long long)r * cpg + (groups == 1 ? c : c % cpg)) * taps + t]);
-    if (i < na) A[i] = __float2bfloat16_rn(v);
-    else Bt[i - na] = __float2bfloat16_rn(v);
-  }
+__global__ void pack_weight_kernel(const NextouPackJob j, long long n) {
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x)
+    pack_element(j, reinterpret_cast<const T*>(j.w), i);
 }
 }  // namespace nextou
 
 extern "C" int nextou_pack_weight(const void* w, int dtype, int R, int Cc, int taps, int groups, int flip_b, void* A, int lda_c,
                                   void* Bt, int ldb_c, void* stream) {
+  return nextou_pack_weight_gap(w, dtype, R, Cc, taps, groups, flip_b, 0, 0, A, lda_c, Bt, ldb_c, stream);
+}
+
+// Same with a zero channel gap [gap_lo, gap_hi) in the input-channel axis of both packs (lda_c >= Cc + gap width; Bt gets
+// Cc + gap width rows): the weight of the first convolution of a decoder stage, whose input is the [up | gap | skip]
+// concatenation buffer (NexToU_Encoder_Decoder.py:322), without materialising a zero-padded copy of the weight.
+extern "C" int nextou_pack_weight_gap(const void* w, int dtype, int R, int Cc, int taps, int groups, int flip_b, int gap_lo,
+                                      int gap_hi, void* A, int lda_c, void* Bt, int ldb_c, void* stream) {
   NEXTOU_REQUIRE(w && A, "pack_weight: null pointer");
-  NEXTOU_REQUIRE(R > 0 && Cc > 0 && taps > 0 && groups > 0 && R % groups == 0 && Cc % groups == 0 && lda_c >= Cc &&
+  NEXTOU_REQUIRE(gap_lo >= 0 && gap_hi >= gap_lo && gap_lo <= Cc && (gap_hi == gap_lo || groups == 1), "pack_weight: bad channel gap");
+  const int Cp = Cc + gap_hi - gap_lo;
+  NEXTOU_REQUIRE(R > 0 && Cc > 0 && taps > 0 && groups > 0 && R % groups == 0 && Cc % groups == 0 && lda_c >= Cp &&
                      (Bt == nullptr || ldb_c >= R), "pack_weight: bad shape");
-  const long long n = (long long)R * taps * lda_c + (Bt ? (long long)Cc * taps * ldb_c : 0);
+  NextouPackJob j = {};
+  j.w = w; j.A = A; j.Bt = Bt; j.R = R; j.Cc = Cc; j.taps = taps; j.groups = groups; j.flip_b = flip_b;
+  j.lda_c = lda_c; j.ldb_c = ldb_c; j.gap_lo = gap_lo; j.gap_hi = gap_hi;
+  const long long n = (long long)R * taps * lda_c + (Bt ? (long long)Cp * taps * ldb_c : 0);
   long long blocks = (n + 255) / 256;
   if (blocks > 4LL * num_sms()) blocks = 4LL * num_sms();
-  DISPATCH_T(dtype, pack_weight_kernel<T><<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(
-                        (const T*)w, R, Cc, taps, groups, flip_b, (__nv_bfloat16*)A, lda_c, (__nv_bfloat16*)Bt, ldb_c);)
+  DISPATCH_T(dtype, pack_weight_kernel<T><<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(j, n);)
   return check_launch("pack_weight_kernel");
 }

@@ -76,13 +76,11 @@ def conv_tokens(tok: torch.Tensor, batch: int, spatial: Sequence[int], conv: tor
         and all(d == 1 for d in conv.dilation) and conv.groups == 1
     if same and _bf16_path(tok):
         stats["tcgen05.conv"] += 1
-        weight = conv.weight
         gap = getattr(conv, "in_gap", None)
-        if gap is not None and gap[1] > gap[0] and tok.shape[1] == conv.in_channels + gap[1] - gap[0]:
-            # input = up_cat layout [up (ca) | zero gap | skip]: give the weight matching zero columns (ED:322 semantics kept)
-            ca, pa = gap
-            weight = torch.cat([weight[:, :ca], weight.new_zeros(weight.shape[0], pa - ca, *weight.shape[2:]), weight[:, ca:]], 1)
-        return native.conv_tokens(tok, weight, conv.bias, batch, spatial), tuple(spatial)
+        if not (gap is not None and gap[1] > gap[0] and tok.shape[1] == conv.in_channels + gap[1] - gap[0]):
+            gap = None
+        # gap: input = up_cat layout [up (ca) | zero gap | skip]; the weight PACKS get matching zero columns (ED:322 semantics kept)
+        return native.conv_tokens(tok, conv.weight, conv.bias, batch, spatial, gap), tuple(spatial)
     plain = all(d == 1 for d in conv.dilation) and conv.groups == 1 and conv.padding_mode == "zeros" \
         and not isinstance(conv.padding, str) and all(1 <= s <= 4 for s in stride) and len(ks) in (2, 3) \
         and int(torch.tensor(ks).prod()) <= 64
@@ -158,7 +156,7 @@ def linear_norm_act_tokens(tok, conv, norm_mod, batch: int, act_slope: Optional[
         xb = ops.tma_ready_bf16(tok)
         w2d = conv.weight.reshape(conv.weight.shape[0], -1)
         N, K = w2d.shape[0], w2d.shape[1] * conv.groups
-        wp, _ = ops.pack_weight_pair(w2d, conv=False, groups=conv.groups, want_b=False)
+        wp, _ = ops.pack_weight_pair(w2d, conv=False, groups=conv.groups, want_b=False, owner=conv.weight)
         y = ops.gemm_bf16_tn(xb, wp[:, :K], shift, n=N, scale=scale, slope=1.0 if act_slope is None else act_slope)[:, :N]
         return y if residual is None else ops.add_tokens(y, residual)
     h = grouped_linear_tokens(tok, conv) if conv.groups > 1 else linear_tokens(tok, conv)
@@ -177,7 +175,7 @@ def conv_norm_act_tokens(tok, batch: int, spatial: Sequence[int], conv, norm_mod
         slope = 1.0 if act_slope is None else act_slope
         xb = ops.tma_ready_bf16(tok)
         cout, cin = conv.weight.shape[:2]
-        wp, _ = ops.pack_weight_pair(conv.weight, conv=True, want_b=False)
+        wp, _ = ops.pack_weight_pair(conv.weight, conv=True, want_b=False, owner=conv.weight)
         same = all(s == 1 for s in stride) and all(k % 2 == 1 for k in ks) and tuple(conv.padding) == tuple(k // 2 for k in ks)
         if same:
             y = ops.conv_ndhwc_bf16(xb, batch, spatial, cin, wp, cout, ks, shift, scale=scale, slope=slope)

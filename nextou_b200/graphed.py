@@ -139,8 +139,8 @@ class GraphedTrainStep:
         loss.backward()
         if self.reducer is not None:
             self.reducer.all_reduce()
-        if self.clip is not None:
-            torch.nn.utils.clip_grad_norm_(self.params, self.clip)
+        if self.clip is not None and not getattr(self.optimizer, "clips_gradients", False):
+            torch.nn.utils.clip_grad_norm_(self.params, self.clip)      # (nextou_b200.optim.FusedSGD clips inside step())
         self.optimizer.step()
         return loss.detach()
 

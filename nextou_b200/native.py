@@ -18,6 +18,19 @@ def _f32(t):
     return None if t is None else t.detach().float()
 
 
+class _Owner:
+    """Carries the nn.Parameter a weight argument is (a view of) through autograd.Function.apply as a NON-tensor argument, so
+    that its persistent operand packs (ops.PackEntry) can be found without making it a second differentiable input."""
+    __slots__ = ("p",)
+
+    def __init__(self, p):
+        self.p = p if isinstance(p, torch.nn.Parameter) else None
+
+
+def _unwrap(owner):
+    return None if owner is None else owner.p
+
+
 def _fork_wgrad(ctx, tensor):
     """A side-stream launcher for the layer's weight-gradient kernel when its data gradient is computed as well (the two
     kernels are independent: they become parallel branches of the step graph), else None."""
@@ -31,13 +44,14 @@ class _LinearTokens(torch.autograd.Function):
     """y[T, N] = x[T, K] @ w2d[N, K]^T + b  with w2d an fp32 / bf16 master weight."""
 
     @staticmethod
-    def forward(ctx, x, w2d, bias, groups=1):
+    def forward(ctx, x, w2d, bias, groups=1, owner=None):
         xb = ops.tma_ready_bf16(x)
         N = w2d.shape[0]
         K = w2d.shape[1] * groups
         # one launch packs the forward operand [N, K] and the data-gradient operand [K, N] (bf16, padded pitches); a grouped
-        # layer (TN:85) becomes the block-diagonal dense operand, which keeps the output token-major without a permute
-        wp, wt = ops.pack_weight_pair(w2d, conv=False, groups=groups, want_b=ctx.needs_input_grad[0])
+        # layer (TN:85) becomes the block-diagonal dense operand, which keeps the output token-major without a permute.
+        # The packs persist on the parameter (`owner`) until it changes (ops.pack_weight_pair).
+        wp, wt = ops.pack_weight_pair(w2d, conv=False, groups=groups, want_b=ctx.needs_input_grad[0], owner=_unwrap(owner))
         y = ops.gemm_bf16_tn(xb, wp[:, :K], bias, n=N)[:, :N]
         ctx.save_for_backward(xb, w2d)
         ctx.wt = wt
@@ -70,59 +84,65 @@ class _LinearTokens(torch.autograd.Function):
             dw = dw.to(w2d.dtype)
         if ctx.has_bias and ctx.needs_input_grad[2]:
             db = ops.colsum_tokens(dyb).to(ctx.bias_dtype)
-        return dx, dw, db, None
+        return dx, dw, db, None, None
 
 
 def linear_tokens(x_tok: torch.Tensor, weight: torch.Tensor, bias: Optional[torch.Tensor]) -> torch.Tensor:
     """1x1 convolution on token rows through the tcgen05 GEMM; weight: (Cout, Cin, 1, ...)."""
-    return _LinearTokens.apply(x_tok, weight.reshape(weight.shape[0], -1), bias)
+    return _LinearTokens.apply(x_tok, weight.reshape(weight.shape[0], -1), bias, 1, _Owner(weight))
 
 
 def grouped_linear_tokens(x_tok: torch.Tensor, weight: torch.Tensor, bias: Optional[torch.Tensor], groups: int):
     """Grouped 1x1 convolution: the groups are the diagonal blocks of one [Cout, Cin] operand (TN:85)."""
-    return _LinearTokens.apply(x_tok, weight.reshape(weight.shape[0], -1), bias, groups)
+    return _LinearTokens.apply(x_tok, weight.reshape(weight.shape[0], -1), bias, groups, _Owner(weight))
 
 
 class _ConvTokens(torch.autograd.Function):
-    """Stride-1 'same' convolution on a token-major bf16 volume (implicit GEMM)."""
+    """Stride-1 'same' convolution on a token-major bf16 volume (implicit GEMM).  gap = (lo, hi): the input rows carry hi - lo
+    extra zero channels after logical channel lo (the decoder's [up | gap | skip] concatenation buffer, ED:322); the weight
+    packs get matching zero columns, the weight gradient drops them again."""
 
     @staticmethod
-    def forward(ctx, x, weight, bias, batch, spatial):
+    def forward(ctx, x, weight, bias, batch, spatial, gap=None, owner=None):
         xb = ops.tma_ready_bf16(x)
         cout, cin = weight.shape[:2]
         ks = tuple(weight.shape[2:])
-        wp, wt = ops.pack_weight_pair(weight, conv=True, flip_b=True, want_b=ctx.needs_input_grad[0])
-        y = ops.conv_ndhwc_bf16(xb, batch, spatial, cin, wp, cout, ks, bias)[:, :cout]
+        gapw = 0 if gap is None else gap[1] - gap[0]
+        wp, wt = ops.pack_weight_pair(weight, conv=True, flip_b=True, want_b=ctx.needs_input_grad[0], gap=gap, owner=_unwrap(owner))
+        y = ops.conv_ndhwc_bf16(xb, batch, spatial, cin + gapw, wp, cout, ks, bias)[:, :cout]
         ctx.save_for_backward(xb, weight)
-        ctx.wt = wt            # data-gradient operator: [Cin, flipped taps * cout_pad]
-        ctx.meta = (batch, tuple(spatial), bias is not None, None if bias is None else bias.dtype)
+        ctx.wt = wt            # data-gradient operator: [Cin (+ gap), flipped taps * cout_pad]
+        ctx.meta = (batch, tuple(spatial), bias is not None, None if bias is None else bias.dtype, gap)
         return y
 
     @staticmethod
     def backward(ctx, dy):
         xb, weight = ctx.saved_tensors
-        batch, spatial, has_bias, bdt = ctx.meta
+        batch, spatial, has_bias, bdt, gap = ctx.meta
         cout, cin = weight.shape[:2]
         ks = tuple(weight.shape[2:])
+        cin_p = cin + (0 if gap is None else gap[1] - gap[0])        # physical input channels
         dyb = ops.tma_ready_bf16(dy)
         dx = dw = db = None
         side = _fork_wgrad(ctx, dyb)
         if ctx.needs_input_grad[1]:
-            dw = ops.conv_wgrad_bf16(dyb, xb, batch, spatial, cin, cout, ks, side=side)
+            dw = ops.conv_wgrad_bf16(dyb, xb, batch, spatial, cin_p, cout, ks, side=side)
         if ctx.needs_input_grad[0]:
-            dx = ops.conv_ndhwc_bf16(dyb, batch, spatial, cout, ctx.wt, cin, ks, None)[:, :cin]
+            dx = ops.conv_ndhwc_bf16(dyb, batch, spatial, cout, ctx.wt, cin_p, ks, None)[:, :cin_p]
         if side is not None:
             side.join()
             dw = dw()
         if ctx.needs_input_grad[1]:
+            if gap is not None and gap[1] > gap[0]:
+                dw = torch.cat([dw[:, :gap[0]], dw[:, gap[1]:]], 1)
             dw = dw.to(weight.dtype)
         if has_bias and ctx.needs_input_grad[2]:
             db = ops.colsum_tokens(dyb).to(bdt)
-        return dx, dw, db, None, None
+        return dx, dw, db, None, None, None, None
 
 
-def conv_tokens(x_tok, weight, bias, batch: int, spatial: Sequence[int]):
-    return _ConvTokens.apply(x_tok, weight, bias, batch, tuple(spatial))
+def conv_tokens(x_tok, weight, bias, batch: int, spatial: Sequence[int], gap=None):
+    return _ConvTokens.apply(x_tok, weight, bias, batch, tuple(spatial), None if gap is None else tuple(gap), _Owner(weight))
 
 
 def _out_spatial(spatial, ks, stride, padding):
@@ -135,11 +155,11 @@ class _ConvStridedTokens(torch.autograd.Function):
     weight gradient = MN-major tcgen05 kernel with a strided X box."""
 
     @staticmethod
-    def forward(ctx, x, weight, bias, batch, spatial, stride, padding):
+    def forward(ctx, x, weight, bias, batch, spatial, stride, padding, owner=None):
         xb = ops.tma_ready_bf16(x)
         cout, cin = weight.shape[:2]
         ks = tuple(weight.shape[2:])
-        wp, wt = ops.pack_weight_pair(weight, conv=True, flip_b=False, want_b=ctx.needs_input_grad[0])
+        wp, wt = ops.pack_weight_pair(weight, conv=True, flip_b=False, want_b=ctx.needs_input_grad[0], owner=_unwrap(owner))
         y, _ = ops.conv_strided_fwd_bf16(xb, batch, spatial, cin, wp, cout, ks, stride, padding, bias)
         ctx.save_for_backward(xb, weight)
         ctx.wt = wt
@@ -167,13 +187,13 @@ class _ConvStridedTokens(torch.autograd.Function):
             dw = dw.permute(0, 2, 1).reshape(cout, cin, *ks).to(weight.dtype)
         if has_bias and ctx.needs_input_grad[2]:
             db = ops.colsum_tokens(dyb).to(bdt)
-        return dx, dw, db, None, None, None, None
+        return dx, dw, db, None, None, None, None, None
 
 
 def conv_strided_tokens(x_tok, weight, bias, batch: int, spatial: Sequence[int], stride, padding):
     """-> (token rows [rows_out, Cout], output spatial shape)."""
     ks = tuple(weight.shape[2:])
-    y = _ConvStridedTokens.apply(x_tok, weight, bias, batch, tuple(spatial), tuple(stride), tuple(padding))
+    y = _ConvStridedTokens.apply(x_tok, weight, bias, batch, tuple(spatial), tuple(stride), tuple(padding), _Owner(weight))
     return y, _out_spatial(spatial, ks, stride, padding)
 
 
@@ -184,14 +204,14 @@ class _ConvTransposeTokens(torch.autograd.Function):
     of the operands exchanged.  weight: (Cin, Cout, *k) as nn.ConvTranspose stores it."""
 
     @staticmethod
-    def forward(ctx, x, weight, bias, batch, spatial):
+    def forward(ctx, x, weight, bias, batch, spatial, owner=None):
         xb = ops.tma_ready_bf16(x)
         cin, cout = weight.shape[:2]
         ks = tuple(weight.shape[2:])
         osp = tuple(n * k for n, k in zip(spatial, ks))
         zero = (0,) * len(ks)
         # A = [Cin][tap][Cout pad] (operand of the data gradient), Bt = [Cout][tap][Cin pad] (operand of the forward)
-        wa, wb = ops.pack_weight_pair(weight, conv=True, flip_b=False)
+        wa, wb = ops.pack_weight_pair(weight, conv=True, flip_b=False, owner=_unwrap(owner))
         y = ops.conv_strided_dgrad_bf16(xb, batch, spatial, cin, wb, cout, ks, ks, zero, osp, bias)
         ctx.save_for_backward(xb, weight)
         ctx.wa = wa
@@ -215,13 +235,13 @@ class _ConvTransposeTokens(torch.autograd.Function):
             dw = dw.permute(0, 2, 1).reshape(cin, cout, *ks).to(weight.dtype)
         if has_bias and ctx.needs_input_grad[2]:
             db = ops.colsum_tokens(dyb).to(bdt)
-        return dx, dw, db, None, None
+        return dx, dw, db, None, None, None
 
 
 def conv_transpose_tokens(x_tok, weight, bias, batch: int, spatial: Sequence[int]):
     """-> (token rows [rows_out, Cout], output spatial shape) of a kernel == stride transposed convolution."""
     ks = tuple(weight.shape[2:])
-    y = _ConvTransposeTokens.apply(x_tok, weight, bias, batch, tuple(spatial))
+    y = _ConvTransposeTokens.apply(x_tok, weight, bias, batch, tuple(spatial), _Owner(weight))
     return y, tuple(n * k for n, k in zip(spatial, ks))
 
 
@@ -233,7 +253,7 @@ class _UpCatTokens(torch.autograd.Function):
     columns, dense.conv_tokens), so both halves of the incoming gradient are TMA-ready views: no copy in the backward."""
 
     @staticmethod
-    def forward(ctx, x, weight, bias, skip, batch, spatial):
+    def forward(ctx, x, weight, bias, skip, batch, spatial, owner=None):
         xb = ops.tma_ready_bf16(x)
         cin, cout = weight.shape[:2]
         ks = tuple(weight.shape[2:])
@@ -243,7 +263,7 @@ class _UpCatTokens(torch.autograd.Function):
         pa = ops.pad8(cout)
         rows = skip.shape[0]
         buf = torch.empty((rows, pa + ops.pad8(cb)), device=x.device, dtype=torch.bfloat16)
-        wa, wb = ops.pack_weight_pair(weight, conv=True, flip_b=False)
+        wa, wb = ops.pack_weight_pair(weight, conv=True, flip_b=False, owner=_unwrap(owner))
         ops.conv_strided_dgrad_bf16(xb, batch, spatial, cin, wb, cout, ks, ks, zero, osp, bias, out=buf, store_cols=pa)
         buf[:, pa:pa + cb].copy_(skip)
         ctx.save_for_backward(xb, weight)
@@ -277,12 +297,12 @@ class _UpCatTokens(torch.autograd.Function):
             dskip = g[:, pa:pa + cb]
             if dskip.dtype != sdt:
                 dskip = dskip.to(sdt)
-        return dx, dw, db, dskip, None, None
+        return dx, dw, db, dskip, None, None, None
 
 
 def up_cat_tokens(x_tok, weight, bias, skip_tok, batch: int, spatial: Sequence[int]):
     """-> (token rows [rows_out, pad8(Cout) + Cskip], output spatial shape, (Cout, pad8(Cout)) gap descriptor)."""
     ks = tuple(weight.shape[2:])
-    y = _UpCatTokens.apply(x_tok, weight, bias, skip_tok, batch, tuple(spatial))
+    y = _UpCatTokens.apply(x_tok, weight, bias, skip_tok, batch, tuple(spatial), _Owner(weight))
     cout = weight.shape[1]
     return y, tuple(n * k for n, k in zip(spatial, ks)), (cout, ops.pad8(cout))

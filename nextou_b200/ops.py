@@ -598,10 +598,29 @@ def pack_conv_weight(w: torch.Tensor, transpose_flip: bool = False, transpose: b
     return wp.reshape(co, taps * ci_pad).to(torch.bfloat16).contiguous()
 
 
-def pack_weight_pair(w: torch.Tensor, conv: bool, flip_b: bool = False, groups: int = 1, want_b: bool = True):
+class PackEntry:
+    """Persistent bf16 operand packs of ONE master weight in ONE layout (kept on the Parameter object, so their lifetime and
+    identity are the parameter's).  `version` is the parameter's in-place version counter at packing time: any in-place
+    update by torch (optimizer.step, load_state_dict, DDP broadcast) invalidates the packs; nextou_b200.optim.FusedSGD
+    updates the weights AND rewrites the packs in one pass, so they stay valid from step to step."""
+    __slots__ = ("a", "b", "version", "ptr", "meta")
+
+    def __init__(self, meta):
+        self.a = self.b = None
+        self.version = self.ptr = -1
+        self.meta = meta          # (R, Cc, taps, groups, flip_b, pa, pb, gap_lo, gap_hi)
+
+
+PACK_CACHE = True   # False: re-pack on every call (A/B measurements)
+
+
+def pack_weight_pair(w: torch.Tensor, conv: bool, flip_b: bool = False, groups: int = 1, want_b: bool = True,
+                     gap: Optional[Tuple[int, int]] = None, owner: Optional[torch.Tensor] = None):
     """Master weight (R, Cc/groups, *k) -> (A [R, taps*pa] bf16, Bt [Cc, taps*pb] bf16 | None) in ONE kernel launch
     (csrc/pool.cu::pack_weight_kernel): A is the forward operand, Bt the data-gradient operand (taps flipped when
-    flip_b).  conv=True pads the channel axes to multiples of 64 (taps are concatenated along K), else to 8 (TMA pitch)."""
+    flip_b).  conv=True pads the channel axes to multiples of 64 (taps are concatenated along K), else to 8 (TMA pitch).
+    gap=(lo, hi): zero input channels [lo, hi) are inserted (the decoder's [up | gap | skip] concatenation layout).
+    owner: the nn.Parameter `w` is (a view of): its packs are kept on it and re-used until the parameter changes."""
     _need_cuda(w)
     w = _work_dtype(w.detach()).contiguous()
     R, cpg = w.shape[:2]
@@ -609,13 +628,31 @@ def pack_weight_pair(w: torch.Tensor, conv: bool, flip_b: bool = False, groups: 
     taps = 1
     for k in w.shape[2:]:
         taps *= k
+    glo, ghi = (0, 0) if gap is None else (int(gap[0]), int(gap[1]))
+    Cp = Cc + ghi - glo
     pad = (lambda c: (c + 63) // 64 * 64) if conv else pad8
-    pa, pb = pad(Cc), pad(R)
-    a = torch.empty((R, taps * pa), device=w.device, dtype=torch.bfloat16)
-    b = torch.empty((Cc, taps * pb), device=w.device, dtype=torch.bfloat16) if want_b else None
-    check(_lib.lib().nextou_pack_weight(ptr(w), dtype_code(w), R, Cc, taps, groups, int(flip_b), ptr(a), pa, ptr(b), pb,
-                                        cstream()), "nextou_pack_weight")
-    return a, b
+    pa, pb = pad(Cp), pad(R)
+    entry = None
+    if PACK_CACHE and owner is not None and w.dtype == torch.float32 and w.data_ptr() == owner.data_ptr():
+        cache = owner.__dict__.setdefault("_nextou_packs", {})
+        key = (conv, bool(flip_b), groups, glo, ghi)
+        entry = cache.get(key)
+        if entry is None:
+            entry = cache[key] = PackEntry((R, Cc, taps, groups, int(flip_b), pa, pb, glo, ghi))
+        if (entry.version == owner._version and entry.ptr == w.data_ptr() and entry.a is not None
+                and (entry.b is not None or not want_b)):
+            return entry.a, (entry.b if want_b else None)
+    if entry is not None and entry.a is not None and entry.ptr == w.data_ptr():
+        a = entry.a                                   # re-pack in place: FusedSGD / CUDA graphs hold these addresses
+        b = entry.b if entry.b is not None else (torch.empty((Cp, taps * pb), device=w.device, dtype=torch.bfloat16) if want_b else None)
+    else:
+        a = torch.empty((R, taps * pa), device=w.device, dtype=torch.bfloat16)
+        b = torch.empty((Cp, taps * pb), device=w.device, dtype=torch.bfloat16) if want_b else None
+    check(_lib.lib().nextou_pack_weight_gap(ptr(w), dtype_code(w), R, Cc, taps, groups, int(flip_b), glo, ghi, ptr(a), pa, ptr(b), pb,
+                                            cstream()), "nextou_pack_weight")
+    if entry is not None:
+        entry.a, entry.b, entry.version, entry.ptr = a, b, owner._version, w.data_ptr()
+    return a, (b if want_b else None)
 
 
 CONV_HALO = True  # use the halo-reuse kernel (csrc/conv_tcgen05.cu) whenever kh, kw are 1 or 3

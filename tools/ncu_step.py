@@ -5,11 +5,12 @@ sys.path.insert(0, ROOT)
 import numpy as np
 import torch
 import bench
-from tests import helpers as H
+from nextou_b200.factory import build_nextou
+from nextou_b200.optim import FusedSGD
 from nextou_b200.losses import DC_and_CE_and_BTI_Loss, DeepSupervisionWrapper, MemoryEfficientSoftDiceLoss
 
 dev = torch.device("cuda", 0)
-model = H.build_product(bench.CFG, seed=0).to(dev).train()
+model = build_nextou(bench.CFG, seed=0).to(dev).train()
 exclusion = bench.make_tensors(bench.SYNAPSE_EXCLUSION)
 inner = DC_and_CE_and_BTI_Loss({"batch_dice": True, "smooth": 1e-5, "do_bg": False, "ddp": False}, {},
                                {"dim": 3, "connectivity": 26, "inclusion": [], "exclusion": exclusion, "min_thick": 1},
@@ -17,7 +18,9 @@ inner = DC_and_CE_and_BTI_Loss({"batch_dice": True, "smooth": 1e-5, "do_bg": Fal
 w = np.array([1 / (2 ** i) for i in range(5)]); w[-1] = 0
 loss_fn = DeepSupervisionWrapper(inner, (w / w.sum()).tolist())
 params = [p for p in model.parameters() if p.requires_grad]
-opt = torch.optim.SGD(params, lr=1e-2, momentum=0.99, nesterov=True, weight_decay=3e-5, fused=True)
+TORCH_SGD = os.environ.get("NEXTOU_TORCH_SGD") == "1"
+opt = torch.optim.SGD(params, lr=1e-2, momentum=0.99, nesterov=True, weight_decay=3e-5, fused=True) if TORCH_SGD else \
+    FusedSGD(params, lr=1e-2, momentum=0.99, nesterov=True, weight_decay=3e-5, max_grad_norm=12)
 x, t = bench.synthetic_batch(0)
 x = x.to(dev); t = [a.to(dev) for a in t]
 
@@ -27,7 +30,8 @@ def step():
     with torch.autocast("cuda", dtype=torch.bfloat16):
         loss = loss_fn(model(x), t)
     loss.backward()
-    torch.nn.utils.clip_grad_norm_(params, 12)
+    if TORCH_SGD:
+        torch.nn.utils.clip_grad_norm_(params, 12)
     opt.step()
 
 
