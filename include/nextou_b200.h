@@ -291,6 +291,12 @@ int nextou_conv3d_ndhwc_strided_wgrad(const void* dy, long long ldy, const void*
                                       int W, int Dx, int Hx, int Wx, int Cin, int Cout, int kd, int kh, int kw, int sd,
                                       int sh, int sw, int pd, int ph, int pw, float* dW, int cin_stride, void* stream);
 
+/* out[r][0..cols) = a[r][0..cols) (+ b[r][0..cols), b may be NULL) on row views of different pitch / column offset (elements;
+ * bases, pitches and cols multiples of 16 bytes: the channel-padded token layout).  The skip half of torch.cat((up, skip), 1)
+ * (NexToU_Encoder_Decoder.py:322) and the gradient sum of a tensor consumed twice (skip connection, residual shortcut). */
+int nextou_rows_copy_add(const void* a, long long lda, const void* b, long long ldb, void* out, long long ldo, long long rows,
+                         int cols, int dtype, void* stream);
+
 /* Weight packing (one launch per layer and step): master weight w[R][Cc/groups][taps] (fp32 | bf16; nn.Conv layout
  * (Cout, Cin/groups, *k) or nn.ConvTranspose layout (Cin, Cout, *k)) ->
  *   A [R][taps][lda_c]  bf16 = w[r][c][t]       (forward operand;       lda_c >= Cc, zero padded)

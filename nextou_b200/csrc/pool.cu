@@ -291,6 +291,68 @@ extern "C" int nextou_maxunpool3d_bwd(const void* dout, int dtype, long long ldo
 }
 
 // ------------------------------------------------------------------------------------------------------
+// Row copy / add on token-major matrices whose views differ in pitch or column offset:
+//   out[r][0..cols) = a[r][0..cols) (+ b[r][0..cols))
+// The two places where the U-Net topology needs a data movement that no GEMM epilogue can absorb: the skip half of
+// torch.cat((up, skip), 1) (NexToU_Encoder_Decoder.py:322) written behind the up-sampled half of the concatenation buffer,
+// and the sum of the two gradients of a tensor that is consumed twice (skip connection / residual shortcut).  `cols` counts
+// 16-byte vectors' worth of columns: callers round it up to the channel padding (padding lanes are don't-care).
+// ------------------------------------------------------------------------------------------------------
+namespace nextou {
+template <bool ADD>
+__global__ void __launch_bounds__(256) rows_copy_add_kernel(const uint4* __restrict__ a, long long lda, const uint4* __restrict__ b,
+                                                            long long ldb, uint4* __restrict__ out, long long ldo,
+                                                            long long rows, int vec_per_row, int is_bf16) {
+  const long long total = rows * vec_per_row;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const long long r = i / vec_per_row;
+    const int v = (int)(i - r * vec_per_row);
+    uint4 x = a[r * lda + v];
+    if (ADD) {
+      const uint4 y = b[r * ldb + v];
+      if (is_bf16) {
+        __nv_bfloat162* xp = reinterpret_cast<__nv_bfloat162*>(&x);
+        const __nv_bfloat162* yp = reinterpret_cast<const __nv_bfloat162*>(&y);
+#pragma unroll
+        for (int e = 0; e < 4; ++e) xp[e] = __hadd2(xp[e], yp[e]);      // one rounding per element, like at::add on bf16
+      } else {
+        float* xp = reinterpret_cast<float*>(&x);
+        const float* yp = reinterpret_cast<const float*>(&y);
+#pragma unroll
+        for (int e = 0; e < 4; ++e) xp[e] += yp[e];
+      }
+    }
+    out[r * ldo + v] = x;
+  }
+}
+}  // namespace nextou
+
+// a, b (may be NULL: plain copy), out: [rows] rows of `cols` elements at pitches lda / ldb / ldo (elements).  Bases and
+// pitches must be 16-byte aligned and cols a multiple of 16 bytes (the channel-padded token layout guarantees both).
+extern "C" int nextou_rows_copy_add(const void* a, long long lda, const void* b, long long ldb, void* out, long long ldo,
+                                    long long rows, int cols, int dtype, void* stream) {
+  NEXTOU_REQUIRE(a && out && rows > 0 && cols > 0, "rows_copy_add: bad arguments");
+  NEXTOU_REQUIRE(dtype == NEXTOU_BF16 || dtype == NEXTOU_F32, "rows_copy_add: bad dtype");
+  const int per = dtype == NEXTOU_BF16 ? 8 : 4;            // elements per 16-byte vector
+  NEXTOU_REQUIRE(cols % per == 0 && lda % per == 0 && ldo % per == 0 && (b == nullptr || ldb % per == 0) && lda >= cols &&
+                     ldo >= cols && (b == nullptr || ldb >= cols),
+                 "rows_copy_add: pitches / cols must be multiples of 16 bytes");
+  NEXTOU_REQUIRE(((uintptr_t)a & 15) == 0 && ((uintptr_t)out & 15) == 0 && ((uintptr_t)b & 15) == 0, "rows_copy_add: 16-byte alignment");
+  const int vpr = cols / per;
+  const long long total = rows * vpr;
+  long long blocks = (total + 255) / 256;
+  if (blocks > 16LL * num_sms()) blocks = 16LL * num_sms();
+  cudaStream_t st = (cudaStream_t)stream;
+  if (b != nullptr)
+    rows_copy_add_kernel<true><<<(unsigned)blocks, 256, 0, st>>>((const uint4*)a, lda / per, (const uint4*)b, ldb / per, (uint4*)out,
+                                                                ldo / per, rows, vpr, dtype == NEXTOU_BF16);
+  else
+    rows_copy_add_kernel<false><<<(unsigned)blocks, 256, 0, st>>>((const uint4*)a, lda / per, nullptr, 0, (uint4*)out, ldo / per,
+                                                                 rows, vpr, dtype == NEXTOU_BF16);
+  return check_launch("rows_copy_add_kernel");
+}
+
+// ------------------------------------------------------------------------------------------------------
 // Weight packing: one launch turns an fp32 / bf16 master weight w[R][Cc/groups][taps] (nn.Conv / nn.ConvTranspose layout,
 // taps = prod(kernel)) into BOTH bf16 operand packs the tcgen05 kernels take:
 //   A[r][t][c]  (row pitch taps*lda_c)  = w[r][c][t]          forward operand   ([Cout][taps][Cin pad])

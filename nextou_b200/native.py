@@ -265,7 +265,8 @@ class _UpCatTokens(torch.autograd.Function):
         buf = torch.empty((rows, pa + ops.pad8(cb)), device=x.device, dtype=torch.bfloat16)
         wa, wb = ops.pack_weight_pair(weight, conv=True, flip_b=False, owner=_unwrap(owner))
         ops.conv_strided_dgrad_bf16(xb, batch, spatial, cin, wb, cout, ks, ks, zero, osp, bias, out=buf, store_cols=pa)
-        buf[:, pa:pa + cb].copy_(skip)
+        if not ops.rows_copy_add(skip, None, buf[:, pa:pa + cb]):      # skip half behind the up-sampled half (ED:322)
+            buf[:, pa:pa + cb].copy_(skip)
         ctx.save_for_backward(xb, weight)
         ctx.wa = wa
         ctx.meta = (batch, tuple(spatial), osp, bias is not None, None if bias is None else bias.dtype, pa, cb, skip.dtype)

@@ -475,6 +475,16 @@ def bti_loss(logits, target, mask_a, mask_c, inclusion, connectivity: int, min_t
 SEG_LOSS_CLASSES = (2, 3, 4, 5, 6, 7, 8, 14, 16, 19)   # instantiated class counts of csrc/dsloss.cu
 
 
+def _empty_like_strided(x: torch.Tensor) -> torch.Tensor:
+    """Uninitialised tensor with x's shape and strides whose storage also covers the channel padding of the LAST token row
+    (torch.empty_strided stops at the last addressed element, which makes the full [rows, pitch] rectangle unaddressable
+    and forces the consumers of the gradient to copy it)."""
+    need = 1 + sum((n - 1) * st for n, st in zip(x.shape, x.stride()))
+    pitch = min((st for st in x.stride() if st > 1), default=1)
+    need = (need + pitch - 1) // pitch * pitch
+    return torch.empty(need, device=x.device, dtype=x.dtype).as_strided(x.shape, x.stride())
+
+
 class _SegLoss(torch.autograd.Function):
     """w_ce * CE + w_dice * SoftDice + w_ti * (B)TI of one deep-supervision scale from two passes over the logits
     (csrc/dsloss.cu).  cfg = (w_ce, w_dice, w_ti, batch_dice, do_bg, smooth, ddp, table | None, connectivity, min_thick)."""
@@ -543,7 +553,7 @@ class _SegLoss(torch.autograd.Function):
         g = gout.to(torch.float64)
         coef32 = (coef * g).float().contiguous()
         scal = (torch.stack([g * (w_ce / (B * V)), g * (w_ti / B)])).float().contiguous()
-        dx = torch.empty_strided(x.shape, x.stride(), device=x.device, dtype=x.dtype)
+        dx = _empty_like_strided(x)
         check(_lib.lib().nextou_dsloss_bwd(ptr(x), dtype_code(x), ll(sb), ll(sc), ll(sv), B, NC, ll(V), ptr(y),
                                            _TGT_CODE[y.dtype], ptr(crit if has_crit else None), ptr(coef32[0]), ptr(coef32[1]),
                                            ptr(scal), ptr(dx), ll(sb), ll(sc), ll(sv), cstream()), "nextou_dsloss_bwd")
@@ -1112,6 +1122,34 @@ def add_tokens(a, b):
     return _AddTokens.apply(a, b)
 
 
+def _rows_view_ok(t: torch.Tensor, cols: int, per: int) -> bool:
+    """True if the [rows, cols] rectangle starting at t (cols >= t.shape[1], the channel padding included) can be moved with
+    16-byte vectors: unit inner stride, pitch / base aligned, rectangle inside the row pitch and inside the storage."""
+    if t.dim() != 2 or t.stride(1) != 1 or t.stride(0) % per or t.stride(0) < cols or t.data_ptr() % 16:
+        return False
+    need = t.storage_offset() + (t.shape[0] - 1) * t.stride(0) + cols
+    return need <= t.untyped_storage().nbytes() // t.element_size()
+
+
+def rows_copy_add(a: torch.Tensor, b: Optional[torch.Tensor], out: torch.Tensor) -> bool:
+    """out[:, :C] = a (+ b) for [rows, C] token views of different pitch / column offset through csrc/pool.cu's vector kernel;
+    the padding lanes up to the next multiple of 16 bytes are moved along (don't-care).  Returns False (nothing done) when a
+    view is not vector-addressable: the caller falls back to the strided ATen op."""
+    if a.dtype != out.dtype or (b is not None and b.dtype != a.dtype) or a.dtype not in (torch.bfloat16, torch.float32):
+        return False
+    per = 8 if a.dtype == torch.bfloat16 else 4
+    C = a.shape[1]
+    cols = (C + per - 1) // per * per
+    if out.shape != a.shape or (b is not None and b.shape != a.shape) or a.shape[0] == 0:
+        return False
+    if not all(_rows_view_ok(t, cols, per) for t in (a, out) + ((b,) if b is not None else ())):
+        return False
+    _need_cuda(a, b, out)
+    check(_lib.lib().nextou_rows_copy_add(ptr(a), ll(a.stride(0)), ptr(b), ll(0 if b is None else b.stride(0)), ptr(out),
+                                          ll(out.stride(0)), ll(a.shape[0]), cols, dtype_code(a), cstream()), "nextou_rows_copy_add")
+    return True
+
+
 def _sum_grads(g1: torch.Tensor, g2: torch.Tensor) -> torch.Tensor:
     """g1 + g2 for two [rows, C] token gradients, keeping the channel-padded layout: one vectorised pass over the physical
     rows when both share it, else one strided add INTO a padded buffer (autograd's own accumulation would produce an
@@ -1123,7 +1161,8 @@ def _sum_grads(g1: torch.Tensor, g2: torch.Tensor) -> torch.Tensor:
     if fa is not None and fb is not None and fa.shape == fb.shape and fa.shape[1] % 8 == 0:
         return (fa + fb)[:, :a.shape[1]]
     out = padded_like(a.shape[0], a.shape[1], a.dtype, a.device)
-    torch.add(a, b, out=out)
+    if not rows_copy_add(a, b, out):          # e.g. the skip half of a concatenation gradient (pitch 80) + a pitch-40 gradient
+        torch.add(a, b, out=out)
     return out
 
 
@@ -1167,7 +1206,8 @@ class _CatTokens(torch.autograd.Function):
         ca, cb = a.shape[1], b.shape[1]
         out = padded_like(a.shape[0], ca + cb, a.dtype, a.device)
         out[:, :ca].copy_(a)
-        out[:, ca:].copy_(b)
+        if not rows_copy_add(b, None, out[:, ca:]):
+            out[:, ca:].copy_(b)
         ctx.split = ca
         return out
 

@@ -288,6 +288,27 @@ def test_norm_act_forward_backward(dtype, C, rows, instances, slope):
         assert ((gg.grad.cpu() - go.grad).norm() / go.grad.norm()).item() < 2e-2
 
 
+@pytest.mark.parametrize("dtype", [torch.bfloat16, torch.float32], ids=["bf16", "f32"])
+@pytest.mark.parametrize("rows,C", [(5000, 33), (777, 66), (64, 132), (3, 8)])
+def test_rows_copy_add_between_different_pitches(dtype, rows, C):
+    """Skip half of the concat buffer / fan-out gradient sum: views with a column offset and different pitches."""
+    from nextou_b200 import ops
+    g = torch.Generator().manual_seed(rows + C)
+    P = ops.pad8(C)
+    big = torch.randn(rows, 2 * P, generator=g).to(dtype).to(DEV)         # [up | gap | skip] rows
+    small = torch.randn(rows, P, generator=g).to(dtype).to(DEV)
+    a, b = big[:, P:P + C], small[:, :C]
+    out = ops.padded_like(rows, C, dtype, DEV)
+    assert ops.rows_copy_add(a, b, out)
+    assert torch.equal(out, a + b)
+    dst = torch.zeros(rows, 2 * P, device=DEV, dtype=dtype)
+    assert ops.rows_copy_add(b, None, dst[:, P:P + C])
+    assert torch.equal(dst[:, P:P + C], b) and torch.count_nonzero(dst[:, :P]) == 0
+    # not vector-addressable (odd pitch): refused, the caller falls back to ATen
+    odd = torch.randn(rows, C + 1, generator=g).to(dtype).to(DEV)[:, :C]
+    assert not ops.rows_copy_add(odd, None, out) or (C + 1) % 8 == 0
+
+
 # ------------------------------------------------------------------------------------------------
 # BTI / TI loss
 # ------------------------------------------------------------------------------------------------
