@@ -297,6 +297,16 @@ int nextou_conv3d_ndhwc_strided_wgrad(const void* dy, long long ldy, const void*
 int nextou_rows_copy_add(const void* a, long long lda, const void* b, long long ldb, void* out, long long ldo, long long rows,
                          int cols, int dtype, void* stream);
 
+/* First convolution of the network (Cin = image modalities <= 4, Cout <= 64; NexToU_Encoder_Decoder.py:125-141 stage 0): K =
+ * taps x Cin is far below one tensor-core slab, so these are streaming CUDA-core kernels.  x, out / dy: bf16 token-major;
+ * w: the fp32 master weight (Cout, Cin, kd, kh, kw) (rounded to bf16 on load, like the operand packs of the tensor-core path);
+ * dW[Cout][taps][cin_stride] fp32, zero-filled by the caller.  `supported` tells whether a layer is covered (taps x Cin <= 12). */
+int nextou_conv3d_small_cin_supported(int Cin, int Cout, int kd, int kh, int kw, long long ldo);
+int nextou_conv3d_small_cin_fwd(const void* x, long long ldx, int B, int D, int H, int W, int Cin, const float* w, int Cout,
+                                int kd, int kh, int kw, const float* bias, void* out, long long ldo, void* stream);
+int nextou_conv3d_small_cin_wgrad(const void* dy, long long ldy, const void* x, long long ldx, int B, int D, int H, int W,
+                                  int Cin, int Cout, int kd, int kh, int kw, float* dW, int cin_stride, void* stream);
+
 /* Weight packing (one launch per layer and step): master weight w[R][Cc/groups][taps] (fp32 | bf16; nn.Conv layout
  * (Cout, Cin/groups, *k) or nn.ConvTranspose layout (Cin, Cout, *k)) ->
  *   A [R][taps][lda_c]  bf16 = w[r][c][t]       (forward operand;       lda_c >= Cc, zero padded)

@@ -104,12 +104,22 @@ class _ConvTokens(torch.autograd.Function):
 
     @staticmethod
     def forward(ctx, x, weight, bias, batch, spatial, gap=None, owner=None):
-        xb = ops.tma_ready_bf16(x)
         cout, cin = weight.shape[:2]
         ks = tuple(weight.shape[2:])
         gapw = 0 if gap is None else gap[1] - gap[0]
-        wp, wt = ops.pack_weight_pair(weight, conv=True, flip_b=True, want_b=ctx.needs_input_grad[0], gap=gap, owner=_unwrap(owner))
-        y = ops.conv_ndhwc_bf16(xb, batch, spatial, cin + gapw, wp, cout, ks, bias)[:, :cout]
+        # the network's first convolution (Cin = image modalities): K = taps x Cin is far below one tensor-core slab
+        ctx.small = gap is None and ops.conv_small_supported(cin, cout, ks, weight)
+        ctx.owner = owner
+        if ctx.small:      # scalar loads: no 16-byte row pitch needed, so the image is not copied into a channel-padded buffer
+            xb = x if (x.dtype == torch.bfloat16 and (x.stride(1) == 1 or x.shape[1] == 1)) else x.to(torch.bfloat16).contiguous()
+        else:
+            xb = ops.tma_ready_bf16(x)
+        if ctx.small:
+            y = ops.conv_small_fwd(xb, batch, spatial, weight, bias)[:, :cout]
+            wt = None
+        else:
+            wp, wt = ops.pack_weight_pair(weight, conv=True, flip_b=True, want_b=ctx.needs_input_grad[0], gap=gap, owner=_unwrap(owner))
+            y = ops.conv_ndhwc_bf16(xb, batch, spatial, cin + gapw, wp, cout, ks, bias)[:, :cout]
         ctx.save_for_backward(xb, weight)
         ctx.wt = wt            # data-gradient operator: [Cin (+ gap), flipped taps * cout_pad]
         ctx.meta = (batch, tuple(spatial), bias is not None, None if bias is None else bias.dtype, gap)
@@ -124,11 +134,15 @@ class _ConvTokens(torch.autograd.Function):
         cin_p = cin + (0 if gap is None else gap[1] - gap[0])        # physical input channels
         dyb = ops.tma_ready_bf16(dy)
         dx = dw = db = None
-        side = _fork_wgrad(ctx, dyb)
+        side = None if ctx.small else _fork_wgrad(ctx, dyb)
         if ctx.needs_input_grad[1]:
-            dw = ops.conv_wgrad_bf16(dyb, xb, batch, spatial, cin_p, cout, ks, side=side)
+            dw = ops.conv_small_wgrad(dyb, xb, batch, spatial, cin, cout, ks) if ctx.small else \
+                ops.conv_wgrad_bf16(dyb, xb, batch, spatial, cin_p, cout, ks, side=side)
         if ctx.needs_input_grad[0]:
-            dx = ops.conv_ndhwc_bf16(dyb, batch, spatial, cout, ctx.wt, cin_p, ks, None)[:, :cin_p]
+            wt = ctx.wt
+            if wt is None:     # small-Cin layer whose input wants a gradient (never the image itself): tensor-core data gradient
+                _, wt = ops.pack_weight_pair(weight, conv=True, flip_b=True, want_b=True, owner=_unwrap(ctx.owner))
+            dx = ops.conv_ndhwc_bf16(dyb, batch, spatial, cout, wt, cin_p, ks, None)[:, :cin_p]
         if side is not None:
             side.join()
             dw = dw()

@@ -702,6 +702,52 @@ def conv_ndhwc_bf16(x_tok: torch.Tensor, batch: int, spatial: Sequence[int], cin
     return out
 
 
+def _k3(spatial, ksize):
+    sp, ks = list(spatial), list(ksize)
+    while len(sp) < 3:
+        sp, ks = [1] + sp, [1] + ks
+    return sp, ks
+
+
+def conv_small_supported(cin: int, cout: int, ksize: Sequence[int], weight: torch.Tensor) -> bool:
+    """True for the network's first convolution (image modalities -> 33 channels): csrc/conv_small.cu covers it."""
+    _, ks = _k3([1] * len(ksize), ksize)
+    return bool(weight.dtype == torch.float32 and
+                _lib.lib().nextou_conv3d_small_cin_supported(int(cin), int(cout), ks[0], ks[1], ks[2], ll(pad8(cout))))
+
+
+def conv_small_fwd(x_tok: torch.Tensor, batch: int, spatial: Sequence[int], weight: torch.Tensor, bias: Optional[torch.Tensor]):
+    """Stride-1 'same' convolution with Cin <= 4 (csrc/conv_small.cu) on bf16 token rows -> padded [rows, pad8(cout)] bf16."""
+    _need_cuda(x_tok, weight)
+    assert x_tok.dtype == torch.bfloat16 and (x_tok.stride(1) == 1 or x_tok.shape[1] == 1)
+    cout, cin = weight.shape[:2]
+    sp, ks = _k3(spatial, weight.shape[2:])
+    V = batch * sp[0] * sp[1] * sp[2]
+    out = torch.empty((V, pad8(cout)), device=x_tok.device, dtype=torch.bfloat16)
+    w32 = weight.detach().contiguous()
+    b32 = None if bias is None else bias.detach().float().contiguous()
+    taps = ks[0] * ks[1] * ks[2]
+    with _lib.timed("conv_small", 2 * V * (cin + cout) + 4 * cin * cout * taps, 2 * V * cin * cout * taps):
+        check(_lib.lib().nextou_conv3d_small_cin_fwd(ptr(x_tok), ll(x_tok.stride(0)), batch, *sp, cin, ptr(w32), cout, *ks, ptr(b32),
+                                                     ptr(out), ll(out.stride(0)), cstream()), "nextou_conv3d_small_cin_fwd")
+    return out
+
+
+def conv_small_wgrad(dy_tok: torch.Tensor, x_tok: torch.Tensor, batch: int, spatial: Sequence[int], cin: int, cout: int,
+                     ksize: Sequence[int]) -> torch.Tensor:
+    """fp32 weight gradient (Cout, Cin, *ksize) of the small-Cin convolution."""
+    _need_cuda(dy_tok, x_tok)
+    assert dy_tok.dtype == torch.bfloat16 and x_tok.dtype == torch.bfloat16 and dy_tok.stride(0) % 8 == 0
+    sp, ks = _k3(spatial, ksize)
+    taps = ks[0] * ks[1] * ks[2]
+    dw = torch.zeros((cout, taps, cin), device=x_tok.device, dtype=torch.float32)
+    V = batch * sp[0] * sp[1] * sp[2]
+    with _lib.timed("conv_small", 2 * V * (cin + cout) + 4 * cin * cout * taps, 2 * V * cin * cout * taps):
+        check(_lib.lib().nextou_conv3d_small_cin_wgrad(ptr(dy_tok), ll(dy_tok.stride(0)), ptr(x_tok), ll(x_tok.stride(0)), batch, *sp,
+                                                       cin, cout, *ks, ptr(dw), cin, cstream()), "nextou_conv3d_small_cin_wgrad")
+    return dw.permute(0, 2, 1).reshape(cout, cin, *ksize)
+
+
 def _geom3(spatial, *lists):
     """Left-pad spatial / kernel / stride / padding lists to 3-D."""
     sp = list(spatial)

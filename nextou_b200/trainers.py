@@ -72,6 +72,40 @@ class nnUNetTrainer_NexToU(_Base):
         model.apply(InitWeights_He(1e-2))
         return model
 
+    # ---- B200 execution settings (no counterpart in the reference: it inherits these hooks from upstream nnU-Net) ----
+    #: autocast dtype of the stock train_step / validation_step / predictor.  Upstream opens `torch.autocast("cuda")` without a
+    #: dtype, i.e. fp16 + GradScaler; the tcgen05 kernels of this package take bf16 operands (fp16 inputs are widened to fp32
+    #: and fall back to the library GEMMs), so the trainer switches the process-wide CUDA autocast default to bf16 — same
+    #: 8-bit-exponent range as fp32, which makes the GradScaler a no-op.  Set NEXTOU_AUTOCAST=fp16 to keep upstream's dtype.
+    autocast_dtype = torch.bfloat16
+
+    def initialize(self):
+        import os
+        if os.environ.get("NEXTOU_AUTOCAST", "bf16").lower() not in ("fp16", "float16", "half") and torch.cuda.is_available():
+            torch.set_autocast_dtype("cuda", self.autocast_dtype)
+            self.print_to_log_file("nextou_b200: CUDA autocast dtype set to %s (tcgen05 tensor-core path)" % self.autocast_dtype)
+        parent = getattr(super(), "initialize", None)
+        if parent is not None:
+            parent()
+
+    def configure_optimizers(self):
+        """Upstream: torch.optim.SGD(lr, weight_decay, momentum 0.99, nesterov) + PolyLRScheduler.  Same hyper-parameters through
+        nextou_b200.optim.FusedSGD (one multi-tensor update that also refreshes the bf16 operand packs); gradient clipping stays
+        in upstream's train_step (clip_grad_norm_), so max_grad_norm is left unset here."""
+        from .optim import FusedSGD
+        params = [p for p in self.network.parameters() if p.requires_grad]
+        lr, wd = getattr(self, "initial_lr", 1e-2), getattr(self, "weight_decay", 3e-5)
+        if params and all(p.is_cuda and p.dtype == torch.float32 for p in params):
+            optimizer = FusedSGD(params, lr, weight_decay=wd, momentum=0.99, nesterov=True)
+        else:
+            optimizer = torch.optim.SGD(params, lr, weight_decay=wd, momentum=0.99, nesterov=True)
+        try:
+            from nnunetv2.training.lr_scheduler.polylr import PolyLRScheduler  # type: ignore
+            scheduler = PolyLRScheduler(optimizer, lr, getattr(self, "num_epochs", 1000))
+        except Exception:
+            scheduler = torch.optim.lr_scheduler.LambdaLR(optimizer, lambda e, n=getattr(self, "num_epochs", 1000): (1 - e / n) ** 0.9)
+        return optimizer, scheduler
+
 
 class nnUNetTrainer_NexToU_NoMirroring(nnUNetTrainer_NexToU):
     """No mirror augmentation / TTA (nnUNetTrainer_NexToU_NoMirroring.py:4-10)."""

@@ -396,3 +396,38 @@ def test_full_resolution_conv_layer_fwd_dgrad_wgrad(spatial, cin, cout, ks, gap)
         assert _rel(bd.grad, bias_ref) < 1e-4
     finally:
         torch.backends.cudnn.allow_tf32, torch.backends.cuda.matmul.allow_tf32 = old
+
+
+@pytest.mark.parametrize("B,spatial,cin,cout,ks", [
+    (1, (8, 32, 40), 1, 33, (1, 3, 3)),       # the first convolution of 3d_fullres_nextou (one CT modality)
+    (2, (24, 20), 1, 8, (3, 3)),               # 2-D, batch 2
+    (1, (4, 16, 24), 4, 33, (1, 1, 3)),        # four MR modalities, 3 taps
+    (1, (4, 16, 24), 2, 16, (1, 1, 1)),
+    (1, (5, 9, 11), 3, 40, (3, 1, 1))])
+def test_small_cin_convolution_fwd_dgrad_wgrad(B, spatial, cin, cout, ks):
+    """csrc/conv_small.cu (CUDA-core streaming kernels for Cin <= 4) through the autograd wrapper vs F.conv on the same
+    bf16-valued operands; the data gradient (only needed when the layer is not the first one) takes the tensor-core path."""
+    from nextou_b200 import _lib, native, ops
+    g = torch.Generator().manual_seed(cin * 11 + cout)
+    dim = len(spatial)
+    conv = F.conv3d if dim == 3 else F.conv2d
+    x = torch.randn(B, cin, *spatial, generator=g).bfloat16()
+    w = (torch.randn(cout, cin, *ks, generator=g) / (cin * 3) ** 0.5).bfloat16().float()
+    bias = torch.randn(cout, generator=g)
+    xr, wr, br = x.float().requires_grad_(True), w.clone().requires_grad_(True), bias.clone().requires_grad_(True)
+    want = conv(xr, wr, br, padding=[k // 2 for k in ks])
+    dy = torch.randn(want.shape, generator=g).bfloat16()
+    want.backward(dy.float())
+    assert ops.conv_small_supported(cin, cout, ks, w.to(DEV))
+    xt = x.permute(0, *range(2, 2 + dim), 1).reshape(-1, cin).contiguous().to(DEV).requires_grad_(True)     # unpadded rows
+    wd, bd = w.to(DEV).requires_grad_(True), bias.to(DEV).requires_grad_(True)
+    n0 = _lib.launch_count()
+    y = native.conv_tokens(xt, wd, bd, B, spatial)
+    assert _lib.launch_count() - n0 == 1                                   # no pack kernel, no padded copy of the image
+    got = _vol_of(y.detach(), B, cout, spatial)
+    assert _rel(got, want.detach()) < 4e-3, _rel(got, want.detach())
+    y.backward(_tok_of(dy, pad_nan=False).to(DEV)[:, :cout])
+    assert _rel(wd.grad.cpu(), wr.grad) < 1e-5, _rel(wd.grad.cpu(), wr.grad)
+    assert _rel(bd.grad.cpu(), br.grad) < 1e-4
+    gx = _vol_of(xt.grad, B, cin, spatial)
+    assert _rel(gx, xr.grad) < 6e-3, _rel(gx, xr.grad)

@@ -126,3 +126,33 @@ def test_fused_step_keeps_operand_packs_current():
                     l2.weight.bfloat16().float(), l2.bias)
     got = ops.from_tokens(y, 1, (6, 8, 8)).float()
     assert ((got - want).norm() / want.norm()).item() < 1e-2
+
+
+def test_trainer_hooks_select_the_tensor_core_path():
+    """nnUNetTrainer_NexToU.initialize() switches the process-wide CUDA autocast default to bf16, so that upstream's unchanged
+    train_step (`with autocast("cuda")`) reaches the tcgen05 kernels; configure_optimizers() returns FusedSGD with upstream's
+    hyper-parameters and a poly learning-rate schedule that the fused step follows."""
+    import types
+    from nextou_b200 import dense, trainers
+    from nextou_b200.optim import FusedSGD
+    old = torch.get_autocast_dtype("cuda")
+    try:
+        tr = trainers.nnUNetTrainer_NexToU(device="cuda")
+        tr.initialize()
+        assert torch.get_autocast_dtype("cuda") == torch.bfloat16
+        tr.network = torch.nn.Conv3d(8, 16, 1).to(DEV)
+        tr.initial_lr, tr.weight_decay, tr.num_epochs = 1e-2, 3e-5, 10
+        opt, sched = tr.configure_optimizers()
+        assert isinstance(opt, FusedSGD) and opt.param_groups[0]["momentum"] == 0.99 and opt.param_groups[0]["nesterov"]
+        dense.stats.clear()
+        x = torch.randn(1, 8, 4, 8, 8, device=DEV)
+        with torch.autocast("cuda"):                       # what upstream's train_step opens
+            y = dense.linear_tokens(__import__("nextou_b200").ops.as_tokens(x), tr.network)
+        assert y.dtype == torch.bfloat16 and dense.stats["tcgen05.linear"] == 1
+        y.float().mean().backward()
+        opt.step()
+        sched.step()
+        assert abs(float(opt.param_groups[0]["lr"]) - 1e-2 * 0.9 ** 0.9) < 1e-9
+        opt.step()
+    finally:
+        torch.set_autocast_dtype("cuda", old)
