@@ -321,6 +321,47 @@ def run_own(args):
             kt[key] = kt[key] * args.steps / roof_steps
     _lib.KernelTimers.enabled = set()
 
+    # ---- inference forward: what nnU-Net's sliding-window predictor calls per patch — eval mode, deep
+    # supervision off, every BatchNorm folded into the epilogue of the conv / GEMM that feeds it.  Secondary number, rank 0 only.
+    infer = None
+    if rank == 0 and not args.no_infer:
+        net = model
+        net.eval()
+        net.decoder.deep_supervision = False
+
+        def fwd():
+            with torch.no_grad(), torch.autocast("cuda", dtype=torch.bfloat16):
+                return net(x_dev)
+        side = torch.cuda.Stream()
+        side.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(side):
+            for _ in range(3):
+                fwd()
+        torch.cuda.current_stream().wait_stream(side)
+        torch.cuda.synchronize()
+        n0 = _lib.launch_count()
+        ig = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(ig):
+            iout = fwd()
+        ilaunch = _lib.launch_count() - n0
+        for _ in range(3):
+            ig.replay()
+        torch.cuda.synchronize()
+        i0, i1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        i0.record()
+        for _ in range(10):
+            ig.replay()
+        i1.record()
+        torch.cuda.synchronize()
+        ims = i0.elapsed_time(i1) / 10
+        infer = {"value": 1e3 / ims, "unit": "patches/s", "ms_per_patch": ims, "gpu_launches": ilaunch,
+                 "finite": bool(torch.isfinite(iout).all()),
+                 "config": "eval forward 1x1x64x224x192, deep supervision off, bf16 autocast, BatchNorm folded into the producing "
+                           "conv / GEMM epilogues, CUDA-graph replay, input resident"}
+        del ig
+        net.train()
+        net.decoder.deep_supervision = True
+
     if world > 1:
         t = torch.tensor([ms, ms_e2e], device=dev, dtype=torch.float64)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
@@ -389,6 +430,8 @@ def run_own(args):
                 "e2e": {"value": world * args.steps / (ms_e2e * 1e-3), "unit": "patches/s", "h2d_bytes_per_step": h2d,
                         "d2h_bytes_per_step": 8, "ms_per_step": ms_e2e / args.steps, "last_loss": last},
                 "gpu_launches": launches, "roofline": roofline}
+        if infer is not None:
+            line["inference"] = infer
         if world == 1 and not args.no_cpu_baseline:
             cores = os.cpu_count() or 1
             torch.set_num_threads(cores)
@@ -429,6 +472,7 @@ def main():
     ap.add_argument("--impl", default="own", choices=["own", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-graph", action="store_true", help="issue every kernel from Python instead of replaying the step graph")
+    ap.add_argument("--no-infer", action="store_true", help="skip the secondary inference-forward measurement")
     ap.add_argument("--torch-sgd", action="store_true", help="torch.optim.SGD(fused=True) + clip_grad_norm_ instead of FusedSGD (A/B)")
     args = ap.parse_args()
     if args.impl == "reference":

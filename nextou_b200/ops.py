@@ -1141,8 +1141,10 @@ def affine_act_tokens(x_tok, scale, shift, slope=1.0):
     _need_cuda(xf)
     P = xf.shape[1]
     y = torch.empty_like(xf)
-    check(_lib.lib().nextou_affine_act(ptr(xf), dtype_code(xf), P, ll(xf.shape[0]), ptr(_pad_vec(scale, P, 0.0)),
-                                       ptr(_pad_vec(shift, P, 0.0)), cf(slope), ptr(y), cstream()), "nextou_affine_act")
+    # (named: a temporary passed straight to ptr() is freed before the launch and its block re-used by the next temporary)
+    sc, sh = _pad_vec(scale, P, 0.0), _pad_vec(shift, P, 0.0)
+    check(_lib.lib().nextou_affine_act(ptr(xf), dtype_code(xf), P, ll(xf.shape[0]), ptr(sc), ptr(sh), cf(slope), ptr(y), cstream()),
+          "nextou_affine_act")
     return y[:, :C]
 
 

@@ -288,6 +288,22 @@ def test_norm_act_forward_backward(dtype, C, rows, instances, slope):
         assert ((gg.grad.cpu() - go.grad).norm() / go.grad.norm()).item() < 2e-2
 
 
+@pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16], ids=["f32", "bf16"])
+@pytest.mark.parametrize("C,rows", [(36, 1536), (33, 5000), (40, 1536), (324, 168)])
+def test_eval_mode_affine_act_on_channel_padded_rows(dtype, C, rows):
+    """Eval-mode BatchNorm (+ LeakyReLU) as a per-channel affine map on rows whose pitch is padded to 8 channels (the scale /
+    shift vectors are padded to the pitch: regression test for a freed-temporary bug that aliased the two vectors)."""
+    import torch.nn.functional as F
+    from nextou_b200 import ops
+    g = torch.Generator().manual_seed(C + rows)
+    x = torch.randn(rows, ops.pad8(C), generator=g).to(dtype).to(DEV)[:, :C]
+    scale, shift = (torch.rand(C, generator=g) + 0.5).to(DEV), torch.randn(C, generator=g).to(DEV)
+    y = ops.affine_act_tokens(x, scale, shift, 0.01)
+    want = F.leaky_relu(x.float() * scale + shift, 0.01)
+    tol = 1e-6 if dtype == torch.float32 else 2 ** -8
+    assert (y.float() - want).abs().max().item() <= tol * want.abs().max().item()
+
+
 @pytest.mark.parametrize("dtype", [torch.bfloat16, torch.float32], ids=["bf16", "f32"])
 @pytest.mark.parametrize("rows,C", [(5000, 33), (777, 66), (64, 132), (3, 8)])
 def test_rows_copy_add_between_different_pitches(dtype, rows, C):
