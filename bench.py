@@ -201,7 +201,8 @@ def run_own(args):
     _lib.lib()  # fail loudly if the CUDA library is missing
 
     model = build_nextou(CFG, seed=0).to(dev)
-    if world > 1:
+    diag = {k: os.environ.get(k) == "1" for k in ("NEXTOU_BENCH_NO_SYNCBN", "NEXTOU_BENCH_NO_ALLREDUCE")}   # diagnostics only
+    if world > 1 and not diag["NEXTOU_BENCH_NO_SYNCBN"]:
         # what upstream nnU-Net does before wrapping the network in DDP (nnUNetTrainer.initialize): batch statistics of the
         # 78 BatchNorm layers are then taken over the patches of ALL ranks (nextou_b200.ops.sync_norm_act_tokens)
         model = torch.nn.SyncBatchNorm.convert_sync_batchnorm(model)
@@ -216,7 +217,7 @@ def run_own(args):
     w[-1] = 0
     loss_fn = DeepSupervisionWrapper(inner, (w / w.sum()).tolist())
     params = [p for p in model.parameters() if p.requires_grad]
-    reducer = GradientAllReducer(params, world) if world > 1 else None
+    reducer = GradientAllReducer(params, world) if world > 1 and not diag["NEXTOU_BENCH_NO_ALLREDUCE"] else None
     if args.torch_sgd:
         opt = torch.optim.SGD(params, lr=1e-2, momentum=0.99, nesterov=True, weight_decay=3e-5, fused=True)
     else:
@@ -419,7 +420,9 @@ def run_own(args):
                 "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": ms / args.steps,
                 "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
                 "config": {"workload": WORKLOAD, "global_batch": world, "parallelism": f"dp{world}",
-                           "batch_norm": "per-GPU batch statistics" if world == 1 else "SyncBatchNorm over all ranks (as upstream DDP)",
+                           "batch_norm": "per-GPU batch statistics" if world == 1 or diag["NEXTOU_BENCH_NO_SYNCBN"] else
+                                         "SyncBatchNorm over all ranks (as upstream DDP), statistics exchanged over NVLink peer memory",
+                           **({"DIAGNOSTIC_RUN_NOT_A_BENCH_VALUE": [k for k, v in diag.items() if v]} if any(diag.values()) else {}),
                            "loss": "DeepSupervision(Dice+CE+1e-6*BTI, Synapse interactions)",
                            "optimizer": "clip 12 + SGD nesterov 0.99 wd 3e-5: " + ("torch.optim.SGD(fused=True) + clip_grad_norm_" if args.torch_sgd
                                          else "nextou_b200.optim.FusedSGD (csrc/optim.cu: norm, clip, update, operand packs in 4 launches)"),

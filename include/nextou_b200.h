@@ -234,6 +234,27 @@ int nextou_norm_bwd_reduce(const void* x, const void* dy, int dtype, int C, int 
 int nextou_norm_bwd_apply(const void* x, const void* dy, int dtype, int C, int c_valid, long long rows, int instances,
                           long long n_total, const float* mean, const float* invstd, const float* gamma, const float* beta,
                           float slope, const float* sums, float* partial, void* dx, float* dx_colsum, void* stream);
+/* First halves of nextou_norm_stats / nextou_norm_bwd_reduce alone: this rank's per-CTA partial rows [*nblk_out][2C] (sized by
+ * nextou_norm_plan), the input of the cross-rank finalize below. */
+int nextou_norm_partial_stats(const void* x, int dtype, int C, long long rows, float* partial, int* nblk_out, void* stream);
+int nextou_norm_bwd_partial(const void* x, const void* dy, int dtype, int C, int c_valid, long long rows, const float* mean,
+                            const float* invstd, const float* gamma, const float* beta, float slope, float* partial,
+                            int* nblk_out, void* stream);
+/* SyncBatchNorm statistics over NVLink peer memory (csrc/syncnorm.cu).  Upstream nnU-Net converts every BatchNorm with
+ * SyncBatchNorm.convert_sync_batchnorm under DDP: 78 layers x (forward + backward) = 156 latency-bound exchanges per step.  One
+ * kernel per exchange: local fp64 column sums -> stores into the slot of every peer (mapped peer addresses) -> per-CTA flags ->
+ * sum in rank order -> mean / invstd / running statistics (forward) or global sums (backward).  No host synchronisation, no
+ * collective library call.  peer_base: DEVICE array [world] with the base address of every rank's symmetric buffer as mapped
+ * on this rank; offset: byte offset of this call site's slot (nextou_sync_slot_bytes, same on all ranks, zeroed once); epoch:
+ * local device array of nextou_sync_slot_ctas zeroed uint64 counters owned by the call site. */
+int nextou_sync_slot_ctas(int C, int backward);
+long long nextou_sync_slot_bytes(int world, int C, int backward);
+int nextou_sync_norm_finalize(const float* partial, int nblk, int C, int c_valid, long long rows, float eps, void* const* peer_base,
+                              long long offset, int rank, int world, unsigned long long* epoch, float* mean, float* invstd,
+                              float* running_mean, float* running_var, float momentum, long long* num_batches_tracked,
+                              double* n_total, void* stream);
+int nextou_sync_norm_bwd_finalize(const float* partial, int nblk, int C, void* const* peer_base, long long offset, int rank, int world,
+                                  unsigned long long* epoch, float* sums_local, float* sums_global, void* stream);
 /* column sums of a dense [rows][C] matrix: sums[0][C] = sum_r x, sums[1][C] = sum_r x^2 (fp32); `partial` as for
  * nextou_norm_stats with instances = 1.  Bias gradients of the 1x1 / spatial convolutions (d bias = colsum(dY)). */
 int nextou_colsum(const void* x, int dtype, int C, long long rows, float* partial, float* sums, void* stream);

@@ -596,3 +596,38 @@ extern "C" int nextou_colsum(const void* x, int dtype, int C, long long rows, fl
   norm_bwd_finalize_kernel<<<dim3((2 * C + 31) / 32, 1), 32 * FIN_SLICES, 0, st>>>(partial, p.nblk, 2 * C, 1, sums);
   return check_launch("norm_bwd_finalize_kernel");
 }
+
+
+// The first half of nextou_norm_stats / nextou_norm_bwd_reduce alone: this rank's per-CTA partial rows [nblk][2C]
+// (nblk = nextou_norm_plan), for the cross-rank finalize of SyncBatchNorm (csrc/syncnorm.cu).
+extern "C" int nextou_norm_partial_stats(const void* x, int dtype, int C, long long rows, float* partial, int* nblk_out,
+                                         void* stream) {
+  NEXTOU_REQUIRE(x && partial && nblk_out, "norm_partial_stats: null pointer");
+  SweepPlan p;
+  int rc = plan_sweep(C, rows, 1, p);
+  if (rc) return rc;
+  DISPATCH_TV(dtype, {
+    rc = ensure_smem(norm_stats_kernel<T, NV>, p.smem);
+    if (rc) return rc;
+    norm_stats_kernel<T, NV><<<dim3(p.nblk, 1), p.threads, p.smem, (cudaStream_t)stream>>>((const T*)x, C, p.R, rows, partial);
+  })
+  *nblk_out = p.nblk;
+  return check_launch("norm_stats_kernel");
+}
+
+extern "C" int nextou_norm_bwd_partial(const void* x, const void* dy, int dtype, int C, int c_valid, long long rows,
+                                       const float* mean, const float* invstd, const float* gamma, const float* beta, float slope,
+                                       float* partial, int* nblk_out, void* stream) {
+  NEXTOU_REQUIRE(x && dy && mean && invstd && partial && nblk_out, "norm_bwd_partial: null pointer");
+  SweepPlan p;
+  int rc = plan_sweep(C, rows, 1, p);
+  if (rc) return rc;
+  DISPATCH_TV(dtype, {
+    rc = ensure_smem(norm_bwd_reduce_kernel<T, NV>, p.smem);
+    if (rc) return rc;
+    norm_bwd_reduce_kernel<T, NV><<<dim3(p.nblk, 1), p.threads, p.smem, (cudaStream_t)stream>>>(
+        (const T*)x, (const T*)dy, C, p.R, rows, mean, invstd, gamma, beta, slope, partial, c_valid);
+  })
+  *nblk_out = p.nblk;
+  return check_launch("norm_bwd_reduce_kernel");
+}

@@ -215,10 +215,9 @@ def batch_norm_tokens(tok: torch.Tensor, bn: torch.nn.modules.batchnorm._BatchNo
             track = bn.track_running_stats and bn.running_mean is not None
             if bn.momentum is None:
                 raise NotImplementedError("SyncBatchNorm with cumulative moving average (momentum=None)")
-            y = ops.sync_norm_act_tokens(tok, bn.weight, bn.bias, bn.running_mean if track else None,
-                                         bn.running_var if track else None, bn.momentum, bn.eps, slope,
-                                         bn.num_batches_tracked if track else None, bn.process_group, world)
-            return y if residual is None else ops.add_tokens(y, residual)
+            return ops.sync_norm_act_tokens(tok, bn.weight, bn.bias, bn.running_mean if track else None,
+                                            bn.running_var if track else None, bn.momentum, bn.eps, slope,
+                                            bn.num_batches_tracked if track else None, bn.process_group, world, residual)
         rm = rv = nbt = None
         momentum = 0.0
         if bn.training and bn.track_running_stats and bn.running_mean is not None:

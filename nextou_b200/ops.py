@@ -8,6 +8,7 @@ tensor already is channels-last.  There is no CPU or PyTorch fallback: a non-CUD
 from __future__ import annotations
 
 import ctypes
+import os
 from typing import Optional, Sequence, Tuple
 
 import torch
@@ -1057,13 +1058,26 @@ def _equal_rows(rows: int, group, world: int) -> bool:
     return hit
 
 
+# SyncBatchNorm statistics over NVLink peer memory (csrc/syncnorm.cu); False / NEXTOU_PEER_EXCHANGE=0: NCCL all-reduce (A/B)
+PEER_EXCHANGE = os.environ.get("NEXTOU_PEER_EXCHANGE", "1") != "0"
+
+
+def _peer_exchange(group, device):
+    if not PEER_EXCHANGE:
+        return None
+    from .parallel import PeerExchange
+    return PeerExchange.get(group, device)
+
+
 class _SyncNormAct(torch.autograd.Function):
-    """Train-mode SyncBatchNorm (+ LeakyReLU): statistics over the rows of ALL ranks.  Forward: local (sum x, sum x^2) ->
-    all-reduce -> normalise; backward: local (sum dy', sum dy' xhat) -> all-reduce -> dx with the global sums and row count
-    (torch.nn.SyncBatchNorm semantics: d gamma / d beta stay local, the gradient all-reduce averages them)."""
+    """Train-mode SyncBatchNorm (+ LeakyReLU): statistics over the rows of ALL ranks.  Forward: local per-CTA partial sums ->
+    one exchange kernel over NVLink peer memory (sum over ranks, mean / invstd / running statistics) -> normalise; backward:
+    local partials of (sum dy', sum dy' xhat) -> one exchange kernel -> dx with the global sums and row count
+    (torch.nn.SyncBatchNorm semantics: d gamma / d beta stay local, the gradient all-reduce averages them).  Without peer
+    memory the sums travel through NCCL all-reduces instead."""
 
     @staticmethod
-    def forward(ctx, x, gamma, beta, running_mean, running_var, momentum, eps, slope, tracked, group, world):
+    def forward(ctx, x, gamma, beta, running_mean, running_var, momentum, eps, slope, tracked, group, world, residual=None):
         xf, C = _physical_rows(x)
         _need_cuda(xf)
         T, P = xf.shape
@@ -1071,40 +1085,77 @@ class _SyncNormAct(torch.autograd.Function):
         f32 = lambda v: None if v is None else v.detach().float().contiguous()
         g32, b32 = f32(gamma), f32(beta)
         partial = _norm_partial(P, T, 1, xf.device)
-        sums = torch.empty(2 * P, device=xf.device, dtype=torch.float32)
-        check(L.nextou_colsum(ptr(xf), dtype_code(xf), P, ll(T), ptr(partial), ptr(sums), cstream()), "nextou_colsum")
-        mean, invstd, unbiased, n = sync_moments(sums.view(2, P), T, eps, group)
-        if running_mean is not None:
-            running_mean.mul_(1.0 - momentum).add_(mean[:C], alpha=momentum)
-            running_var.mul_(1.0 - momentum).add_(unbiased[:C], alpha=momentum)
-            if tracked is not None:
-                tracked.add_(1)
+        px = _peer_exchange(group, xf.device)
+        key = (gamma.data_ptr() if gamma is not None else id(ctx), P)
+        if px is not None:
+            nblk = ctypes.c_int(0)
+            check(L.nextou_norm_partial_stats(ptr(xf), dtype_code(xf), P, ll(T), ptr(partial), ctypes.byref(nblk), cstream()),
+                  "nextou_norm_partial_stats")
+            off, ep = px.slot((key, "fwd"), P, False)
+            mean = torch.empty(P, device=xf.device, dtype=torch.float32)
+            invstd = torch.empty_like(mean)
+            n = torch.empty((), device=xf.device, dtype=torch.float64)
+            track = running_mean is not None
+            check(L.nextou_sync_norm_finalize(ptr(partial), nblk.value, P, C, ll(T), cf(eps), ptr(px.peer_base), ll(off), px.rank,
+                                              px.world, ptr(ep), ptr(mean), ptr(invstd), ptr(running_mean if track else None),
+                                              ptr(running_var if track else None), cf(momentum), ptr(tracked if track else None),
+                                              ptr(n), cstream()), "nextou_sync_norm_finalize")
+        else:
+            sums = torch.empty(2 * P, device=xf.device, dtype=torch.float32)
+            check(L.nextou_colsum(ptr(xf), dtype_code(xf), P, ll(T), ptr(partial), ptr(sums), cstream()), "nextou_colsum")
+            mean, invstd, unbiased, n = sync_moments(sums.view(2, P), T, eps, group)
+            if running_mean is not None:
+                running_mean.mul_(1.0 - momentum).add_(mean[:C], alpha=momentum)
+                running_var.mul_(1.0 - momentum).add_(unbiased[:C], alpha=momentum)
+                if tracked is not None:
+                    tracked.add_(1)
         y = torch.empty_like(xf)
-        check(L.nextou_norm_apply_cv(ptr(xf), dtype_code(xf), P, C, ll(T), 1, ptr(mean), ptr(invstd), ptr(g32), ptr(b32),
-                                     cf(slope), ptr(y), cstream()), "nextou_norm_apply")
+        rf = None
+        if residual is not None:      # shortcut of the residual block, in the same physical layout as x
+            rf = full_rows(_tok2d(residual))
+            if rf is None or rf.shape != xf.shape or rf.dtype != xf.dtype:
+                rf = _rows_like(residual, T, C, P, xf.dtype)
+        check(L.nextou_norm_apply_res(ptr(xf), dtype_code(xf), P, C, ll(T), 1, ptr(mean), ptr(invstd), ptr(g32), ptr(b32),
+                                      cf(slope), ptr(rf), ptr(y), cstream()), "nextou_norm_apply")
+        ctx.has_residual = residual is not None
         # backward divides the all-reduced sums by the number of rows normalised together.  Equal row counts on every rank
-        # (one patch each: checked ONCE per (group, rows) on the host) -> T * world; else the true count from the all-reduce
+        # (one patch each: checked ONCE per (group, rows) on the host) -> T * world; else the true count from the exchange
         fix = None if _equal_rows(T, group, world) else ((T * world) / n).float().reshape(1)
         ctx.save_for_backward(xf, mean, invstd, g32, b32, fix)
-        ctx.meta = (C, P, T, slope, gamma is not None, None if gamma is None else gamma.dtype, group, world)
+        ctx.meta = (C, P, T, slope, gamma is not None, None if gamma is None else gamma.dtype, group, world, key)
         return y[:, :C]
 
     @staticmethod
     def backward(ctx, dy):
         import torch.distributed as dist
         xf, mean, invstd, g32, b32, fix = ctx.saved_tensors
-        C, P, T, slope, affine, pdt, group, world = ctx.meta
+        C, P, T, slope, affine, pdt, group, world, key = ctx.meta
         L = _lib.lib()
         dyf = _rows_like(dy, T, C, P, xf.dtype)
         partial = _norm_partial(P, T, 1, xf.device)
-        sums = torch.empty(2 * P, device=xf.device, dtype=torch.float32)
-        check(L.nextou_norm_bwd_reduce(ptr(xf), ptr(dyf), dtype_code(xf), P, C, ll(T), 1, ptr(mean), ptr(invstd), ptr(g32),
-                                       ptr(b32), cf(slope), ptr(partial), ptr(sums), cstream()), "nextou_norm_bwd_reduce")
-        local = sums.view(2, P)
-        dgamma = dbeta = None
-        if affine:
-            dbeta, dgamma = local[0, :C].clone().to(pdt), local[1, :C].clone().to(pdt)   # `sums` is reduced in place below
-        dist.all_reduce(sums, op=dist.ReduceOp.SUM, group=group)
+        px = _peer_exchange(group, xf.device)
+        if px is not None:
+            nblk = ctypes.c_int(0)
+            check(L.nextou_norm_bwd_partial(ptr(xf), ptr(dyf), dtype_code(xf), P, C, ll(T), ptr(mean), ptr(invstd), ptr(g32), ptr(b32),
+                                            cf(slope), ptr(partial), ctypes.byref(nblk), cstream()), "nextou_norm_bwd_partial")
+            off, ep = px.slot((key, "bwd"), P, True)
+            local = torch.empty(2 * P, device=xf.device, dtype=torch.float32)
+            sums = torch.empty(2 * P, device=xf.device, dtype=torch.float32)
+            check(L.nextou_sync_norm_bwd_finalize(ptr(partial), nblk.value, P, ptr(px.peer_base), ll(off), px.rank, px.world, ptr(ep),
+                                                  ptr(local), ptr(sums), cstream()), "nextou_sync_norm_bwd_finalize")
+            local = local.view(2, P)
+            dgamma = dbeta = None
+            if affine:
+                dbeta, dgamma = local[0, :C].to(pdt), local[1, :C].to(pdt)
+        else:
+            sums = torch.empty(2 * P, device=xf.device, dtype=torch.float32)
+            check(L.nextou_norm_bwd_reduce(ptr(xf), ptr(dyf), dtype_code(xf), P, C, ll(T), 1, ptr(mean), ptr(invstd), ptr(g32),
+                                           ptr(b32), cf(slope), ptr(partial), ptr(sums), cstream()), "nextou_norm_bwd_reduce")
+            local = sums.view(2, P)
+            dgamma = dbeta = None
+            if affine:
+                dbeta, dgamma = local[0, :C].clone().to(pdt), local[1, :C].clone().to(pdt)   # `sums` is reduced in place below
+            dist.all_reduce(sums, op=dist.ReduceOp.SUM, group=group)
         if fix is not None:
             sums.mul_(fix)      # uneven batch split: sums / n_true == (sums * T * world / n_true) / (T * world)
         dx = torch.empty_like(xf)
@@ -1113,14 +1164,14 @@ class _SyncNormAct(torch.autograd.Function):
                                       ptr(g32), ptr(b32), cf(slope), ptr(sums), ptr(partial), ptr(dx), ptr(dxsum), cstream()),
               "nextou_norm_bwd_apply")
         _DxColsum.put(dx, dxsum)
-        return dx[:, :C], dgamma, dbeta, None, None, None, None, None, None, None, None
+        return dx[:, :C], dgamma, dbeta, None, None, None, None, None, None, None, None, (dy if ctx.has_residual else None)
 
 
 def sync_norm_act_tokens(x_tok, gamma, beta, running_mean, running_var, momentum, eps, slope, num_batches_tracked, group,
-                         world: int):
-    """SyncBatchNorm (+ LeakyReLU) over the rows of every rank of `group` (equal row counts per rank: one patch each)."""
+                         world: int, residual=None):
+    """SyncBatchNorm (+ LeakyReLU) (+ residual shortcut) over the rows of every rank of `group`."""
     return _SyncNormAct.apply(x_tok, gamma, beta, running_mean, running_var, float(momentum), float(eps), float(slope),
-                              num_batches_tracked, group, int(world))
+                              num_batches_tracked, group, int(world), residual)
 
 
 def norm_act_tokens(x_tok, gamma, beta, running_mean=None, running_var=None, momentum=0.1, eps=1e-5, slope=1.0,

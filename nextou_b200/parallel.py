@@ -9,6 +9,7 @@ no copy into / out of communication buffers ever happens.
 """
 from __future__ import annotations
 
+import ctypes
 from typing import Iterable, List
 
 import torch
@@ -88,3 +89,64 @@ class GradientAllReducer:
         self._handles = []
         self._pending = [0] * len(self.buckets)
         torch._foreach_mul_(self.buckets, 1.0 / self.world)
+
+
+class PeerExchange:
+    """NVLink peer-memory workspace for the SyncBatchNorm statistics exchange (csrc/syncnorm.cu).
+
+    One symmetric buffer per process group (torch symmetric memory: every rank maps every peer's buffer), carved into one
+    slot per exchange call site (a layer's forward / backward statistics); `peer_base` is the device array of the peers' base
+    addresses the kernels index.  Everything is allocated and zeroed once, outside any CUDA-graph capture; slots are handed
+    out in first-use order, which is the same on every rank because all ranks run the same model."""
+    _instances = {}
+    BYTES = 48 << 20
+
+    def __init__(self, group, device):
+        import torch.distributed._symmetric_memory as symm
+        self.group = group
+        self.world = dist.get_world_size(group)
+        self.rank = dist.get_rank(group)
+        self.buf = symm.empty(self.BYTES // 8, dtype=torch.float64, device=device)
+        self.buf.zero_()
+        torch.cuda.synchronize(device)
+        self.handle = symm.rendezvous(self.buf, group if group is not None else dist.group.WORLD)
+        self.peer_base = torch.tensor(list(self.handle.buffer_ptrs), device=device, dtype=torch.int64)
+        self.epochs = torch.zeros(1 << 16, device=device, dtype=torch.int64)
+        self.offset = 0
+        self.epoch_used = 0
+        self.slots = {}
+        torch.cuda.synchronize(device)
+        dist.barrier(group)          # nobody pushes before every rank has zeroed its buffer
+
+    @classmethod
+    def get(cls, group, device):
+        """The exchange of `group`, or None when peer memory is unavailable (then SyncBatchNorm falls back to NCCL)."""
+        key = (id(group), device.index)
+        if key not in cls._instances:
+            inst = None
+            if dist.get_backend(group) == "nccl":
+                try:
+                    inst = cls(group, device)
+                except Exception as exc:      # no peer access / symmetric memory support on this system
+                    import warnings
+                    warnings.warn(f"nextou_b200: NVLink peer exchange unavailable ({exc}); SyncBatchNorm uses NCCL all-reduce")
+            cls._instances[key] = inst
+        return cls._instances[key]
+
+    def slot(self, key, C: int, backward: bool):
+        """(byte offset of the slot, int64 view of its epoch counters) of call site `key`."""
+        hit = self.slots.get(key)
+        if hit is None:
+            if torch.cuda.is_current_stream_capturing():
+                raise RuntimeError("run one eager step before capturing (exchange slots are handed out on first use)")
+            from . import _lib
+            L = _lib.lib()
+            L.nextou_sync_slot_bytes.restype = ctypes.c_longlong
+            nbytes = int(L.nextou_sync_slot_bytes(self.world, C, int(backward)))
+            ncta = int(L.nextou_sync_slot_ctas(C, int(backward)))
+            if self.offset + nbytes > self.BYTES or self.epoch_used + ncta > self.epochs.numel():
+                raise RuntimeError("PeerExchange workspace exhausted")
+            hit = self.slots[key] = (self.offset, self.epochs[self.epoch_used:self.epoch_used + ncta])
+            self.offset += nbytes
+            self.epoch_used += ncta
+        return hit

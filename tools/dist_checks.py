@@ -1,0 +1,184 @@
+"""Multi-GPU checks (run under torchrun, one rank per GPU; tests/test_gpu_multi.py launches it when >= 2 GPUs are visible):
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node N --master-addr 127.0.0.1 --master-port 29511 tools/dist_checks.py
+
+1. SyncBatchNorm through nextou_b200.dense — with the NVLink peer-memory exchange (csrc/syncnorm.cu) and with the NCCL
+   fallback — against an fp64 BatchNorm over the concatenated rows of all ranks: outputs, input gradients, parameter
+   gradients, running statistics, over several steps (the exchange slots are re-used every step).
+2. DDP batch-dice: the fused segmentation loss with ddp=True back-propagates world_size x the local derivative, like upstream's
+   AllGatherGrad; checked against the unfused composition (torch.distributed.nn all_gather) and an fp64 global-batch Dice.
+3. Data-parallel gradient parity: N ranks x 1 patch with SyncBatchNorm + GradientAllReducer vs ONE
+   process running the same network with plain BatchNorm on the batch of N patches; all-reduced gradients == gradients of the
+   batch-mean loss (teacher-forcing is not needed: identical kernels see identical statistics up to summation order).
+Exit code 0 iff every check passes on every rank."""
+import os
+import sys
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+import copy
+
+import torch
+import torch.distributed as dist
+
+from nextou_b200 import dense, ops
+
+
+def rel(a, b):
+    return float((a.double().cpu() - b.double().cpu()).norm() / b.double().cpu().norm().clamp_min(1e-30))
+
+
+def check_syncbn(rank, world, dev, log):
+    ok = True
+    rows, C = 4099, 33
+    for peer in (True, False):
+        ops.PEER_EXCHANGE = peer
+        bn = torch.nn.SyncBatchNorm(C).to(dev).train()
+        with torch.no_grad():
+            bn.weight.uniform_(0.5, 1.5, generator=torch.Generator(device=dev).manual_seed(1))
+            bn.bias.uniform_(-0.5, 0.5, generator=torch.Generator(device=dev).manual_seed(2))
+        for dtype, tol in ((torch.float32, 2e-5), (torch.bfloat16, 2e-2)):
+            ref = torch.nn.BatchNorm1d(C).double()
+            ref.load_state_dict({k: v.detach().cpu().double() if v.dtype.is_floating_point else v.cpu() for k, v in bn.state_dict().items()})
+            for step in range(3):
+                xs = [torch.randn(rows, C, generator=torch.Generator().manual_seed(7 + r + 10 * step)) * (1 + 0.5 * r) + 0.3 * r
+                      for r in range(world)]
+                gs = [torch.randn(rows, C, generator=torch.Generator().manual_seed(70 + r + 10 * step)) for r in range(world)]
+                x = xs[rank].to(dev, dtype).requires_grad_(True)
+                bn.zero_grad()
+                y = dense.batch_norm_tokens(x, bn, 0.01)
+                y.backward(gs[rank].to(dev, dtype))
+                ref.zero_grad()
+                xa = torch.cat([t.to(dtype).double() for t in xs]).requires_grad_(True)
+                ya = torch.nn.functional.leaky_relu(ref(xa), 0.01)
+                ya.backward(torch.cat([t.to(dtype).double() for t in gs]))
+                sl = slice(rank * rows, (rank + 1) * rows)
+                errs = dict(y=rel(y.detach(), ya.detach()[sl]), dx=rel(x.grad, xa.grad[sl]))
+                gw, gb = bn.weight.grad.clone(), bn.bias.grad.clone()
+                dist.all_reduce(gw)
+                dist.all_reduce(gb)
+                errs["dgamma"], errs["dbeta"] = rel(gw, ref.weight.grad), rel(gb, ref.bias.grad)
+                errs["rmean"], errs["rvar"] = rel(bn.running_mean, ref.running_mean), rel(bn.running_var, ref.running_var)
+                good = all(v <= tol for v in errs.values()) and int(bn.num_batches_tracked) == int(ref.num_batches_tracked)
+                ok = ok and good
+                log(f"syncbn peer={peer} {str(dtype)[6:]} step {step}: " + ", ".join(f"{k} {v:.1e}" for k, v in errs.items()) + (" OK" if good else " FAIL"))
+    ops.PEER_EXCHANGE = True
+    return ok
+
+
+def check_batch_dice(rank, world, dev, log):
+    from nextou_b200.losses import DC_and_CE_and_BTI_Loss
+    B, NC, sp = 1, 5, (6, 20, 24)
+    logits_all = [torch.randn(B, NC, *sp, generator=torch.Generator().manual_seed(100 + r)) for r in range(world)]
+    tgt_all = [torch.randint(0, NC, (B, 1, *sp), generator=torch.Generator().manual_seed(200 + r)).float() for r in range(world)]
+    exc = [[torch.tensor(1), torch.tensor(2)]]
+    mod = DC_and_CE_and_BTI_Loss({"batch_dice": True, "smooth": 1e-5, "do_bg": False, "ddp": True}, {},
+                                 {"dim": 3, "connectivity": 26, "inclusion": [], "exclusion": exc, "min_thick": 1},
+                                 weight_ce=0, weight_dice=1, weight_ti=0.0)
+    out = {}
+    for fused in (True, False):
+        mod.fused = fused
+        lg = logits_all[rank].to(dev).requires_grad_(True)
+        val = mod(lg, tgt_all[rank].to(dev))
+        val.backward()
+        g = lg.grad.clone()
+        out[fused] = (float(val.detach()), g)
+    # fp64 reference: Dice over the global batch; DDP averages the ranks' gradients, each rank's loss = the global Dice
+    lgs = [t.double().requires_grad_(True) for t in logits_all]
+    p = [torch.softmax(t, 1) for t in lgs]
+    onehot = [torch.zeros_like(pp).scatter_(1, t.long(), 1) for pp, t in zip(p, tgt_all)]
+    axes = (0, 2, 3, 4)
+    inter = sum((pp * oh).sum(axes) for pp, oh in zip(p, onehot))[1:]
+    pred = sum(pp.sum(axes) for pp in p)[1:]
+    gt = sum(oh.sum(axes) for oh in onehot)[1:]
+    dc = -((2 * inter + 1e-5) / torch.clip(gt + pred + 1e-5, 1e-8)).mean()
+    (dc * world).backward()          # every rank holds this loss; the all-reduce SUM of upstream's AllGatherGrad adds world copies
+    ref_g = lgs[rank].grad
+    e_val = abs(out[True][0] - float(dc)) / abs(float(dc))
+    e_f, e_u = rel(out[True][1], ref_g), rel(out[False][1], ref_g)
+    good = e_val <= 1e-5 and e_f <= 1e-4 and e_u <= 1e-4
+    log(f"batch-dice ddp: value {e_val:.1e}, fused grad vs fp64 global {e_f:.1e}, unfused (torch all_gather) {e_u:.1e}" + (" OK" if good else " FAIL"))
+    return good
+
+
+def check_gradient_parity(rank, world, dev, log):
+    from nextou_b200.factory import MINI3D, build_nextou
+    from nextou_b200.parallel import GradientAllReducer
+    torch.backends.cudnn.allow_tf32 = False
+    torch.backends.cuda.matmul.allow_tf32 = False
+    cfg = MINI3D
+    xs = [torch.randn(1, 1, *cfg["patch"], generator=torch.Generator().manual_seed(r)) for r in range(world)]
+    base = build_nextou(cfg, seed=0)
+    model = torch.nn.SyncBatchNorm.convert_sync_batchnorm(copy.deepcopy(base)).to(dev).train()
+    params = [p for p in model.parameters() if p.requires_grad]
+    red = GradientAllReducer(params, world)
+    red.zero_grad()
+    outs = model(xs[rank].to(dev))
+    sum(o.float().mean() for o in outs).backward()
+    red.all_reduce()
+    torch.cuda.synchronize()
+    ok = True
+    if rank == 0:
+        ref = copy.deepcopy(base).to(dev).train()               # plain BatchNorm over the batch of `world` patches
+        outs = ref(torch.cat(xs).to(dev))
+        # mean over the batch of each output == mean over ranks of the per-patch means
+        sum(o.float().mean() for o in outs).backward()
+        num = den = 0.0
+        worst = ("", 0.0)
+        n_tensors = n_close = 0
+        gmax = max(p.grad.norm().item() for p in ref.parameters() if p.grad is not None)
+        for (n, p), (_, q) in zip(model.named_parameters(), ref.named_parameters()):
+            if q.grad is None or n.startswith("decoder.encoder."):
+                continue
+            d = (p.grad - q.grad).double().norm().item()
+            num += d * d
+            den += q.grad.double().norm().item() ** 2
+            if n.endswith(("conv.bias", "fc1.0.bias", "fc2.0.bias", "nn.0.bias")) and "seg_layers" not in n:
+                continue            # bias in front of a norm: analytically zero gradient (round-off only)
+            r = d / max(q.grad.norm().item(), 1e-3 * gmax)
+            n_tensors += 1
+            n_close += r <= 5e-2
+            if r > worst[1]:
+                worst = (n, r)
+        total = (num / den) ** 0.5
+        # no teacher forcing here: the two runs sum their batch statistics in different orders, and a randomly initialised
+        # NexToU flips a few near-tied neighbours / max-pool positions on such 1e-7 differences.  Hence an
+        # overall bound plus a bound on the share of tensors that are off (the single-GPU test with replayed graphs has 5e-2
+        # for every tensor)
+        ok = total <= 2e-2 and n_close >= 0.85 * n_tensors and worst[1] <= 0.3
+        log(f"gradient parity {world} ranks x 1 patch vs 1 process x batch {world}: overall relative L2 {total:.2e}, "
+            f"{n_close}/{n_tensors} tensors within 5e-2, worst {worst[0]} {worst[1]:.2e}" + (" OK" if ok else " FAIL"))
+    return ok
+
+
+def main():
+    rank, world, local = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"]), int(os.environ["LOCAL_RANK"])
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    dist.init_process_group("nccl", device_id=dev)
+
+    def log(msg):
+        if rank == 0:
+            print(msg, flush=True)
+    which = sys.argv[1:] or ["syncbn", "dice", "grads"]
+    ok = True
+    if "syncbn" in which:
+        ok = check_syncbn(rank, world, dev, log) and ok
+    if "dice" in which:
+        ok = check_batch_dice(rank, world, dev, log) and ok
+    if "grads" in which:
+        ok = check_gradient_parity(rank, world, dev, log) and ok
+    t = torch.tensor([1.0 if ok else 0.0], device=dev)
+    dist.all_reduce(t, op=dist.ReduceOp.MIN)
+    log("ALL CHECKS PASSED" if float(t) == 1.0 else "SOME CHECK FAILED")
+    torch.cuda.synchronize()
+    import threading
+    threading.Timer(15.0, lambda: os._exit(0 if float(t) == 1.0 else 1)).start()
+    try:
+        dist.barrier()
+        dist.destroy_process_group()
+    finally:
+        os._exit(0 if float(t) == 1.0 else 1)
+
+
+if __name__ == "__main__":
+    main()
