@@ -328,6 +328,14 @@ int nextou_conv3d_small_cin_fwd(const void* x, long long ldx, int B, int D, int 
 int nextou_conv3d_small_cin_wgrad(const void* dy, long long ldy, const void* x, long long ldx, int B, int D, int H, int W,
                                   int Cin, int Cout, int kd, int kh, int kw, float* dW, int cin_stride, void* stream);
 
+/* Weight gradient of a down-sampling convolution (3 x 3 in-plane kernel, in-plane stride 2, padding 1; depth kernel 1 | 3, depth
+ * stride 1 | 2) with halo reuse over the four (h, w)-parity planes of the input (tensor maps with doubled strides over the same
+ * memory: no copy).  Covers ceil16(Cin) * 9 <= 512 (the full-resolution encoder layer); `supported` tells. */
+int nextou_conv3d_ndhwc_planes_wgrad_supported(int Cin, int kd, int kh, int kw, int sd, int sh, int sw, int pd, int ph, int pw);
+int nextou_conv3d_ndhwc_planes_wgrad(const void* dy, long long ldy, const void* x, long long ldx, int B, int Do, int Ho, int Wo,
+                                     int Di, int Hi, int Wi, int Cin, int Cout, int kd, int sd, int pd, float* dW, int cin_stride,
+                                     void* stream);
+
 /* Weight packing (one launch per layer and step): master weight w[R][Cc/groups][taps] (fp32 | bf16; nn.Conv layout
  * (Cout, Cin/groups, *k) or nn.ConvTranspose layout (Cin, Cout, *k)) ->
  *   A [R][taps][lda_c]  bf16 = w[r][c][t]       (forward operand;       lda_c >= Cc, zero padded)

@@ -683,6 +683,213 @@ extern "C" int nextou_conv3d_ndhwc_halo_wgrad(const void* dy, long long ldy, con
 }
 
 // ======================================================================================================
+// Weight gradient of the DOWN-SAMPLING convolution of an encoder stage (3x3 in-plane kernel, in-plane stride 2, padding 1;
+// NexToU_Encoder_Decoder.py:125-141, stages 1-5) with halo reuse:  dW[co][tap][ci] += sum_o dY[o][co] * X[2o + tap - 1][ci].
+// The per-tap kernel of gemm_tcgen05.cu gathers X with an element-strided TMA box per tap (every voxel a separate fetch, 9
+// boxes per brick and depth tap: 895 us for enc s1 conv0, 672 MB of DRAM traffic against 273 MB algorithmic).  Here the input
+// is addressed as its four (h, w)-PARITY PLANES — plain tensor maps over the same memory with doubled row / column strides,
+// no copy — because tap (kh, kw) of output voxel (ho, wo) reads plane (kh != 1, kw != 1) at (ho - (kh == 0), wo - (kw == 0)):
+// inside a plane the taps of an 8 x 8 brick of output voxels are row-shifted views of ONE haloed 9 x 9 box, exactly like the
+// stride-1 kernel above.  Per brick a CTA fetches the dY brick and the four plane boxes and issues all nine in-plane taps.
+// Requires ceil16(Cin) * 9 <= 512 tensor-memory columns (Cin <= 48: the full-resolution layer that dominates); depth taps and
+// Cout tiles are separate CTAs, the voxel axis is split over CTAs and reduced with fp32 vector reds.
+// ======================================================================================================
+namespace nextou {
+
+struct WgradPlanesParams {
+  int Cout, Cin;
+  int Do, Ho, Wo, B;          // output (dY) grid
+  int nh, nw;                 // 8 x 8 bricks per output slice
+  int kd, pd, sd;             // depth taps, padding and stride (in-plane: 3 x 3, padding 1, stride 2)
+  int n_tile, n_mtiles, ksplit, tmem_cols, stages;
+  int xbox_bytes;             // one plane box {64 ch, 9, 9} rounded up to 1024
+  long long total_bricks;
+  float* dW;
+  int cin_stride;
+};
+
+__global__ void __launch_bounds__(WH_THREADS, 1)
+    wgrad_planes_tcgen05_kernel(const __grid_constant__ CUtensorMap tmDY, const __grid_constant__ CUtensorMap tmX00,
+                                const __grid_constant__ CUtensorMap tmX01, const __grid_constant__ CUtensorMap tmX10,
+                                const __grid_constant__ CUtensorMap tmX11, const WgradPlanesParams p) {
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  const int stage_bytes = 2 * 8192 + 4 * p.xbox_bytes;
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + (size_t)p.stages * stage_bytes);
+  uint64_t* empty_bar = full_bar + p.stages;
+  uint64_t* tmem_full = empty_bar + p.stages;
+  uint32_t* tmem_holder = reinterpret_cast<uint32_t*>(tmem_full + 1);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int mt = blockIdx.y % p.n_mtiles, kd_ = blockIdx.y / p.n_mtiles;
+  const int m0 = mt * 128;
+  const int ks = blockIdx.x;
+
+  if (warp == 0 && lane == 0) {
+    prefetch_tmap(&tmDY);
+    prefetch_tmap(&tmX00); prefetch_tmap(&tmX01); prefetch_tmap(&tmX10); prefetch_tmap(&tmX11);
+    for (int s = 0; s < p.stages; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1); }
+    mbar_init(tmem_full, 1);
+    fence_barrier_init();
+  }
+  if (warp == 2) tmem_alloc(tmem_holder, (uint32_t)p.tmem_cols);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_holder;
+  const long long nb = p.total_bricks > ks ? (p.total_bricks - ks + p.ksplit - 1) / p.ksplit : 0;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      int st = 0;
+      uint32_t ph = 0;
+      for (long long i = 0; i < nb; ++i) {
+        long long b = ks + i * p.ksplit;
+        const int wt = (int)(b % p.nw); b /= p.nw;
+        const int ht = (int)(b % p.nh); b /= p.nh;
+        const int d0 = (int)(b % p.Do);
+        const int bn = (int)(b / p.Do);
+        const int w0 = wt * 8, h0 = ht * 8;
+        const int di = d0 * p.sd + kd_ - p.pd;                 // out-of-range depth: the TMA unit zero-fills (= padding)
+        mbar_wait(&empty_bar[st], ph ^ 1);
+        mbar_expect_tx(&full_bar[st], (uint32_t)(2 * 8192 + 4 * 81 * 128));
+        uint8_t* sp = smem + (size_t)st * stage_bytes;
+        tma_load_5d(sp, &tmDY, &full_bar[st], m0, w0, h0, d0, bn);
+        tma_load_5d(sp + 8192, &tmDY, &full_bar[st], m0 + 64, w0, h0, d0, bn);
+        uint8_t* xb = sp + 2 * 8192;
+        // plane (ph, pw) holds input voxels (2i + ph, 2j + pw); every box starts one plane row / column before the brick
+        tma_load_5d(xb, &tmX00, &full_bar[st], 0, w0 - 1, h0 - 1, di, bn);
+        tma_load_5d(xb + p.xbox_bytes, &tmX01, &full_bar[st], 0, w0 - 1, h0 - 1, di, bn);
+        tma_load_5d(xb + 2 * p.xbox_bytes, &tmX10, &full_bar[st], 0, w0 - 1, h0 - 1, di, bn);
+        tma_load_5d(xb + 3 * p.xbox_bytes, &tmX11, &full_bar[st], 0, w0 - 1, h0 - 1, di, bn);
+        if (++st == p.stages) { st = 0; ph ^= 1; }
+      }
+    }
+  } else if (warp == 1) {
+    if (nb > 0) {
+      const uint32_t idesc = make_idesc_bf16(128, p.n_tile) | (1u << 15) | (1u << 16);  // both operands MN-major
+      const uint32_t xbox16 = (uint32_t)p.xbox_bytes >> 4;
+      int st = 0;
+      uint32_t ph = 0;
+      for (long long i = 0; i < nb; ++i) {
+        mbar_wait(&full_bar[st], ph);
+        tc_fence_after();
+        const uint32_t sp = smem_u32(smem + (size_t)st * stage_bytes);
+        if (elect_one()) {
+          const uint64_t ad0 = make_mnmajor_sw128_desc2(sp, 8192, 1024);
+          const uint64_t bd0 = make_mnmajor_sw128_desc2(sp + 2 * 8192, (uint32_t)p.xbox_bytes, 9 * 128);
+          const uint32_t accum0 = i != 0 ? 1u : 0u;
+#pragma unroll
+          for (int tp = 0; tp < 9; ++tp) {
+            const int kh = tp / 3, kw = tp % 3;
+            // tap (kh, kw): plane (kh != 1, kw != 1); inside the 9 x 9 box (origin = brick origin - 1) the view starts at row
+            // (kh != 0), column (kw != 0); rows of 128 B, in 16-byte units
+            const uint32_t toff = (uint32_t)((kh != 1 ? 2 : 0) + (kw != 1 ? 1 : 0)) * xbox16 +
+                                  (uint32_t)((kh != 0 ? 9 : 0) + (kw != 0 ? 1 : 0)) * 8u;
+#pragma unroll
+            for (int k = 0; k < 4; ++k)   // 16 voxels = two 8-voxel groups = 2 box rows of 9 x 128 B (144 units); dY: 2048 B
+              umma_f16(tmem_base + (uint32_t)(tp * p.n_tile), ad0 + (uint64_t)(k * 128), bd0 + (uint64_t)(toff + k * 144), idesc,
+                       k != 0 ? 1u : accum0);
+          }
+          umma_commit(&empty_bar[st]);
+        }
+        __syncwarp();
+        if (++st == p.stages) { st = 0; ph ^= 1; }
+      }
+      if (elect_one()) umma_commit(tmem_full);
+      __syncwarp();
+    }
+  } else if (nb > 0) {
+    mbar_wait(tmem_full, 0);
+    tc_fence_after();
+    const int q = warp & 3;
+    const int co = m0 + q * 32 + lane;
+    const bool vec = (p.cin_stride & 3) == 0 && (reinterpret_cast<uintptr_t>(p.dW) & 15) == 0;
+    for (int tp = 0; tp < 9; ++tp) {
+      const int tap = kd_ * 9 + tp;
+      for (int c = 0; c < p.n_tile; c += 16) {
+        uint32_t raw[16];
+        tmem_ld16(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(tp * p.n_tile + c), raw);
+        tmem_ld_wait();
+        if (co < p.Cout)
+          red_add_row16(p.dW + ((long long)co * (p.kd * 9) + tap) * p.cin_stride + c, raw, p.cin_stride - c, vec);
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 2) tmem_dealloc(tmem_base, (uint32_t)p.tmem_cols);
+}
+
+}  // namespace nextou
+
+// 1 if nextou_conv3d_ndhwc_planes_wgrad covers the layer (else: nextou_conv3d_ndhwc_strided_wgrad)
+extern "C" int nextou_conv3d_ndhwc_planes_wgrad_supported(int Cin, int kd, int kh, int kw, int sd, int sh, int sw, int pd, int ph, int pw) {
+  const int n_tile = (Cin + 15) / 16 * 16;
+  return kh == 3 && kw == 3 && sh == 2 && sw == 2 && ph == 1 && pw == 1 && (kd == 1 || kd == 3) && pd == kd / 2 && (sd == 1 || sd == 2) &&
+         n_tile * 9 <= 512;
+}
+
+// dW[Cout][kd*9][cin_stride] (fp32, zero-filled by the caller) += sum_o dy[o][co] * x[(do*sd + a - pd, 2ho + kh - 1, 2wo + kw - 1)][ci]
+// dy: bf16 tokens of the output grid [B][Do][Ho][Wo][ldy]; x: bf16 tokens of the input volume [B][Di][Hi][Wi][ldx]
+extern "C" int nextou_conv3d_ndhwc_planes_wgrad(const void* dy, long long ldy, const void* x, long long ldx, int B, int Do, int Ho,
+                                                int Wo, int Di, int Hi, int Wi, int Cin, int Cout, int kd, int sd, int pd, float* dW,
+                                                int cin_stride, void* stream) {
+  NEXTOU_REQUIRE(dy && x && dW, "conv3d_ndhwc_planes_wgrad: null pointer");
+  NEXTOU_REQUIRE(nextou_conv3d_ndhwc_planes_wgrad_supported(Cin, kd, 3, 3, sd, 2, 2, pd, 1, 1), "conv3d_ndhwc_planes_wgrad: unsupported layer");
+  NEXTOU_REQUIRE(B > 0 && Do > 0 && Ho > 0 && Wo > 0 && Di > 0 && Hi > 0 && Wi > 0 && Cout > 0 && cin_stride >= Cin, "conv3d_ndhwc_planes_wgrad: bad shape");
+  NEXTOU_REQUIRE(Ho == (Hi + 2 - 3) / 2 + 1 && Wo == (Wi + 2 - 3) / 2 + 1 && Do == (Di + 2 * pd - kd) / sd + 1, "conv3d_ndhwc_planes_wgrad: grids do not match");
+  NEXTOU_REQUIRE(ldy % 8 == 0 && ldy >= Cout && ldx % 8 == 0 && ldx >= Cin, "conv3d_ndhwc_planes_wgrad: pitches must be multiples of 8");
+  NEXTOU_REQUIRE(((uintptr_t)dy & 15) == 0 && ((uintptr_t)x & 15) == 0, "conv3d_ndhwc_planes_wgrad: 16-byte alignment");
+  WgradPlanesParams p = {};
+  p.Cout = Cout; p.Cin = Cin; p.Do = Do; p.Ho = Ho; p.Wo = Wo; p.B = B; p.kd = kd; p.pd = pd; p.sd = sd;
+  p.dW = dW; p.cin_stride = cin_stride;
+  p.nh = (Ho + 7) / 8; p.nw = (Wo + 7) / 8;
+  p.total_bricks = (long long)B * Do * p.nh * p.nw;
+  p.n_tile = (Cin + 15) / 16 * 16;
+  p.n_mtiles = (Cout + 127) / 128;
+  p.xbox_bytes = (81 * 128 + 1023) / 1024 * 1024;
+  p.tmem_cols = pow2_cols(9 * p.n_tile);
+  const long long tiles = (long long)kd * p.n_mtiles;
+  long long ksplit = (3LL * num_sms() + tiles - 1) / tiles;
+  if (ksplit > p.total_bricks / 16) ksplit = p.total_bricks / 16;
+  if (ksplit < 1) ksplit = 1;
+  p.ksplit = (int)ksplit;
+  p.stages = 3;
+  CUtensorMap tmDY, tmX[4];
+  {
+    cuuint64_t dims[5] = {(cuuint64_t)Cout, (cuuint64_t)Wo, (cuuint64_t)Ho, (cuuint64_t)Do, (cuuint64_t)B};
+    cuuint64_t str[4] = {(cuuint64_t)ldy * 2, (cuuint64_t)ldy * 2 * Wo, (cuuint64_t)ldy * 2 * Wo * Ho, (cuuint64_t)ldy * 2 * Wo * Ho * Do};
+    cuuint32_t box[5] = {64, 8, 8, 1, 1};
+    int rc = encode_bf16_map(&tmDY, dy, 5, dims, str, box, "wgrad planes dY");
+    if (rc) return rc;
+  }
+  for (int ph = 0; ph < 2; ++ph)
+    for (int pw = 0; pw < 2; ++pw) {
+      // parity plane (ph, pw) of the input: the same memory with doubled H / W strides, starting at voxel (ph, pw)
+      const int Hp = (Hi - ph + 1) / 2, Wp = (Wi - pw + 1) / 2;
+      if (Hp <= 0 || Wp <= 0) {   // degenerate (1-voxel extents): an empty plane contributes nothing; alias plane (0, 0) out of range
+        set_error("conv3d_ndhwc_planes_wgrad: extents < 2 are not supported");
+        return NEXTOU_ERR_UNSUPPORTED;
+      }
+      cuuint64_t dims[5] = {(cuuint64_t)Cin, (cuuint64_t)Wp, (cuuint64_t)Hp, (cuuint64_t)Di, (cuuint64_t)B};
+      cuuint64_t str[4] = {(cuuint64_t)ldx * 2 * 2, (cuuint64_t)ldx * 2 * Wi * 2, (cuuint64_t)ldx * 2 * Wi * Hi,
+                           (cuuint64_t)ldx * 2 * Wi * Hi * Di};
+      cuuint32_t box[5] = {64, 9, 9, 1, 1};
+      const char* base = reinterpret_cast<const char*>(x) + ((long long)ph * Wi + pw) * ldx * 2;
+      int rc = encode_bf16_map(&tmX[ph * 2 + pw], base, 5, dims, str, box, "wgrad planes X");
+      if (rc) return rc;
+    }
+  const size_t smem = 1024 + (size_t)p.stages * (2 * 8192 + 4 * p.xbox_bytes) + (2 * p.stages + 1) * sizeof(uint64_t) + 16;
+  int rc = ensure_smem(wgrad_planes_tcgen05_kernel, smem);
+  if (rc) return rc;
+  NEXTOU_REQUIRE(tiles <= 65535, "conv3d_ndhwc_planes_wgrad: too many tiles");
+  dim3 grid((unsigned)p.ksplit, (unsigned)tiles);
+  wgrad_planes_tcgen05_kernel<<<grid, WH_THREADS, smem, (cudaStream_t)stream>>>(tmDY, tmX[0], tmX[1], tmX[2], tmX[3], p);
+  return check_launch("wgrad_planes_tcgen05_kernel");
+}
+
+// ======================================================================================================
 // Diagnostics: issue / completion cost of back-to-back tcgen05.mma (M = 128, K = 16, bf16, SS operands) for a given N.
 // out[0] = cycles to ISSUE `reps` MMAs, out[1] = cycles until the last one has COMPLETED (commit + wait).
 // ======================================================================================================

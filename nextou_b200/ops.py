@@ -824,13 +824,22 @@ def conv_strided_wgrad_bf16(dense_tok: torch.Tensor, strided_tok: torch.Tensor, 
     cs = (c_strided + 3) // 4 * 4
     dw = torch.zeros((c_dense, taps, cs), device=dense_tok.device, dtype=torch.float32)
     V = batch * dsp[0] * dsp[1] * dsp[2]
+    L = _lib.lib()
+    # down-sampling 3x3 convolutions with a small Cin: halo reuse over the four parity planes of the input (csrc/conv_tcgen05.cu)
+    planes = bool(L.nextou_conv3d_ndhwc_planes_wgrad_supported(c_strided, *ks, *st, *pd)) and min(ssp[1], ssp[2]) >= 2
     with (side if side is not None else _null_ctx()):
-        with _lib.timed("wgrad_tcgen05", 2 * V * c_dense + 2 * batch * ssp[0] * ssp[1] * ssp[2] * c_strided + 4 * c_dense * c_strided * taps,
+        with _lib.timed("wgrad_planes_tcgen05" if planes else "wgrad_tcgen05",
+                        2 * V * c_dense + 2 * batch * ssp[0] * ssp[1] * ssp[2] * c_strided + 4 * c_dense * c_strided * taps,
                         2 * V * c_dense * c_strided * taps):
-            check(_lib.lib().nextou_conv3d_ndhwc_strided_wgrad(ptr(dense_tok), ll(dense_tok.stride(0)), ptr(strided_tok),
-                                                               ll(strided_tok.stride(0)), batch, *dsp, *ssp, c_strided, c_dense,
-                                                               *ks, *st, *pd, ptr(dw), cs, cstream()),
-                  "nextou_conv3d_ndhwc_strided_wgrad")
+            if planes:
+                check(L.nextou_conv3d_ndhwc_planes_wgrad(ptr(dense_tok), ll(dense_tok.stride(0)), ptr(strided_tok),
+                                                         ll(strided_tok.stride(0)), batch, *dsp, *ssp, c_strided, c_dense, ks[0],
+                                                         st[0], pd[0], ptr(dw), cs, cstream()), "nextou_conv3d_ndhwc_planes_wgrad")
+            else:
+                check(L.nextou_conv3d_ndhwc_strided_wgrad(ptr(dense_tok), ll(dense_tok.stride(0)), ptr(strided_tok),
+                                                          ll(strided_tok.stride(0)), batch, *dsp, *ssp, c_strided, c_dense,
+                                                          *ks, *st, *pd, ptr(dw), cs, cstream()),
+                      "nextou_conv3d_ndhwc_strided_wgrad")
     finish = lambda: dw[:, :, :c_strided]
     return finish if side is not None else finish()
 
