@@ -269,7 +269,7 @@ def run_own(args):
     if rank == 0:
         sampler.start()
     timed = {"knn_topk", "gemm_tcgen05", "conv_halo_tcgen05", "conv_pertap_tcgen05", "wgrad_halo_tcgen05", "wgrad_tcgen05",
-             "wgrad_planes_tcgen05", "conv_small"}
+             "wgrad_planes_tcgen05", "conv_small", "convtranspose_scatter"}
     if gstep is None:
         _lib.KernelTimers.enabled = timed
         _lib.KernelTimers.reset()

@@ -336,6 +336,15 @@ int nextou_conv3d_ndhwc_planes_wgrad(const void* dy, long long ldy, const void* 
                                      int Di, int Hi, int Wi, int Cin, int Cout, int kd, int sd, int pd, float* dW, int cin_stride,
                                      void* stream);
 
+/* Forward of a kernel == stride transposed convolution (decoder up-sampling, NexToU_Encoder_Decoder.py:273-276, 321) as ONE
+ * persistent GEMM over the input voxels whose epilogue scatters the kd*kh*kw class segments of a row to their output voxels
+ * (the input is read once).  wpack_t: the Bt pack of nextou_pack_weight on the (Cin, Cout, *k) weight, [Cout][taps][cin_pad64];
+ * out rows: columns [0, store_cols) written.  `supported`: ceil16(store_cols) <= 256. */
+int nextou_convtranspose_scatter_fwd_supported(int Cout, int store_cols, int kd, int kh, int kw);
+int nextou_convtranspose_scatter_fwd(const void* x, long long ldx, int B, int D, int H, int W, int Cin, const void* wpack_t, int Cout,
+                                     int kd, int kh, int kw, const float* bias, void* out, long long ldo, int store_cols,
+                                     void* stream);
+
 /* Weight packing (one launch per layer and step): master weight w[R][Cc/groups][taps] (fp32 | bf16; nn.Conv layout
  * (Cout, Cin/groups, *k) or nn.ConvTranspose layout (Cin, Cout, *k)) ->
  *   A [R][taps][lda_c]  bf16 = w[r][c][t]       (forward operand;       lda_c >= Cc, zero padded)

@@ -263,6 +263,11 @@ struct PGemmParams {
   int row32;
   const float* scale;
   float slope;
+  // scatter mode (kernel == stride transposed convolution, ED:273-276, 321): row m is INPUT voxel (b, d, h, w) of a [B][D][H][W]
+  // grid; the N tile holds `cpt` output parity classes of `cpb` columns each (class t = (a, i, j) of the kd x kh x kw kernel), and
+  // class t of row m is written to output voxel (d*kd + a, h*kh + i, w*kw + j) of the [B][D*kd][H*kh][W*kw] volume
+  int scatter, cpt, cpb, cp_store;
+  int D, H, W, kd, kh, kw;
 };
 
 __device__ __forceinline__ void mbar_arrive_cta(uint64_t* bar) {
@@ -289,7 +294,15 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1)
   __shared__ __align__(16) float sbias[512];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int n0 = blockIdx.y * p.block_n;
-  stage_bias(sbias, p.bias, n0, p.N, p.block_n, p.scale);
+  if (p.scatter) {     // every class segment carries the same per-channel bias
+    for (int i = threadIdx.x; i < p.block_n; i += blockDim.x) {
+      const int co = i % p.cpb;
+      sbias[i] = (p.bias != nullptr && co < p.N) ? p.bias[co] : 0.f;
+      sbias[256 + i] = 1.f;
+    }
+  } else {
+    stage_bias(sbias, p.bias, n0, p.N, p.block_n, p.scale);
+  }
 
   if (warp == 0 && lane == 0) {
     prefetch_tmap(&tmA);
@@ -307,9 +320,11 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1)
 
   if (warp == 0) {
     if (lane == 0) {
+      // B tile: rows n0 .. n0 + block_n of a plain [N][K] operand, or (scatter) `cpt` classes x `cpb` rows of [class][Cout][K]
+      const int bn1 = p.scatter ? 0 : n0, bn2 = p.scatter ? blockIdx.y * p.cpt : 0;
       if (p.b_resident) {
         mbar_expect_tx(bres_bar, (uint32_t)(p.kblocks * b_bytes));
-        for (int kb = 0; kb < p.kblocks; ++kb) tma_load_2d(smBres + (size_t)kb * b_bytes, &tmB, bres_bar, kb * GEMM_BK, n0);
+        for (int kb = 0; kb < p.kblocks; ++kb) tma_load_3d(smBres + (size_t)kb * b_bytes, &tmB, bres_bar, kb * GEMM_BK, bn1, bn2);
       }
       int st = 0;
       uint32_t ph = 0;
@@ -319,7 +334,7 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1)
           mbar_wait(&empty_bar[st], ph ^ 1);
           mbar_expect_tx(&full_bar[st], (uint32_t)stage_bytes);
           tma_load_2d(ring + (size_t)st * stage_bytes, &tmA, &full_bar[st], kb * GEMM_BK, m0);
-          if (!p.b_resident) tma_load_2d(ring + (size_t)st * stage_bytes + a_bytes, &tmB, &full_bar[st], kb * GEMM_BK, n0);
+          if (!p.b_resident) tma_load_3d(ring + (size_t)st * stage_bytes + a_bytes, &tmB, &full_bar[st], kb * GEMM_BK, bn1, bn2);
           if (++st == p.a_stages) { st = 0; ph ^= 1; }
         }
       }
@@ -360,7 +375,23 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1)
       const int acc = it & 1;
       mbar_wait(&tmem_full[acc], (it >> 1) & 1);
       tc_fence_after();
-      if (p.out_dtype == NEXTOU_BF16) {
+      if (p.scatter) {
+        // input voxel of this row -> the output voxel of every class of the tile; cp_store columns per class (zero padded)
+        long long t = row;
+        const int w = (int)(t % p.W); t /= p.W;
+        const int h = (int)(t % p.H); t /= p.H;
+        const int d = (int)(t % p.D);
+        const long long b = t / p.D;
+        const int Ho = p.H * p.kh, Wo = p.W * p.kw;
+        for (int tl = 0; tl < p.cpt; ++tl) {
+          const int cls = blockIdx.y * p.cpt + tl;
+          const int j = cls % p.kw, i = (cls / p.kw) % p.kh, a = cls / (p.kw * p.kh);
+          const long long orow = ((b * (p.D * p.kd) + d * p.kd + a) * Ho + h * p.kh + i) * Wo + w * p.kw + j;
+          __nv_bfloat16* dst = row < p.M ? reinterpret_cast<__nv_bfloat16*>(p.C) + orow * p.ldc : nullptr;
+          epilogue_row_bf16(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * p.block_n + tl * p.cpb), p.cpb, sbias + tl * p.cpb,
+                            dst, p.cp_store, false, p.slope);
+        }
+      } else if (p.out_dtype == NEXTOU_BF16) {
         __nv_bfloat16* dst = row < p.M ? reinterpret_cast<__nv_bfloat16*>(p.C) + row * p.ldc + n0 : nullptr;
         const long long left = p.ldc - n0;
         epilogue_row_bf16(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * p.block_n), p.block_n, sbias, dst,
@@ -443,10 +474,10 @@ extern "C" int nextou_gemm_bf16_tn_affine(const void* A, long long lda, const vo
     if (rc) return rc;
   }
   {
-    cuuint64_t dims[2] = {(cuuint64_t)K, (cuuint64_t)N};
-    cuuint64_t str[1] = {(cuuint64_t)ldb * 2};
-    cuuint32_t box[2] = {GEMM_BK, (cuuint32_t)p.block_n};
-    int rc = encode_bf16_map(&tmB, B, 2, dims, str, box, "B");
+    cuuint64_t dims[3] = {(cuuint64_t)K, (cuuint64_t)N, 1};
+    cuuint64_t str[2] = {(cuuint64_t)ldb * 2, (cuuint64_t)ldb * 2 * N};
+    cuuint32_t box[3] = {GEMM_BK, (cuuint32_t)p.block_n, 1};
+    int rc = encode_bf16_map(&tmB, B, 3, dims, str, box, "B");
     if (rc) return rc;
   }
   const size_t smem = 1024 + (size_t)p.a_stages * (p.b_resident ? a_bytes : a_bytes + b_bytes) + (p.b_resident ? (size_t)bres : 0) +
@@ -461,6 +492,90 @@ extern "C" int nextou_gemm_bf16_tn_affine(const void* A, long long lda, const vo
   if (ctas > p.m_tiles) ctas = p.m_tiles;
   if (ctas < 1) ctas = 1;
   NEXTOU_REQUIRE(n_tiles <= 65535, "gemm_bf16_tn: grid too large");
+  dim3 grid((unsigned)ctas, (unsigned)n_tiles);
+  gemm_pers_tcgen05_kernel<<<grid, GEMM_THREADS, smem, (cudaStream_t)stream>>>(tmA, tmB, p);
+  return check_launch("gemm_pers_tcgen05_kernel");
+}
+
+// Forward of a kernel == stride transposed convolution (decoder up-sampling, NexToU_Encoder_Decoder.py:273-276, 321) as ONE
+// persistent GEMM: every input voxel owns a disjoint kd x kh x kw block of output voxels, so
+//   out[(d*kd + a, h*kh + i, w*kw + j)][co] = bias[co] + sum_ci x[(d, h, w)][ci] * W[ci][co][a][i][j]
+// is x[M][Cin] times the [classes * Cout][Cin] operand, with the epilogue scattering the class segments of a row to their
+// output voxels.  The input is read once (the per-class launches of nextou_conv3d_ndhwc_strided_dgrad re-read it per class).
+// x: bf16 tokens [B*D*H*W][ldx]; wpack_t: bf16 [Cout][taps][cin_pad] (taps in (kd, kh, kw) order, cin_pad = ceil(Cin/64)*64: the
+// Bt pack of nextou_pack_weight on the (Cin, Cout, *k) weight); out: bf16 [B*D*kd*H*kh*W*kw][ldo], columns [0, store_cols) of
+// every row written (store_cols % 8 == 0, Cout <= store_cols <= ldo; [Cout, store_cols) zero-filled).
+extern "C" int nextou_convtranspose_scatter_fwd_supported(int Cout, int store_cols, int kd, int kh, int kw) {
+  const int cpb = (store_cols + 15) / 16 * 16;
+  return Cout > 0 && store_cols % 8 == 0 && store_cols >= Cout && cpb <= 256 && kd >= 1 && kh >= 1 && kw >= 1 && kd * kh * kw <= 64;
+}
+
+extern "C" int nextou_convtranspose_scatter_fwd(const void* x, long long ldx, int B, int D, int H, int W, int Cin, const void* wpack_t,
+                                                int Cout, int kd, int kh, int kw, const float* bias, void* out, long long ldo,
+                                                int store_cols, void* stream) {
+  NEXTOU_REQUIRE(x && wpack_t && out, "convtranspose_scatter_fwd: null pointer");
+  NEXTOU_REQUIRE(nextou_convtranspose_scatter_fwd_supported(Cout, store_cols, kd, kh, kw), "convtranspose_scatter_fwd: unsupported layer");
+  NEXTOU_REQUIRE(B > 0 && D > 0 && H > 0 && W > 0 && Cin > 0 && ldx % 8 == 0 && ldx >= Cin && ldo % 8 == 0 && ldo >= store_cols,
+                 "convtranspose_scatter_fwd: bad shape / pitches");
+  NEXTOU_REQUIRE(((uintptr_t)x & 15) == 0 && ((uintptr_t)wpack_t & 15) == 0 && ((uintptr_t)out & 15) == 0, "convtranspose_scatter_fwd: 16-byte alignment");
+  const long long M = (long long)B * D * H * W;
+  NEXTOU_REQUIRE(M < 2147483647LL, "convtranspose_scatter_fwd: too many voxels");
+  const int taps = kd * kh * kw;
+  PGemmParams p = {};
+  p.M = (int)M; p.N = Cout; p.K = Cin;
+  p.kblocks = (Cin + GEMM_BK - 1) / GEMM_BK;
+  p.last_ksteps = (Cin - (p.kblocks - 1) * GEMM_BK + 15) / 16;
+  p.scatter = 1;
+  p.cpb = (store_cols + 15) / 16 * 16;                 // tensor-memory columns / weight rows per class (UMMA N granularity)
+  p.cp_store = store_cols;
+  p.cpt = 1;
+  for (int c = taps; c >= 1; --c)                       // most classes per tile with cpt | taps and cpt * cpb <= 256
+    if (taps % c == 0 && c * p.cpb <= 256) { p.cpt = c; break; }
+  p.block_n = p.cpt * p.cpb;
+  p.tmem_cols = pow2_cols(2 * p.block_n);
+  p.m_tiles = (M + GEMM_BM - 1) / GEMM_BM;
+  p.C = out; p.ldc = ldo; p.out_dtype = NEXTOU_BF16; p.bias = bias; p.scale = nullptr; p.slope = 1.f; p.row32 = 0;
+  p.D = D; p.H = H; p.W = W; p.kd = kd; p.kh = kh; p.kw = kw;
+  const int a_bytes = GEMM_BM * GEMM_BK * 2, b_bytes = p.block_n * GEMM_BK * 2;
+  const int budget = 200 * 1024;
+  const long long bres = (long long)p.kblocks * b_bytes;
+  p.b_resident = bres <= budget - 3 * a_bytes ? 1 : 0;
+  {
+    const int per_stage = p.b_resident ? a_bytes : a_bytes + b_bytes;
+    int st = (int)((budget - (p.b_resident ? bres : 0)) / per_stage);
+    if (st > PG_MAX_STAGES) st = PG_MAX_STAGES;
+    NEXTOU_REQUIRE(st >= 2, "convtranspose_scatter_fwd: tile does not fit in shared memory");
+    p.a_stages = st;
+  }
+  const int cin_pad = p.kblocks * GEMM_BK;
+  CUtensorMap tmA, tmB;
+  {
+    cuuint64_t dims[2] = {(cuuint64_t)Cin, (cuuint64_t)M};
+    cuuint64_t str[1] = {(cuuint64_t)ldx * 2};
+    cuuint32_t box[2] = {GEMM_BK, GEMM_BM};
+    int rc = encode_bf16_map(&tmA, x, 2, dims, str, box, "convtranspose x");
+    if (rc) return rc;
+  }
+  {
+    // [Cout][taps][cin_pad] viewed as (ci, co, class): a box {64, cpb, cpt} lands as rows (class, co) = the N axis of the tile;
+    // rows co >= Cout are zero-filled by the TMA unit
+    cuuint64_t dims[3] = {(cuuint64_t)Cin, (cuuint64_t)Cout, (cuuint64_t)taps};
+    cuuint64_t str[2] = {(cuuint64_t)taps * cin_pad * 2, (cuuint64_t)cin_pad * 2};
+    cuuint32_t box[3] = {GEMM_BK, (cuuint32_t)p.cpb, (cuuint32_t)p.cpt};
+    int rc = encode_bf16_map(&tmB, wpack_t, 3, dims, str, box, "convtranspose weights");
+    if (rc) return rc;
+  }
+  const size_t smem = 1024 + (size_t)p.a_stages * (p.b_resident ? a_bytes : a_bytes + b_bytes) + (p.b_resident ? (size_t)bres : 0) +
+                      (2 * p.a_stages + 5) * sizeof(uint64_t) + 16;
+  int rc = ensure_smem(gemm_pers_tcgen05_kernel, smem);
+  if (rc) return rc;
+  const int n_tiles = taps / p.cpt;
+  int per_sm = (int)((220 * 1024) / smem);
+  if (per_sm > 512 / p.tmem_cols) per_sm = 512 / p.tmem_cols;
+  if (per_sm < 1) per_sm = 1;
+  long long ctas = ((long long)num_sms() * per_sm + n_tiles - 1) / n_tiles;
+  if (ctas > p.m_tiles) ctas = p.m_tiles;
+  if (ctas < 1) ctas = 1;
   dim3 grid((unsigned)ctas, (unsigned)n_tiles);
   gemm_pers_tcgen05_kernel<<<grid, GEMM_THREADS, smem, (cudaStream_t)stream>>>(tmA, tmB, p);
   return check_launch("gemm_pers_tcgen05_kernel");

@@ -226,7 +226,7 @@ class _ConvTransposeTokens(torch.autograd.Function):
         zero = (0,) * len(ks)
         # A = [Cin][tap][Cout pad] (operand of the data gradient), Bt = [Cout][tap][Cin pad] (operand of the forward)
         wa, wb = ops.pack_weight_pair(weight, conv=True, flip_b=False, owner=_unwrap(owner))
-        y = ops.conv_strided_dgrad_bf16(xb, batch, spatial, cin, wb, cout, ks, ks, zero, osp, bias)
+        y = ops.convtranspose_fwd_bf16(xb, batch, spatial, cin, wb, cout, ks, bias)
         ctx.save_for_backward(xb, weight)
         ctx.wa = wa
         ctx.meta = (batch, tuple(spatial), osp, bias is not None, None if bias is None else bias.dtype)
@@ -278,7 +278,7 @@ class _UpCatTokens(torch.autograd.Function):
         rows = skip.shape[0]
         buf = torch.empty((rows, pa + ops.pad8(cb)), device=x.device, dtype=torch.bfloat16)
         wa, wb = ops.pack_weight_pair(weight, conv=True, flip_b=False, owner=_unwrap(owner))
-        ops.conv_strided_dgrad_bf16(xb, batch, spatial, cin, wb, cout, ks, ks, zero, osp, bias, out=buf, store_cols=pa)
+        ops.convtranspose_fwd_bf16(xb, batch, spatial, cin, wb, cout, ks, bias, out=buf, store_cols=pa)
         if not ops.rows_copy_add(skip, None, buf[:, pa:pa + cb]):      # skip half behind the up-sampled half (ED:322)
             buf[:, pa:pa + cb].copy_(skip)
         ctx.save_for_backward(xb, weight)

@@ -809,6 +809,34 @@ def conv_strided_dgrad_bf16(dy_tok: torch.Tensor, batch: int, out_spatial: Seque
     return out
 
 
+def convtranspose_fwd_bf16(x_tok: torch.Tensor, batch: int, spatial: Sequence[int], cin: int, wpack_t: torch.Tensor, cout: int,
+                           ksize: Sequence[int], bias: Optional[torch.Tensor] = None, out: Optional[torch.Tensor] = None,
+                           store_cols: Optional[int] = None) -> torch.Tensor:
+    """Forward of a kernel == stride transposed convolution (ED:273-276, 321): x [rows_in, cin] on `spatial` -> padded
+    [rows_out, pad8(cout)] on spatial * ksize (or written into the first `store_cols` columns of `out`).  One scatter GEMM over the
+    input voxels (csrc/gemm_tcgen05.cu) when the class segment fits a tile, else one per-tap launch per output parity class."""
+    _need_cuda(x_tok, wpack_t)
+    assert x_tok.dtype == torch.bfloat16 and x_tok.stride(1) == 1 and wpack_t.dtype == torch.bfloat16
+    sp, ks = _k3(spatial, ksize)
+    osp = [n * k for n, k in zip(sp, ks)]
+    Vo = batch * osp[0] * osp[1] * osp[2]
+    if out is None:
+        out = torch.empty((Vo, pad8(cout)), device=x_tok.device, dtype=torch.bfloat16)
+    cols = int(out.stride(0)) if store_cols is None else int(store_cols)
+    L = _lib.lib()
+    if not L.nextou_convtranspose_scatter_fwd_supported(cout, cols, *ks) or out.dtype != torch.bfloat16:
+        zero = (0,) * len(ksize)
+        return conv_strided_dgrad_bf16(x_tok, batch, spatial, cin, wpack_t, cout, ksize, ksize, zero,
+                                       tuple(n * k for n, k in zip(spatial, ksize)), bias, out=out, store_cols=store_cols)
+    bias32 = None if bias is None else bias.detach().float().contiguous()
+    V = batch * sp[0] * sp[1] * sp[2]
+    taps = ks[0] * ks[1] * ks[2]
+    with _lib.timed("convtranspose_scatter", 2 * V * cin + 2 * Vo * cout + 2 * cin * cout * taps, 2 * V * cin * cout * taps):
+        check(L.nextou_convtranspose_scatter_fwd(ptr(x_tok), ll(x_tok.stride(0)), batch, *sp, cin, ptr(wpack_t), cout, *ks, ptr(bias32),
+                                                 ptr(out), ll(out.stride(0)), cols, cstream()), "nextou_convtranspose_scatter_fwd")
+    return out
+
+
 def conv_strided_wgrad_bf16(dense_tok: torch.Tensor, strided_tok: torch.Tensor, batch: int, dense_spatial: Sequence[int],
                             strided_spatial: Sequence[int], c_strided: int, c_dense: int, ksize: Sequence[int],
                             stride: Sequence[int], padding: Sequence[int], side: Optional["side_launch"] = None):
