@@ -43,6 +43,7 @@ struct ConvParams {
   int b_groups;          // groups per slab = ceil(kh*kw / b_group)
   int b_stages;          // depth of the weight ring (== all groups of all slabs when resident)
   int b_resident;        // weights loaded once per CTA and kept
+  int halves;            // 1: 16 x 8 bricks; 2: 16 x 16 bricks = two M = 128 accumulators that share every streamed weight tile
   void* C;
   long long ldc;
   int out_dtype;
@@ -74,25 +75,37 @@ __device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
 // Issue the MMAs of NT consecutive in-plane taps of a 3x3 kernel (NT = 9: the whole plane, 3: one kernel row, 1: one tap)
 // x KS K16-steps with compile-time descriptor deltas: per MMA two 64-bit adds + the tcgen05.mma, nothing else.
 // adesc0 / bdesc0 = descriptors of the group's first tap at k = 0; bstep = one tap's weight tile in 16-byte units.
-template <int KS, int NT>
-__device__ __forceinline__ void issue_group_3x3(uint32_t tacc, uint64_t adesc0, uint64_t bdesc0, uint32_t bstep, uint32_t idesc,
-                                                uint32_t accum_first) {
-  constexpr int BOXW = CV_TW + 2;
+template <int KS, int NT, int HALVES>
+__device__ __forceinline__ void issue_group_3x3(uint32_t tacc, uint32_t block_n, uint64_t adesc0, uint64_t bdesc0, uint32_t bstep,
+                                                uint32_t idesc, uint32_t accum_first) {
+  constexpr int BOXW = CV_TW * HALVES + 2;
 #pragma unroll
   for (int j = 0; j < NT; ++j) {
     const uint32_t aoff = (uint32_t)((j / 3) * BOXW + (j % 3)) * 8u;   // (kh * box_w + kw) rows of 128 B, in 16-byte units
 #pragma unroll
-    for (int k = 0; k < KS; ++k)
-      umma_f16(tacc, adesc0 + (uint64_t)(aoff + 2 * k), bdesc0 + (uint64_t)(j * bstep + 2 * k), idesc,
-               (j | k) != 0 ? 1u : accum_first);
+    for (int h = 0; h < HALVES; ++h)       // the second half of a wide brick starts 8 voxels (8 rows of 128 B) further along W
+#pragma unroll
+      for (int k = 0; k < KS; ++k)
+        umma_f16(tacc + (uint32_t)h * block_n, adesc0 + (uint64_t)(aoff + 64 * h + 2 * k), bdesc0 + (uint64_t)(j * bstep + 2 * k), idesc,
+                 (j | k) != 0 ? 1u : accum_first);
   }
 }
-template <int KS>
-__device__ __forceinline__ void issue_group_3x3_nt(int nt, uint32_t tacc, uint64_t adesc0, uint64_t bdesc0, uint32_t bstep,
-                                                   uint32_t idesc, uint32_t accum_first) {
-  if (nt == 9) issue_group_3x3<KS, 9>(tacc, adesc0, bdesc0, bstep, idesc, accum_first);
-  else if (nt == 3) issue_group_3x3<KS, 3>(tacc, adesc0, bdesc0, bstep, idesc, accum_first);
-  else issue_group_3x3<KS, 1>(tacc, adesc0, bdesc0, bstep, idesc, accum_first);
+template <int KS, int HALVES>
+__device__ __forceinline__ void issue_group_3x3_nt(int nt, uint32_t tacc, uint32_t block_n, uint64_t adesc0, uint64_t bdesc0,
+                                                   uint32_t bstep, uint32_t idesc, uint32_t accum_first) {
+  if (nt == 9) issue_group_3x3<KS, 9, HALVES>(tacc, block_n, adesc0, bdesc0, bstep, idesc, accum_first);
+  else if (nt == 3) issue_group_3x3<KS, 3, HALVES>(tacc, block_n, adesc0, bdesc0, bstep, idesc, accum_first);
+  else issue_group_3x3<KS, 1, HALVES>(tacc, block_n, adesc0, bdesc0, bstep, idesc, accum_first);
+}
+template <int HALVES>
+__device__ __forceinline__ void issue_group_3x3_ks(int ksteps, int nt, uint32_t tacc, uint32_t block_n, uint64_t ad, uint64_t bd,
+                                                   uint32_t bstep, uint32_t idesc, uint32_t accum_first) {
+  switch (ksteps) {
+    case 4: issue_group_3x3_nt<4, HALVES>(nt, tacc, block_n, ad, bd, bstep, idesc, accum_first); break;
+    case 3: issue_group_3x3_nt<3, HALVES>(nt, tacc, block_n, ad, bd, bstep, idesc, accum_first); break;
+    case 2: issue_group_3x3_nt<2, HALVES>(nt, tacc, block_n, ad, bd, bstep, idesc, accum_first); break;
+    default: issue_group_3x3_nt<1, HALVES>(nt, tacc, block_n, ad, bd, bstep, idesc, accum_first); break;
+  }
 }
 
 __global__ void __launch_bounds__(CV_THREADS, 1)
@@ -145,7 +158,7 @@ __global__ void __launch_bounds__(CV_THREADS, 1)
         const int ht = (int)(t % p.nh); t /= p.nh;
         const int d0 = (int)(t % p.D);
         const int bn = (int)(t / p.D);
-        const int h0 = ht * CV_TH, w0 = wt * CV_TW;
+        const int h0 = ht * CV_TH, w0 = wt * CV_TW * p.halves;
         int kd_ = 0, cb = 0;
         for (int s = 0; s < slabs; ++s) {
           mbar_wait(&emptyA[st], ph ^ 1);
@@ -203,7 +216,7 @@ __global__ void __launch_bounds__(CV_THREADS, 1)
         mbar_wait(&tmem_empty[acc], ((it >> 1) & 1) ^ 1);   // epilogue has drained this accumulator
         if (dbg) w_acc += clock64() - c0;
         tc_fence_after();
-        const uint32_t tacc = tmem_base + (uint32_t)(acc * p.block_n);
+        const uint32_t tacc = tmem_base + (uint32_t)(acc * p.halves * p.block_n);
         uint32_t first_mma = 1;
         int cb = 0;
         for (int s = 0; s < slabs; ++s) {
@@ -225,12 +238,8 @@ __global__ void __launch_bounds__(CV_THREADS, 1)
                 const uint64_t ad = make_kmajor_sw128_desc_rows(abase + (uint32_t)(kh_ * p.box_w + kw_) * 128, sbo);
                 const uint64_t bd = make_kmajor_sw128_desc(bbase);
                 const uint32_t bstep = (uint32_t)b_bytes >> 4;
-                switch (ksteps) {
-                  case 4: issue_group_3x3_nt<4>(nt, tacc, ad, bd, bstep, idesc, first_mma ^ 1u); break;
-                  case 3: issue_group_3x3_nt<3>(nt, tacc, ad, bd, bstep, idesc, first_mma ^ 1u); break;
-                  case 2: issue_group_3x3_nt<2>(nt, tacc, ad, bd, bstep, idesc, first_mma ^ 1u); break;
-                  default: issue_group_3x3_nt<1>(nt, tacc, ad, bd, bstep, idesc, first_mma ^ 1u); break;
-                }
+                if (p.halves == 2) issue_group_3x3_ks<2>(ksteps, nt, tacc, (uint32_t)p.block_n, ad, bd, bstep, idesc, first_mma ^ 1u);
+                else issue_group_3x3_ks<1>(ksteps, nt, tacc, (uint32_t)p.block_n, ad, bd, bstep, idesc, first_mma ^ 1u);
                 if (!p.b_resident) umma_commit(&emptyB[sb]);
               }
             } else if (elect_one()) {
@@ -239,8 +248,9 @@ __global__ void __launch_bounds__(CV_THREADS, 1)
                 const uint32_t astart = abase + (uint32_t)(kh2 * p.box_w + kw2) * 128;
                 const uint64_t bdesc = make_kmajor_sw128_desc(bbase + (uint32_t)(j * b_bytes));
                 for (int k = 0; k < ksteps; ++k) {
-                  umma_f16(tacc, make_kmajor_sw128_desc_rows(astart + k * 32, sbo), bdesc + (uint64_t)(2 * k), idesc,
-                           first_mma ^ 1u);
+                  for (int h = 0; h < p.halves; ++h)
+                    umma_f16(tacc + (uint32_t)(h * p.block_n), make_kmajor_sw128_desc_rows(astart + h * 1024 + k * 32, sbo),
+                             bdesc + (uint64_t)(2 * k), idesc, first_mma ^ 1u);
                   first_mma = 0;
                 }
                 if (++kw2 == p.kw) { kw2 = 0; ++kh2; }
@@ -278,35 +288,35 @@ __global__ void __launch_bounds__(CV_THREADS, 1)
       const int ht = (int)(t % p.nh); t /= p.nh;
       const int d0 = (int)(t % p.D);
       const int bn = (int)(t / p.D);
-      const int h = ht * CV_TH + hy, w = wt * CV_TW + wx;
-      const long long out_row = (h < p.H && w < p.W) ? (((long long)bn * p.D + d0) * p.H + h) * p.W + w : -1;
       const int acc = it & 1;
       if (dbg) c0 = clock64();
       mbar_wait(&tmem_full[acc], (it >> 1) & 1);
       if (dbg) e_wait += clock64() - c0;
       tc_fence_after();
-      if (p.out_dtype == NEXTOU_BF16) {
-        __nv_bfloat16* dst = out_row >= 0 ? reinterpret_cast<__nv_bfloat16*>(p.C) + out_row * p.ldc + n0 : nullptr;
-        const long long left = p.ldc - n0;
-        epilogue_row_bf16(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * p.block_n), p.block_n, sbias, dst,
-                          (int)(left < p.block_n ? left : p.block_n), p.row32 != 0, p.slope);
-      } else
-      for (int c = 0; c < p.block_n; c += 16) {
-        uint32_t raw[16];
-        tmem_ld16(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * p.block_n + c), raw);
-        tmem_ld_wait();
-        if (out_row >= 0 && n0 + c < p.ldc) {
-          float v[16];
+      for (int half = 0; half < p.halves; ++half) {
+        const int h = ht * CV_TH + hy, w = (wt * p.halves + half) * CV_TW + wx;
+        const long long out_row = (h < p.H && w < p.W) ? (((long long)bn * p.D + d0) * p.H + h) * p.W + w : -1;
+        const uint32_t tcol = (uint32_t)((acc * p.halves + half) * p.block_n);
+        if (p.out_dtype == NEXTOU_BF16) {
+          __nv_bfloat16* dst = out_row >= 0 ? reinterpret_cast<__nv_bfloat16*>(p.C) + out_row * p.ldc + n0 : nullptr;
+          const long long left = p.ldc - n0;
+          epilogue_row_bf16(tmem_base + ((uint32_t)(q * 32) << 16) + tcol, p.block_n, sbias, dst,
+                            (int)(left < p.block_n ? left : p.block_n), p.row32 != 0, p.slope);
+        } else
+        for (int c = 0; c < p.block_n; c += 16) {
+          uint32_t raw[16];
+          tmem_ld16(tmem_base + ((uint32_t)(q * 32) << 16) + tcol + (uint32_t)c, raw);
+          tmem_ld_wait();
+          if (out_row >= 0 && n0 + c < p.ldc) {
+            float v[16];
 #pragma unroll
-          for (int j = 0; j < 16; ++j) {
-            const int col = n0 + c + j;
-            const float x = affine_act(raw[j], sbias[256 + c + j], sbias[c + j], p.slope);
-            v[j] = col < p.N ? x : 0.f;
-          }
-          if (p.out_dtype == NEXTOU_BF16)
-            store_chunk16(reinterpret_cast<__nv_bfloat16*>(p.C) + out_row * p.ldc, n0 + c, v, p.ldc);
-          else
+            for (int j = 0; j < 16; ++j) {
+              const int col = n0 + c + j;
+              const float x = affine_act(raw[j], sbias[256 + c + j], sbias[c + j], p.slope);
+              v[j] = col < p.N ? x : 0.f;
+            }
             store_chunk16(reinterpret_cast<float*>(p.C) + out_row * p.ldc, n0 + c, v, p.ldc);
+          }
         }
       }
       // accumulator drained: hand it back to the MMA warp
@@ -352,24 +362,31 @@ extern "C" int nextou_conv3d_ndhwc_halo_fwd_affine(const void* x, long long ldx,
   ConvParams p = {};
   p.N = Cout; p.Cin = Cin;
   p.block_n = pick_block_n(Cout);
-  p.tmem_cols = pow2_cols(2 * p.block_n);   // double-buffered accumulator
   p.kblocks = (Cin + 63) / 64;
   p.kd = kd; p.kh = kh; p.kw = kw; p.pd = kd / 2; p.ph = kh / 2; p.pw = kw / 2;
   p.D = D; p.H = H; p.W = W; p.B = B;
-  p.nh = (H + CV_TH - 1) / CV_TH; p.nw = (W + CV_TW - 1) / CV_TW;
-  p.box_w = CV_TW + kw - 1;
-  p.box_rows = p.box_w * (CV_TH + kh - 1);
-  p.a_stage_bytes = (p.box_rows * 128 + 1023) / 1024 * 1024;
   p.C = out; p.ldc = ldo; p.out_dtype = out_dtype; p.bias = bias; p.scale = scale; p.slope = slope; p.dbg = g_conv_dbg;
   p.row32 = (ldo % 16 == 0 && ((uintptr_t)out & 31) == 0) ? 1 : 0;
   const int taps = kd * kh * kw, inplane = kh * kw;
   const int cin_pad = p.kblocks * 64;
   const int b_bytes = p.block_n * 128;
   const int total_budget = 200 * 1024;
-  p.a_stages = 3;
-  const int b_budget = total_budget - p.a_stages * p.a_stage_bytes;
   const long long all_b = (long long)taps * p.kblocks * b_bytes;
-  if (all_b <= b_budget && kd * p.kblocks * 1 <= CV_B_MAX_STAGES) {
+  // Filters that do not fit shared memory are streamed through a ring, once per brick: 553 KB per 128 voxels for the 66 -> 66
+  // 3x3x3 layers, which makes the kernel bound by weight traffic (L2 -> shared memory writes contend with the operand reads
+  // of the MMAs; measured 107 cycles per MMA instead of 84).  Then a CTA takes 16 x 16 bricks: two M = 128 accumulators that
+  // consume every streamed weight tile twice (needs 4 x block_n tensor-memory columns for the double buffer).
+  const bool resident_narrow = all_b <= total_budget - 3 * (((CV_TW + kw - 1) * (CV_TH + kh - 1) * 128 + 1023) / 1024 * 1024) &&
+                               kd * p.kblocks <= CV_B_MAX_STAGES;
+  p.halves = (!resident_narrow && 4 * p.block_n <= 512 && W > CV_TW && kw == 3 && kh == 3) ? 2 : 1;
+  p.tmem_cols = pow2_cols(2 * p.halves * p.block_n);   // double-buffered accumulator(s)
+  p.nh = (H + CV_TH - 1) / CV_TH; p.nw = (W + CV_TW * p.halves - 1) / (CV_TW * p.halves);
+  p.box_w = CV_TW * p.halves + kw - 1;
+  p.box_rows = p.box_w * (CV_TH + kh - 1);
+  p.a_stage_bytes = (p.box_rows * 128 + 1023) / 1024 * 1024;
+  p.a_stages = p.halves == 2 ? 2 : 3;
+  const int b_budget = total_budget - p.a_stages * p.a_stage_bytes;
+  if (resident_narrow) {
     // whole filter resident: one stage per (depth tap, slab) holding all in-plane taps
     p.b_resident = 1; p.b_group = inplane; p.b_groups = 1; p.b_stages = kd * p.kblocks;
     int as = (int)((total_budget - all_b) / p.a_stage_bytes);   // spend the rest on a deeper activation ring
