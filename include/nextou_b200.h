@@ -164,6 +164,14 @@ int nextou_dsloss_bwd(const void* logits, int dtype, long long stride_b, long lo
                       int NC, long long V, const void* target, int target_code, const uint8_t* crit, const float* coef_a,
                       const float* coef_b, const float* scal, void* dlogits, long long dstride_b, long long dstride_c,
                       long long dstride_v, void* stream);
+/* The per-class algebra between the two passes in one tiny launch each (instead of ~30 ATen kernels on [B, NC] doubles):
+ * total = w_ce * mean CE - w_dice * mean Dice + w_ti * ti and the Dice derivative coefficients coef[2][B][NC] (fp64);
+ * then, in backward, coef32 = coef * gout and the CE / TI scales nextou_dsloss_bwd takes. */
+int nextou_dsloss_finish(const double* sums, const double* pooled, int B, int NC, long long V, double w_ce, double w_dice, double w_ti,
+                         const double* ti, int batch_dice, int do_bg, double smooth, double grad_world, double* total,
+                         double* coef, void* stream);
+int nextou_dsloss_scale(const double* coef, const double* gout, int B, int NC, long long V, double w_ce, double w_ti, float* coef32,
+                        float* scal, void* stream);
 
 /* Same contract, restricted to kh, kw in {1, 3} (all non-down-sampling NexToU convolutions): halo-reuse variant
  * (csrc/conv_tcgen05.cu) — one haloed activation box per depth tap feeds all in-plane taps through row-shifted

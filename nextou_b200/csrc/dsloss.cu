@@ -146,6 +146,61 @@ __global__ void __launch_bounds__(DSL_THREADS)
   }
 }
 
+// Per-class algebra between the two passes, one tiny launch (it replaces ~25 ATen kernels on [B, NC] doubles per scale):
+//   total = w_ce * mean CE  -  w_dice * mean_{b, c >= first} (2 I + smooth) / clip(G + P + smooth, 1e-8)  +  w_ti * ti
+//   coef[0][b][c] = d total / d I_bc,  coef[1][b][c] = d total / d P_bc   (zero for c < first; times grad_world under DDP)
+// (MemoryEfficientSoftDiceLoss.forward; batch_dice: the sums of the batch items are pooled first.)  sums: [B][3 NC + 1];
+// pooled != NULL: [3 NC] already summed over the batch (and all-reduced over the ranks by the caller).
+__global__ void dsloss_finish_kernel(const double* __restrict__ sums, const double* __restrict__ pooled, int B, int NC, double V,
+                                     double w_ce, double w_dice, double w_ti, const double* __restrict__ ti, int batch_dice,
+                                     int first, double smooth, double grad_world, double* __restrict__ total,
+                                     double* __restrict__ coef) {
+  if (threadIdx.x != 0 || blockIdx.x != 0) return;
+  const int width = 3 * NC + 1;
+  const int rows = batch_dice ? 1 : B;
+  const double n_terms = (double)rows * (NC - first);
+  double ce = 0.0;
+  for (int b = 0; b < B; ++b) ce += sums[(long long)b * width + 3 * NC];
+  double dice = 0.0;
+  for (int r = 0; r < rows; ++r)
+    for (int c = 0; c < NC; ++c) {
+      double P = 0.0, I = 0.0, G = 0.0;
+      if (batch_dice) {
+        if (pooled != nullptr) { P = pooled[c]; I = pooled[NC + c]; G = pooled[2 * NC + c]; }
+        else for (int b = 0; b < B; ++b) { P += sums[(long long)b * width + c]; I += sums[(long long)b * width + NC + c]; G += sums[(long long)b * width + 2 * NC + c]; }
+      } else {
+        P = sums[(long long)r * width + c]; I = sums[(long long)r * width + NC + c]; G = sums[(long long)r * width + 2 * NC + c];
+      }
+      const double raw = G + P + smooth;
+      const double den = raw < 1e-8 ? 1e-8 : raw;
+      const double num = 2.0 * I + smooth;
+      double dI = 0.0, dP = 0.0;
+      if (c >= first) {
+        dice += num / den;
+        dI = -2.0 * w_dice * grad_world / n_terms / den;
+        dP = raw >= 1e-8 ? w_dice * grad_world / n_terms * num / (den * den) : 0.0;
+      }
+      for (int b = (batch_dice ? 0 : r); b < (batch_dice ? B : r + 1); ++b) {
+        coef[(long long)b * NC + c] = dI;
+        coef[(long long)(B + b) * NC + c] = dP;
+      }
+    }
+  double t = ce * (w_ce / ((double)B * V)) - dice * (w_dice / n_terms);
+  if (ti != nullptr) t += w_ti * ti[0];
+  total[0] = t;
+}
+
+// backward scalars: coef32 = coef * gout, scal = (gout * w_ce / (B V), gout * w_ti / B)
+__global__ void dsloss_scale_kernel(const double* __restrict__ coef, const double* __restrict__ gout, int n, double s_ce, double s_ti,
+                                    float* __restrict__ coef32, float* __restrict__ scal) {
+  const double g = gout[0];
+  for (int i = threadIdx.x; i < n; i += blockDim.x) coef32[i] = (float)(coef[i] * g);
+  if (threadIdx.x == 0) {
+    scal[0] = (float)(g * s_ce);
+    scal[1] = (float)(g * s_ti);
+  }
+}
+
 #define DSL_DISPATCH_NC(NCV, ...)                     \
   switch (NCV) {                                      \
     case 2: { constexpr int NC = 2; __VA_ARGS__ } break;   \
@@ -212,4 +267,26 @@ extern "C" int nextou_dsloss_bwd(const void* logits, int dtype, long long stride
                                             (const T*)logits, stride_b, stride_c, stride_v, V, target, target_code, crit, coef_a,
                                             coef_b, scal, (T*)dlogits, dstride_b, dstride_c, dstride_v);))
   return check_launch("dsloss_bwd_kernel");
+}
+
+
+// total (fp64 scalar) and the Dice derivative coefficients coef[2][B][NC] (fp64) from the sums of nextou_dsloss_stats; `pooled`
+// (may be NULL): the [3 NC] batch-pooled P | I | G sums when the caller has already reduced them (DDP batch dice); ti: the
+// (B)TI term (device scalar) or NULL.
+extern "C" int nextou_dsloss_finish(const double* sums, const double* pooled, int B, int NC, long long V, double w_ce, double w_dice,
+                                    double w_ti, const double* ti, int batch_dice, int do_bg, double smooth, double grad_world,
+                                    double* total, double* coef, void* stream) {
+  NEXTOU_REQUIRE(sums && total && coef && B > 0 && NC >= 2 && NC <= DSL_MAXC && V > 0, "dsloss_finish: bad arguments");
+  dsloss_finish_kernel<<<1, 32, 0, (cudaStream_t)stream>>>(sums, pooled, B, NC, (double)V, w_ce, w_dice, w_ti, ti, batch_dice, do_bg ? 0 : 1,
+                                                          smooth, grad_world, total, coef);
+  return check_launch("dsloss_finish_kernel");
+}
+
+// coef32[2*B*NC] = coef * gout[0]; scal[0] = gout * w_ce / (B V), scal[1] = gout * w_ti / B   (inputs of nextou_dsloss_bwd)
+extern "C" int nextou_dsloss_scale(const double* coef, const double* gout, int B, int NC, long long V, double w_ce, double w_ti,
+                                   float* coef32, float* scal, void* stream) {
+  NEXTOU_REQUIRE(coef && gout && coef32 && scal && B > 0 && NC > 0 && V > 0, "dsloss_scale: bad arguments");
+  dsloss_scale_kernel<<<1, 128, 0, (cudaStream_t)stream>>>(coef, gout, 2 * B * NC, w_ce / ((double)B * (double)V), w_ti / (double)B, coef32,
+                                                          scal);
+  return check_launch("dsloss_scale_kernel");
 }

@@ -517,32 +517,21 @@ class _SegLoss(torch.autograd.Function):
             ws = torch.empty(L.nextou_bti_masked_sum_workspace_bytes(B) // 8, device=dev, dtype=torch.float64)
             ti = torch.empty((), device=dev, dtype=torch.float64)
             check(L.nextou_bti_masked_sum(ptr(ce), ptr(crit), B, ll(V), ptr(ws), ptr(ti), cstream()), "nextou_bti_masked_sum")
-        # per-class algebra on [B, NC] doubles (MemoryEfficientSoftDiceLoss.forward; CrossEntropyLoss mean reduction)
-        P, I, G = sums[:, :NC], sums[:, NC:2 * NC], sums[:, 2 * NC:3 * NC]
+        # per-class algebra on [B, NC] doubles (MemoryEfficientSoftDiceLoss.forward; CrossEntropyLoss mean reduction): one launch
+        pooled = None
         grad_world = 1.0
-        if batch_dice:
-            if ddp and torch.distributed.is_available() and torch.distributed.is_initialized():
-                pig = sums[:, :3 * NC].sum(0, keepdim=True)
-                torch.distributed.all_reduce(pig)
-                P, I, G = pig[:, :NC], pig[:, NC:2 * NC], pig[:, 2 * NC:]
-                # upstream gathers with AllGatherGrad, whose backward all-reduces (SUM) the incoming gradient: every rank's
-                # loss depends on every rank's sums, so the local derivative is world_size x d(dice)/d(sums); DDP's gradient
-                # averaging then yields the gradient of the global-batch Dice (same as torch.distributed.nn all_gather)
-                grad_world = float(torch.distributed.get_world_size())
-            else:
-                P, I, G = P.sum(0, keepdim=True), I.sum(0, keepdim=True), G.sum(0, keepdim=True)
-        first = 0 if do_bg else 1
-        raw = G + P + smooth
-        den = torch.clip(raw, 1e-8)
-        num = 2 * I + smooth
-        n_terms = den[:, first:].numel()
-        total = sums[:, 3 * NC].sum() * (w_ce / (B * V)) - (num / den)[:, first:].sum() * (w_dice / n_terms)
-        if ti is not None:
-            total = total + w_ti * ti
-        dI = -2.0 * w_dice * grad_world / n_terms / den
-        dP = torch.where(raw >= 1e-8, w_dice * grad_world / n_terms * num / (den * den), torch.zeros_like(den))
-        coef = torch.stack([dI, dP]).expand(2, B, NC).clone()
-        coef[:, :, :first] = 0
+        if batch_dice and ddp and torch.distributed.is_available() and torch.distributed.is_initialized():
+            pooled = sums[:, :3 * NC].sum(0)
+            torch.distributed.all_reduce(pooled)
+            # upstream gathers with AllGatherGrad, whose backward all-reduces (SUM) the incoming gradient: every rank's
+            # loss depends on every rank's sums, so the local derivative is world_size x d(dice)/d(sums); DDP's gradient
+            # averaging then yields the gradient of the global-batch Dice (same as torch.distributed.nn all_gather)
+            grad_world = float(torch.distributed.get_world_size())
+        total = torch.empty((), device=dev, dtype=torch.float64)
+        coef = torch.empty((2, B, NC), device=dev, dtype=torch.float64)
+        cd = ctypes.c_double
+        check(L.nextou_dsloss_finish(ptr(sums), ptr(pooled), B, NC, ll(V), cd(w_ce), cd(w_dice), cd(w_ti), ptr(ti), int(batch_dice),
+                                     int(do_bg), cd(smooth), cd(grad_world), ptr(total), ptr(coef), cstream()), "nextou_dsloss_finish")
         ctx.save_for_backward(x, y, crit if crit is not None else labels, coef)
         ctx.meta = (sb, sc, sv, B, NC, V, logits.dtype, crit is not None, w_ce, w_ti)
         return total
@@ -551,13 +540,17 @@ class _SegLoss(torch.autograd.Function):
     def backward(ctx, gout):
         x, y, crit, coef = ctx.saved_tensors
         sb, sc, sv, B, NC, V, in_dtype, has_crit, w_ce, w_ti = ctx.meta
-        g = gout.to(torch.float64)
-        coef32 = (coef * g).float().contiguous()
-        scal = (torch.stack([g * (w_ce / (B * V)), g * (w_ti / B)])).float().contiguous()
+        g = gout.to(torch.float64).contiguous()
+        L = _lib.lib()
+        coef32 = torch.empty((2, B, NC), device=x.device, dtype=torch.float32)
+        scal = torch.empty(2, device=x.device, dtype=torch.float32)
+        cd = ctypes.c_double
+        check(L.nextou_dsloss_scale(ptr(coef), ptr(g), B, NC, ll(V), cd(w_ce), cd(w_ti), ptr(coef32), ptr(scal), cstream()),
+              "nextou_dsloss_scale")
         dx = _empty_like_strided(x)
-        check(_lib.lib().nextou_dsloss_bwd(ptr(x), dtype_code(x), ll(sb), ll(sc), ll(sv), B, NC, ll(V), ptr(y),
-                                           _TGT_CODE[y.dtype], ptr(crit if has_crit else None), ptr(coef32[0]), ptr(coef32[1]),
-                                           ptr(scal), ptr(dx), ll(sb), ll(sc), ll(sv), cstream()), "nextou_dsloss_bwd")
+        check(L.nextou_dsloss_bwd(ptr(x), dtype_code(x), ll(sb), ll(sc), ll(sv), B, NC, ll(V), ptr(y),
+                                  _TGT_CODE[y.dtype], ptr(crit if has_crit else None), ptr(coef32[0]), ptr(coef32[1]),
+                                  ptr(scal), ptr(dx), ll(sb), ll(sc), ll(sv), cstream()), "nextou_dsloss_bwd")
         return dx.to(in_dtype), None, None
 
 
