@@ -162,58 +162,64 @@ __global__ void norm_stats_kernel(const T* __restrict__ x, int C, int R, long lo
   block_channel_reduce<NV>(acc, C, R, smem, partial + ((long long)blockIdx.y * gridDim.x + blockIdx.x) * 2 * C);
 }
 
-// Fixed-order fp64 sum of the CTA partial rows: block = 32 columns x FIN_SLICES slices; slice s adds rows s, s+8, ...
-// (independent loads in flight), then the slices are combined in order.  `cols` = row length of `partial`.
-constexpr int FIN_SLICES = 32;   // 1024 threads: the finalize is a chain of L2-latency-bound loads, so spread the rows widely
-__device__ __forceinline__ double sliced_column_sum(const float* __restrict__ rows_base, int nblk, int cols, int col,
-                                                    bool valid, double* sh) {
-  const int lane = threadIdx.x & 31, slice = threadIdx.x >> 5;
+// Fixed-order fp64 column sums of the CTA partial rows.  The finalize kernels are pure latency chains (a few hundred rows of a
+// few hundred columns from L2), so the rows are spread as widely as possible: a block of 1024 threads owns FIN_COLS = 8 columns
+// x 128 row slices (slice s adds rows s, s + 128, ...: at most 5 loads per thread for 592 partial rows, all in flight at once);
+// the slices are combined by warp shuffles (lanes of equal column), shared memory across the 32 warps, and shuffles again.
+// `cols` = row length of `partial`.  Returns the sum of column `col` in lanes 0..7 of warp 0 (col = blockIdx.x * 8 + lane).
+constexpr int FIN_COLS = 8;
+constexpr int FIN_THREADS = 1024;
+__device__ __forceinline__ double sliced_column_sum(const float* __restrict__ rows_base, int nblk, int cols, int col0, double* sh) {
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int c = col0 + (threadIdx.x & (FIN_COLS - 1));
+  const int slice = threadIdx.x / FIN_COLS;                 // 0 .. 127
   double s = 0.0;
-  if (valid) {
-    int b = slice;
-    for (; b + 7 * FIN_SLICES < nblk; b += 8 * FIN_SLICES) {
-      float v[8];
+  if (c < cols) {
+    float v[5];
+    int n = 0;
 #pragma unroll
-      for (int u = 0; u < 8; ++u) v[u] = rows_base[(long long)(b + u * FIN_SLICES) * cols + col];
+    for (int u = 0; u < 5; ++u) {
+      const int b = slice + u * (FIN_THREADS / FIN_COLS);
+      v[u] = b < nblk ? rows_base[(long long)b * cols + c] : 0.f;
+      n = u;
+    }
+    (void)n;
 #pragma unroll
-      for (int u = 0; u < 8; ++u) s += (double)v[u];
-    }
-    for (; b + 3 * FIN_SLICES < nblk; b += 4 * FIN_SLICES) {
-      const float v0 = rows_base[(long long)b * cols + col];
-      const float v1 = rows_base[(long long)(b + FIN_SLICES) * cols + col];
-      const float v2 = rows_base[(long long)(b + 2 * FIN_SLICES) * cols + col];
-      const float v3 = rows_base[(long long)(b + 3 * FIN_SLICES) * cols + col];
-      s += (double)v0;
-      s += (double)v1;
-      s += (double)v2;
-      s += (double)v3;
-    }
-    for (; b < nblk; b += FIN_SLICES) s += (double)rows_base[(long long)b * cols + col];
+    for (int u = 0; u < 5; ++u) s += (double)v[u];
+    for (int b = slice + 5 * (FIN_THREADS / FIN_COLS); b < nblk; b += FIN_THREADS / FIN_COLS) s += (double)rows_base[(long long)b * cols + c];
   }
-  sh[slice * 32 + lane] = s;
+  s += __shfl_xor_sync(0xffffffffu, s, 8);
+  s += __shfl_xor_sync(0xffffffffu, s, 16);
+  if (lane < FIN_COLS) sh[warp * FIN_COLS + lane] = s;
   __syncthreads();
   double tot = 0.0;
-  if (slice == 0)
-    for (int i = 0; i < FIN_SLICES; ++i) tot += sh[i * 32 + lane];
+  if (warp == 0) {
+    const int part = lane / FIN_COLS, cc = lane & (FIN_COLS - 1);     // 4 parts x 8 warps each
+#pragma unroll
+    for (int w = 0; w < 8; ++w) tot += sh[(part * 8 + w) * FIN_COLS + cc];
+    tot += __shfl_xor_sync(0xffffffffu, tot, 8);
+    tot += __shfl_xor_sync(0xffffffffu, tot, 16);
+  }
   __syncthreads();
-  return tot;  // meaningful in slice 0 only
+  return tot;  // meaningful in lanes 0..7 of warp 0
 }
 
-// grid (ceil(C/32), instances), block 32 x FIN_SLICES: mean / invstd per (instance, channel), running stats
-__global__ void __launch_bounds__(32 * FIN_SLICES)
+// grid (ceil(C/8), instances): mean / invstd per (instance, channel), running stats
+__global__ void __launch_bounds__(FIN_THREADS)
     norm_finalize_kernel(const float* __restrict__ partial, int nblk, int C, long long rows, int instances, float eps,
                          float* __restrict__ mean, float* __restrict__ invstd, float* __restrict__ running_mean,
                          float* __restrict__ running_var, float momentum, long long* __restrict__ num_batches_tracked,
                          int c_valid) {
-  __shared__ double sh[FIN_SLICES * 32];
+  __shared__ double sh[32 * FIN_COLS];
   const int inst = blockIdx.y;
   if (num_batches_tracked != nullptr && blockIdx.x == 0 && blockIdx.y == 0 && threadIdx.x == 0) *num_batches_tracked += 1;
-  const int c = blockIdx.x * 32 + (threadIdx.x & 31);
-  const bool valid = c < C;
+  const int col0 = blockIdx.x * FIN_COLS;
+  const int c = col0 + (threadIdx.x & (FIN_COLS - 1));
   const float* base = partial + (long long)inst * nblk * 2 * C;
-  const double s1 = sliced_column_sum(base, nblk, 2 * C, c, valid, sh);
-  const double s2 = sliced_column_sum(base, nblk, 2 * C, C + c, valid, sh);
-  if (!valid || threadIdx.x >= 32) return;
+  // columns [0, C) hold sum x, [C, 2C) sum x^2: the second call reads the same channels of the second half
+  const double s1 = sliced_column_sum(base, nblk, 2 * C, col0, sh);
+  const double s2 = sliced_column_sum(base + C, nblk, 2 * C, col0, sh);
+  if (threadIdx.x >= FIN_COLS || c >= C) return;
   const double n = (double)rows;
   const double m = s1 / n;
   double var = s2 / n - m * m;  // biased variance (what normalisation uses)
@@ -306,16 +312,16 @@ __global__ void norm_bwd_reduce_kernel(const T* __restrict__ x, const T* __restr
 }
 
 // sums[inst][cols] (fp32) from the CTA partial rows [inst][nblk][cols], fixed order, fp64 accumulation;
-// grid (ceil(cols/32), instances)
-__global__ void __launch_bounds__(32 * FIN_SLICES)
+// grid (ceil(cols/8), instances)
+__global__ void __launch_bounds__(FIN_THREADS)
     norm_bwd_finalize_kernel(const float* __restrict__ partial, int nblk, int cols, int instances,
                              float* __restrict__ sums) {
-  __shared__ double sh[FIN_SLICES * 32];
+  __shared__ double sh[32 * FIN_COLS];
   const int inst = blockIdx.y;
-  const int c = blockIdx.x * 32 + (threadIdx.x & 31);
-  const bool valid = c < cols;
-  const double s = sliced_column_sum(partial + (long long)inst * nblk * cols, nblk, cols, c, valid, sh);
-  if (valid && threadIdx.x < 32) sums[(long long)inst * cols + c] = (float)s;
+  const int col0 = blockIdx.x * FIN_COLS;
+  const int c = col0 + (threadIdx.x & (FIN_COLS - 1));
+  const double s = sliced_column_sum(partial + (long long)inst * nblk * cols, nblk, cols, col0, sh);
+  if (threadIdx.x < FIN_COLS && c < cols) sums[(long long)inst * cols + c] = (float)s;
 }
 
 // backward pass 2: dx = gamma * invstd * (dy' - s1/n - xhat * s2/n)
@@ -466,7 +472,7 @@ extern "C" int nextou_norm_stats_tracked(const void* x, int dtype, int C, int c_
   })
   rc = check_launch("norm_stats_kernel");
   if (rc) return rc;
-  norm_finalize_kernel<<<dim3((C + 31) / 32, instances), 32 * FIN_SLICES, 0, st>>>(
+  norm_finalize_kernel<<<dim3((C + FIN_COLS - 1) / FIN_COLS, instances), FIN_THREADS, 0, st>>>(
       partial, p.nblk, C, rows, instances, eps, mean, invstd, running_mean, running_var, momentum, num_batches_tracked,
       c_valid);
   return check_launch("norm_finalize_kernel");
@@ -532,7 +538,7 @@ extern "C" int nextou_norm_bwd_reduce(const void* x, const void* dy, int dtype, 
   })
   rc = check_launch("norm_bwd_reduce_kernel");
   if (rc) return rc;
-  norm_bwd_finalize_kernel<<<dim3((2 * C + 31) / 32, instances), 32 * FIN_SLICES, 0, st>>>(partial, p.nblk, 2 * C,
+  norm_bwd_finalize_kernel<<<dim3((2 * C + FIN_COLS - 1) / FIN_COLS, instances), FIN_THREADS, 0, st>>>(partial, p.nblk, 2 * C,
                                                                                               instances, sums);
   return check_launch("norm_bwd_finalize_kernel");
 }
@@ -561,7 +567,7 @@ extern "C" int nextou_norm_bwd_apply(const void* x, const void* dy, int dtype, i
   })
   rc = check_launch("norm_bwd_apply_kernel");
   if (rc || !dx_colsum) return rc;
-  norm_bwd_finalize_kernel<<<dim3((C + 31) / 32, instances), 32 * FIN_SLICES, 0, st>>>(partial, p.nblk, C, instances,
+  norm_bwd_finalize_kernel<<<dim3((C + FIN_COLS - 1) / FIN_COLS, instances), FIN_THREADS, 0, st>>>(partial, p.nblk, C, instances,
                                                                                           dx_colsum);
   return check_launch("norm_bwd_finalize_kernel");
 }
@@ -593,7 +599,7 @@ extern "C" int nextou_colsum(const void* x, int dtype, int C, long long rows, fl
   })
   rc = check_launch("norm_stats_kernel");
   if (rc) return rc;
-  norm_bwd_finalize_kernel<<<dim3((2 * C + 31) / 32, 1), 32 * FIN_SLICES, 0, st>>>(partial, p.nblk, 2 * C, 1, sums);
+  norm_bwd_finalize_kernel<<<dim3((2 * C + FIN_COLS - 1) / FIN_COLS, 1), FIN_THREADS, 0, st>>>(partial, p.nblk, 2 * C, 1, sums);
   return check_launch("norm_bwd_finalize_kernel");
 }
 

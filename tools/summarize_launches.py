@@ -13,6 +13,7 @@ FAMILIES = {  # bench.py roofline family -> kernel-name regex
     "conv_halo_tcgen05": r"conv_halo_tcgen05_kernel", "wgrad_halo_tcgen05": r"wgrad_halo_tcgen05_kernel",
     "gemm_tcgen05": r"gemm_pers_tcgen05_kernel", "conv_pertap_tcgen05": r"nextou::gemm_tcgen05_kernel",
     "wgrad_tcgen05": r"nextou::wgrad_tcgen05_kernel", "knn_topk": r"knn_topk_kernel",
+    "wgrad_planes_tcgen05": r"wgrad_planes_tcgen05_kernel", "conv_small": r"conv_small_(fwd|wgrad)_kernel",
 }
 
 
