@@ -1,5 +1,5 @@
 """Diagnostic (not a test): per-module and whole-network error of the CUDA product against the CPU oracle.
-    python -m tests.debug_model_parity [mini3d|mini2d]
+    python -m tools.debug_model_parity [mini3d|mini2d]
 """
 import sys
 
