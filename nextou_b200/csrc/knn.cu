@@ -108,15 +108,72 @@ __device__ __forceinline__ void bitonic_merge32(float& d, int& i, int lane) {
 
 constexpr int KNN_KC = 16;
 
+constexpr int KNN_CAP = 48;   // candidates of one row and chunk that may tie with / beat the row threshold (else: slow path)
+
 template <int BM, int BN, int TM, int TN>
 struct KnnCfg {
   static constexpr int TX = BN / TN, TY = BM / TM, NT = TX * TY;
   static constexpr int DS = BN + 4;  // distance tile row stride (floats)
   static constexpr size_t smem_bytes =
-      sizeof(float) * (2 * KNN_KC * BM + 2 * KNN_KC * BN + (size_t)BM * DS + (size_t)BM * 32) + sizeof(int) * BM * 32;
+      sizeof(float) * (2 * KNN_KC * BM + 2 * KNN_KC * BN + (size_t)BM * DS + (size_t)BM * 32) + sizeof(int) * BM * 32 +
+      (sizeof(float) + sizeof(int)) * ((size_t)BM * KNN_CAP + BM);
 };
 
-template <int BM, int BN, int TM, int TN>
+// The running top-32 list of one row, merged with its BN chunk candidates by ONE FULL WARP (sorted across the lanes): a few
+// qualifying candidates are inserted one by one (ballot -> position, shfl_up -> shift), many take the bitonic sort + merge.
+// Slow path of knn_topk_kernel (rows whose threshold ties with more than KNN_CAP candidates) — the order (distance, index) is
+// total, so both paths produce the same list.
+template <int BN, int DS>
+__device__ __forceinline__ void warp_row_topk(const float* __restrict__ Ds, int row, int j0, int M, int K, int lane, float& td,
+                                              int& ti) {
+#pragma unroll 1
+  for (int s = 0; s < (BN + 31) / 32; ++s) {
+    const int col = s * 32 + lane;
+    const int gj = j0 + col;
+    float d = __int_as_float(0x7f800000);
+    int ci = INT_MAX;
+    if (col < BN && gj < M) {
+      d = Ds[row * DS + col];
+      ci = gj;
+    }
+    const float thr_d = __shfl_sync(0xffffffffu, td, K - 1);
+    const int thr_i = __shfl_sync(0xffffffffu, ti, K - 1);
+    unsigned q = __ballot_sync(0xffffffffu, cand_less(d, ci, thr_d, thr_i));
+    if (q == 0u) continue;
+    if (__popc(q) > 10) {
+      bitonic_sort32(d, ci, lane);
+      const float rd = __shfl_sync(0xffffffffu, d, 31 - lane);
+      const int ri = __shfl_sync(0xffffffffu, ci, 31 - lane);
+      if (cand_less(rd, ri, td, ti)) {
+        td = rd;
+        ti = ri;
+      }
+      bitonic_merge32(td, ti, lane);
+    } else {
+      while (q) {
+        const int src = __ffs(q) - 1;
+        q &= q - 1;
+        const float cd = __shfl_sync(0xffffffffu, d, src);
+        const int cx = __shfl_sync(0xffffffffu, ci, src);
+        const unsigned m = __ballot_sync(0xffffffffu, cand_less(cd, cx, td, ti));
+        if (m == 0u) continue;
+        const int pos = __ffs(m) - 1;          // the list is sorted: lanes >= pos hold larger entries
+        const float ud = __shfl_up_sync(0xffffffffu, td, 1);
+        const int ui = __shfl_up_sync(0xffffffffu, ti, 1);
+        if (lane > pos) {
+          td = ud;
+          ti = ui;
+        } else if (lane == pos) {
+          td = cd;
+          ti = cx;
+        }
+      }
+    }
+  }
+}
+
+// LK = 8 / 16 / 32: register list length of the per-row threshold search (>= k * dilation)
+template <int BM, int BN, int TM, int TN, int LK>
 __global__ void __launch_bounds__(KnnCfg<BM, BN, TM, TN>::NT)
     knn_topk_kernel(const float* __restrict__ xn, const float* __restrict__ sqx, int ldn,
                     const float* __restrict__ yn, const float* __restrict__ sqy, int ldm,
@@ -131,6 +188,10 @@ __global__ void __launch_bounds__(KnnCfg<BM, BN, TM, TN>::NT)
   float* Ds = Ys + 2 * KC * BN;        // [BM][DS]
   float* Ld = Ds + BM * DS;            // [BM][32]
   int* Li = reinterpret_cast<int*>(Ld + BM * 32);
+  float* Cd = reinterpret_cast<float*>(Li + BM * 32);   // [BM][KNN_CAP] candidates of the chunk: distance,
+  int* Ci = reinterpret_cast<int*>(Cd + BM * KNN_CAP);  //                 index
+  float* Thr = reinterpret_cast<float*>(Ci + BM * KNN_CAP);   // [BM] row threshold = K-th smallest distance so far
+  int* Cnt = reinterpret_cast<int*>(Thr + BM);                // [BM] candidates <= threshold
 
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int tx = tid % TX, ty = tid / TX;
@@ -253,77 +314,150 @@ __global__ void __launch_bounds__(KnnCfg<BM, BN, TM, TN>::NT)
     }
     __syncthreads();
 
-    // per-row running top-32 (one FULL warp per row, rows strided over the full warps).  Only candidates that beat the
-    // current K-th best can change the answer: a few of them are inserted one by one into the sorted list held across
-    // the lanes (ballot -> position, shfl_up -> shift); many of them (the first chunks) take the bitonic sort + merge.
-    // Both paths keep the list sorted by the strict total order (distance, index), so the result is unique.
-    constexpr int NFULL = NT / 32;
-    if (warp < NFULL) {
-      for (int row = warp; row < BM; row += NFULL) {
-        const int gi = i0 + row;
-        if (gi >= N) continue;
-        float td = Ld[row * 32 + lane];
-        int ti = Li[row * 32 + lane];
-#pragma unroll 1
-        for (int s = 0; s < (BN + 31) / 32; ++s) {
-          const int col = s * 32 + lane;
-          const int gj = j0 + col;
-          float d = __int_as_float(0x7f800000);
-          int ci = INT_MAX;
-          if (col < BN && gj < M) {
-            d = Ds[row * DS + col];
-            ci = gj;
-          }
-          const float thr_d = __shfl_sync(0xffffffffu, td, K - 1);
-          const int thr_i = __shfl_sync(0xffffffffu, ti, K - 1);
-          unsigned q = __ballot_sync(0xffffffffu, cand_less(d, ci, thr_d, thr_i));
-          if (q == 0u) continue;
-          if (__popc(q) > 10) {
-            bitonic_sort32(d, ci, lane);
-            const float rd = __shfl_sync(0xffffffffu, d, 31 - lane);
-            const int ri = __shfl_sync(0xffffffffu, ci, 31 - lane);
-            if (cand_less(rd, ri, td, ti)) {
-              td = rd;
-              ti = ri;
-            }
-            bitonic_merge32(td, ti, lane);
-          } else {
-            while (q) {
-              const int src = __ffs(q) - 1;
-              q &= q - 1;
-              const float cd = __shfl_sync(0xffffffffu, d, src);
-              const int cx = __shfl_sync(0xffffffffu, ci, src);
-              const unsigned m = __ballot_sync(0xffffffffu, cand_less(cd, cx, td, ti));
-              if (m == 0u) continue;
-              const int pos = __ffs(m) - 1;          // the list is sorted: lanes >= pos hold larger entries
-              const float ud = __shfl_up_sync(0xffffffffu, td, 1);
-              const int ui = __shfl_up_sync(0xffffffffu, ti, 1);
-              if (lane > pos) {
-                td = ud;
-                ti = ui;
-              } else if (lane == pos) {
-                td = cd;
-                ti = cx;
-              }
-            }
+    // Running top-K of every row (sorted by the strict total order (distance, index), hence unique), in three steps that keep
+    // all lanes busy (the warp-per-row sorted-list insertion this replaces took 56 % of the kernel time):
+    // (1) TPR threads per row, each over a segment of the chunk (thread 0 of the row also over the running list): the K
+    //     smallest distance VALUES in a sorted register list (min / max insertion; slots below LK - K are -inf sentinels);
+    //     the lists of a row are combined pairwise through shared memory -> the row threshold T = K-th smallest value.
+    //     A thread walks its segment rotated by (row / 8) % 4 columns: DS = 172 maps 8 consecutive rows to banks 4 apart.
+    const bool first = (j0 == jbeg);
+    const float INF = __int_as_float(0x7f800000);
+    {
+      constexpr int TPR = (NT / BM >= 4) ? 4 : (NT / BM >= 2 ? 2 : 1);
+      constexpr int SEG = (BN + TPR - 1) / TPR;
+      static_assert(2 * 32 <= 2 * KNN_CAP, "the published lists live in the candidate arrays");
+      float* Ls = Cd;                      // [2][32][BM] published lists (Cd and Ci are contiguous; row-minor: no bank conflicts)
+      const bool active = tid < BM * TPR;
+      const int row = tid % BM, part = tid / BM;
+      float lst[LK];
+#pragma unroll
+      for (int p = 0; p < LK; ++p) lst[p] = (p < LK - K) ? -INF : INF;
+      auto push = [&](float v) {
+        if (v < lst[LK - 1]) {
+#pragma unroll
+          for (int p = 0; p < LK; ++p) {
+            const float t = fminf(lst[p], v);
+            v = fmaxf(lst[p], v);
+            lst[p] = t;
           }
         }
-        Ld[row * 32 + lane] = td;
-        Li[row * 32 + lane] = ti;
-        if (j0 + BN >= jend) {
-          if (split) {
-            const long long o = (((long long)b * N + gi) * gridDim.z + blockIdx.z) * 32 + lane;
-            part_d[o] = td;
-            part_i[o] = ti;
-          } else if (lane < K && (lane % dilation) == 0) {
-            const long long o = ((long long)b * N + gi) * k + lane / dilation;
-            out[o] = ti;
-            if (out32) out32[o] = ti;
+      };
+      auto publish = [&](int slot) {
+#pragma unroll
+        for (int p = 0; p < LK; ++p) Ls[(slot * 32 + p) * BM + row] = lst[p];
+      };
+      auto absorb = [&](int slot) {
+        for (int p = LK - K; p < LK; ++p) {       // ascending: stop at the first value that cannot enter
+          const float v = Ls[(slot * 32 + p) * BM + row];
+          if (!(v < lst[LK - 1])) break;
+          push(v);
+        }
+      };
+      if (active) {
+        if (!first && part == 0)
+          for (int q = 0; q < K; ++q) push(Ld[row * 32 + q]);
+        const int c0 = part * SEG;
+        const int len = min(SEG, BN - c0);
+        const int skew = (row >> 3) & 3;
+        const float* drow = Ds + row * DS + c0;
+#pragma unroll 4
+        for (int c = 0; c < len; ++c) {
+          int col = c + skew;
+          col -= (col >= len) ? len : 0;
+          push(drow[col]);
+        }
+      }
+      if constexpr (TPR == 4) {
+        if (active && (part & 1)) publish(part >> 1);
+        __syncthreads();
+        if (active && !(part & 1)) absorb(part >> 1);
+        __syncthreads();
+      }
+      if constexpr (TPR >= 2) {
+        if (active && part == TPR / 2) publish(0);
+        __syncthreads();
+        if (active && part == 0) absorb(0);
+      }
+      if (active && part == 0) {
+        Thr[row] = lst[LK - 1];
+        Cnt[row] = 0;
+      }
+    }
+    __syncthreads();
+    // (2) all threads: the entries <= T (the K best and whatever ties with the K-th) -> the row's candidate array
+    for (int e = tid; e < BM * BN; e += NT) {
+      const int row = e / BN, col = e - row * BN;
+      const float d = Ds[row * DS + col];
+      if (d <= Thr[row] && j0 + col < M && i0 + row < N) {
+        const int pos = atomicAdd(&Cnt[row], 1);
+        if (pos < KNN_CAP) {
+          Cd[row * KNN_CAP + pos] = d;
+          Ci[row * KNN_CAP + pos] = j0 + col;
+        }
+      }
+    }
+    if (!first) {
+      for (int e = tid; e < BM * 32; e += NT) {
+        const int row = e >> 5;
+        const float d = Ld[e];
+        const int ci = Li[e];
+        if ((e & 31) < K && ci != INT_MAX && d <= Thr[row]) {
+          const int pos = atomicAdd(&Cnt[row], 1);
+          if (pos < KNN_CAP) {
+            Cd[row * KNN_CAP + pos] = d;
+            Ci[row * KNN_CAP + pos] = ci;
           }
         }
       }
     }
     __syncthreads();
+    // (3) rank of every candidate among its row's candidates = its slot in the new running list
+    for (int e = tid; e < BM * 32; e += NT) {
+      const int row = e >> 5;
+      const int cnt = Cnt[row];
+      if (cnt > KNN_CAP) continue;                 // slow path below
+      const float* cd = Cd + row * KNN_CAP;
+      const int* cx = Ci + row * KNN_CAP;
+      for (int a = e & 31; a < cnt; a += 32) {
+        const float d = cd[a];
+        const int ci = cx[a];
+        int rank = 0;
+        for (int bq = 0; bq < cnt; ++bq) rank += cand_less(cd[bq], cx[bq], d, ci) ? 1 : 0;
+        if (rank < K) {
+          Ld[row * 32 + rank] = d;
+          Li[row * 32 + rank] = ci;
+        }
+      }
+    }
+    // rows with more than KNN_CAP candidates at or below the threshold (massive distance ties): one full warp per row
+    constexpr int NFULL = NT / 32;
+    if (warp < NFULL) {
+      for (int row = warp; row < BM; row += NFULL) {
+        if (Cnt[row] <= KNN_CAP) continue;
+        float td = first ? INF : Ld[row * 32 + lane];
+        int ti = first ? INT_MAX : Li[row * 32 + lane];
+        warp_row_topk<BN, DS>(Ds, row, j0, M, K, lane, td, ti);
+        Ld[row * 32 + lane] = td;
+        Li[row * 32 + lane] = ti;
+      }
+    }
+    __syncthreads();
+    if (j0 + BN >= jend) {
+      for (int e = tid; e < BM * 32; e += NT) {
+        const int row = e >> 5, q = e & 31;
+        const int gi = i0 + row;
+        if (gi >= N) continue;
+        if (split) {
+          const long long o = (((long long)b * N + gi) * gridDim.z + blockIdx.z) * 32 + q;
+          part_d[o] = q < K ? Ld[e] : INF;
+          part_i[o] = q < K ? Li[e] : INT_MAX;
+        } else if (q < K && (q % dilation) == 0) {
+          const long long o = ((long long)b * N + gi) * k + q / dilation;
+          out[o] = Li[e];
+          if (out32) out32[o] = Li[e];
+        }
+      }
+    }
   }
 }
 
@@ -358,7 +492,9 @@ static int launch_topk(const float* xn, const float* sqx, int ldn, const float* 
                        const float* relpos, int B, int N, int M, int C, int k, int dilation, int64_t* out,
                        int32_t* out32, cudaStream_t st, int msplit = 1, void* workspace = nullptr) {
   using Cfg = KnnCfg<BM, BN, TM, TN>;
-  auto kern = knn_topk_kernel<BM, BN, TM, TN>;
+  const int K = k * dilation;
+  auto kern = K <= 8 ? knn_topk_kernel<BM, BN, TM, TN, 8> : K <= 16 ? knn_topk_kernel<BM, BN, TM, TN, 16>
+                                                                      : knn_topk_kernel<BM, BN, TM, TN, 32>;
   int rc = ensure_smem(kern, Cfg::smem_bytes);
   if (rc) return rc;
   dim3 grid((N + BM - 1) / BM, B, msplit);
