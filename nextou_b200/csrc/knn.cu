@@ -110,14 +110,31 @@ constexpr int KNN_KC = 16;
 
 constexpr int KNN_CAP = 48;   // candidates of one row and chunk that may tie with / beat the row threshold (else: slow path)
 
+constexpr int KNN_STAGES = 3;  // cp.async ring of channel slabs: three stages need only one CTA barrier per slab
+
 template <int BM, int BN, int TM, int TN>
 struct KnnCfg {
   static constexpr int TX = BN / TN, TY = BM / TM, NT = TX * TY;
   static constexpr int DS = BN + 4;  // distance tile row stride (floats)
+  // the operand ring is dead while a chunk's top-K runs: the candidate arrays (+ thresholds, counters) live in it
+  static constexpr size_t ring_floats = (size_t)KNN_STAGES * KNN_KC * (BM + BN);
+  static constexpr size_t cand_floats = 2 * ((size_t)BM * KNN_CAP + BM);
   static constexpr size_t smem_bytes =
-      sizeof(float) * (2 * KNN_KC * BM + 2 * KNN_KC * BN + (size_t)BM * DS + (size_t)BM * 32) + sizeof(int) * BM * 32 +
-      (sizeof(float) + sizeof(int)) * ((size_t)BM * KNN_CAP + BM);
+      sizeof(float) * ((ring_floats > cand_floats ? ring_floats : cand_floats) + (size_t)BM * DS + 2 * (size_t)BM * 32);
 };
+
+// two fp32 FMAs per instruction (FFMA2): each half is an IEEE fma.rn, i.e. bit-identical to fmaf
+__device__ __forceinline__ unsigned long long pack_f32x2(float lo, float hi) {
+  unsigned long long r;
+  asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi));
+  return r;
+}
+__device__ __forceinline__ void unpack_f32x2(unsigned long long v, float& lo, float& hi) {
+  asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(v));
+}
+__device__ __forceinline__ void ffma2(unsigned long long& c, unsigned long long a, unsigned long long b) {
+  asm("fma.rn.f32x2 %0, %1, %2, %0;" : "+l"(c) : "l"(a), "l"(b));
+}
 
 // The running top-32 list of one row, merged with its BN chunk candidates by ONE FULL WARP (sorted across the lanes): a few
 // qualifying candidates are inserted one by one (ballot -> position, shfl_up -> shift), many take the bitonic sort + merge.
@@ -174,7 +191,7 @@ __device__ __forceinline__ void warp_row_topk(const float* __restrict__ Ds, int 
 
 // LK = 8 / 16 / 32: register list length of the per-row threshold search (>= k * dilation)
 template <int BM, int BN, int TM, int TN, int LK>
-__global__ void __launch_bounds__(KnnCfg<BM, BN, TM, TN>::NT)
+__global__ void __launch_bounds__(KnnCfg<BM, BN, TM, TN>::NT, (TM * TN <= 32 ? 2 : 1))
     knn_topk_kernel(const float* __restrict__ xn, const float* __restrict__ sqx, int ldn,
                     const float* __restrict__ yn, const float* __restrict__ sqy, int ldm,
                     const float* __restrict__ relpos, int N, int M, int C, int k, int dilation,
@@ -183,13 +200,15 @@ __global__ void __launch_bounds__(KnnCfg<BM, BN, TM, TN>::NT)
   using Cfg = KnnCfg<BM, BN, TM, TN>;
   constexpr int KC = KNN_KC, TX = Cfg::TX, TY = Cfg::TY, NT = Cfg::NT, DS = Cfg::DS;
   extern __shared__ __align__(16) float smem[];
-  float* Xs = smem;                    // [2][KC][BM]
-  float* Ys = Xs + 2 * KC * BM;        // [2][KC][BN]
-  float* Ds = Ys + 2 * KC * BN;        // [BM][DS]
+  constexpr int ST = KNN_STAGES;
+  constexpr size_t RING = Cfg::ring_floats > Cfg::cand_floats ? Cfg::ring_floats : Cfg::cand_floats;
+  float* Xs = smem;                    // [ST][KC][BM]
+  float* Ys = Xs + ST * KC * BM;       // [ST][KC][BN]
+  float* Ds = smem + RING;             // [BM][DS]
   float* Ld = Ds + BM * DS;            // [BM][32]
   int* Li = reinterpret_cast<int*>(Ld + BM * 32);
-  float* Cd = reinterpret_cast<float*>(Li + BM * 32);   // [BM][KNN_CAP] candidates of the chunk: distance,
-  int* Ci = reinterpret_cast<int*>(Cd + BM * KNN_CAP);  //                 index
+  float* Cd = smem;                                     // (aliases the ring) [BM][KNN_CAP] candidates of the chunk: distance,
+  int* Ci = reinterpret_cast<int*>(Cd + BM * KNN_CAP);  //                                   index
   float* Thr = reinterpret_cast<float*>(Ci + BM * KNN_CAP);   // [BM] row threshold = K-th smallest distance so far
   int* Cnt = reinterpret_cast<int*>(Thr + BM);                // [BM] candidates <= threshold
 
@@ -228,44 +247,73 @@ __global__ void __launch_bounds__(KnnCfg<BM, BN, TM, TN>::NT)
     return;
   }
 
+  // cp.async slots of this thread: the (channel, 16-byte column group) pairs are the same for every slab
+  constexpr int XCH = KC * BM / 4, YCH = KC * BN / 4;
+  constexpr int NXS = (XCH + NT - 1) / NT, NYS = (YCH + NT - 1) / NT;
+  int xs_off[NXS], xg_off[NXS], xkc[NXS], ys_off[NYS], yg_off[NYS], ykc[NYS];
+#pragma unroll
+  for (int n = 0; n < NXS; ++n) {
+    const int g = tid + n * NT;
+    const int kc = g / (BM / 4), q = g % (BM / 4);
+    const bool ok = g < XCH && i0 + q * 4 < ldn;
+    xkc[n] = ok ? kc : (1 << 30);            // channel index inside the slab (huge = never load)
+    xs_off[n] = kc * BM + q * 4;
+    xg_off[n] = kc * ldn + i0 + q * 4;
+    if (g >= XCH) xs_off[n] = -1;
+  }
+#pragma unroll
+  for (int n = 0; n < NYS; ++n) {
+    const int g = tid + n * NT;
+    const int kc = g / (BN / 4), q = g % (BN / 4);
+    ykc[n] = kc;
+    ys_off[n] = g < YCH ? kc * BN + q * 4 : -1;
+    yg_off[n] = kc * ldm + q * 4;
+  }
+
   for (int j0 = jbeg; j0 < jend; j0 += BN) {
-    float acc[TM][TN];
+    unsigned long long acc2[TM][TN / 2];
 #pragma unroll
     for (int i = 0; i < TM; ++i)
 #pragma unroll
-      for (int j = 0; j < TN; ++j) acc[i][j] = 0.f;
+      for (int j = 0; j < TN / 2; ++j) acc2[i][j] = 0ull;
 
-    auto load_slab = [&](int s, int buf) {
+    auto load_slab = [&](int s) {
       const int c0 = s * KC;
-      for (int g = tid; g < KC * BM / 4; g += NT) {
-        const int kc = g / (BM / 4), q = g % (BM / 4);
-        const int c = c0 + kc, col = i0 + q * 4;
-        const bool ok = (c < C) && (col < ldn);
-        cp_async16(Xs + (buf * KC + kc) * BM + q * 4, ok ? (const void*)(xb + (long long)c * ldn + col) : (const void*)xb, ok);
+      float* xs = Xs + (s % ST) * KC * BM;
+      float* ys = Ys + (s % ST) * KC * BN;
+      const float* xsrc = xb + (long long)c0 * ldn;
+      const float* ysrc = yb + (long long)c0 * ldm + j0;
+#pragma unroll
+      for (int n = 0; n < NXS; ++n) {
+        if (xs_off[n] < 0) continue;
+        const bool ok = c0 + xkc[n] < C;
+        cp_async16(xs + xs_off[n], ok ? (const void*)(xsrc + xg_off[n]) : (const void*)xb, ok);
       }
-      for (int g = tid; g < KC * BN / 4; g += NT) {
-        const int kc = g / (BN / 4), q = g % (BN / 4);
-        const int c = c0 + kc, col = j0 + q * 4;
-        const bool ok = (c < C) && (col < ldm);
-        cp_async16(Ys + (buf * KC + kc) * BN + q * 4, ok ? (const void*)(yb + (long long)c * ldm + col) : (const void*)yb, ok);
+#pragma unroll
+      for (int n = 0; n < NYS; ++n) {
+        if (ys_off[n] < 0) continue;
+        const bool ok = (c0 + ykc[n] < C) && (j0 + (ys_off[n] - ykc[n] * BN) < ldm);
+        cp_async16(ys + ys_off[n], ok ? (const void*)(ysrc + yg_off[n]) : (const void*)yb, ok);
       }
-      cp_async_commit();
     };
 
-    load_slab(0, 0);
+    // three-stage ring, one barrier per slab: the barrier of slab s also proves that every thread is done with slab s - 1,
+    // whose buffer the load issued right after it (slab s + 2) overwrites
+    load_slab(0);
+    cp_async_commit();
+    if (nslab > 1) load_slab(1);
+    cp_async_commit();
     for (int s = 0; s < nslab; ++s) {
-      if (s + 1 < nslab) {
-        load_slab(s + 1, (s + 1) & 1);
-        cp_async_wait<1>();
-      } else {
-        cp_async_wait<0>();
-      }
+      cp_async_wait<1>();
       __syncthreads();
-      const float* xs = Xs + (s & 1) * KC * BM;
-      const float* ys = Ys + (s & 1) * KC * BN;
+      if (s + 2 < nslab) load_slab(s + 2);
+      cp_async_commit();
+      const float* xs = Xs + (s % ST) * KC * BM;
+      const float* ys = Ys + (s % ST) * KC * BN;
 #pragma unroll
       for (int kc = 0; kc < KC; ++kc) {
-        float a[TM], bb[TN];
+        float a[TM];
+        unsigned long long b2[TN / 2];
         if constexpr (TM >= 4) {
 #pragma unroll
           for (int g = 0; g < TM / 4; ++g) {
@@ -279,15 +327,23 @@ __global__ void __launch_bounds__(KnnCfg<BM, BN, TM, TN>::NT)
 #pragma unroll
         for (int g = 0; g < TN / 4; ++g) {
           const float4 v = *reinterpret_cast<const float4*>(ys + kc * BN + g * 4 * TX + tx * 4);
-          bb[g * 4 + 0] = v.x; bb[g * 4 + 1] = v.y; bb[g * 4 + 2] = v.z; bb[g * 4 + 3] = v.w;
+          b2[g * 2 + 0] = pack_f32x2(v.x, v.y);
+          b2[g * 2 + 1] = pack_f32x2(v.z, v.w);
         }
 #pragma unroll
-        for (int i = 0; i < TM; ++i)
+        for (int i = 0; i < TM; ++i) {
+          const unsigned long long aa = pack_f32x2(a[i], a[i]);
 #pragma unroll
-          for (int j = 0; j < TN; ++j) acc[i][j] = fmaf(a[i], bb[j], acc[i][j]);
+          for (int j = 0; j < TN / 2; ++j) ffma2(acc2[i][j], aa, b2[j]);
+        }
       }
-      __syncthreads();
     }
+    cp_async_wait<0>();
+    float acc[TM][TN];
+#pragma unroll
+    for (int i = 0; i < TM; ++i)
+#pragma unroll
+      for (int j = 0; j < TN / 2; ++j) unpack_f32x2(acc2[i][j], acc[i][2 * j], acc[i][2 * j + 1]);
 
     // epilogue: distances -> shared tile
 #pragma unroll

@@ -45,6 +45,9 @@ if "gemm" in which:
     ops.gemm_bf16_tn(a132, b528, None)
 if "knn" in which:
     ops.knn_graph(xs, 512, 168, relpos=rp, k=7)
+if "knn_pool" in which:      # Pool-GNN stage 3: 10 752 query tokens x 1 344 pooled candidates, 264 channels, k = 28
+    ops.knn_graph(torch.randn(10752, 264, device=dev), 1, 10752, y=torch.randn(1344, 264, device=dev), m=1344,
+                  relpos=torch.randn(1, 10752, 1344, device=dev) * 0.1, k=28)
 if "norm" in which:
     g = torch.ones(136, device=dev)
     ops.norm_act_tokens(a132, g[:132], g[:132], None, None, 0.1, 1e-5, 0.01, 1)
