@@ -345,23 +345,48 @@ __global__ void __launch_bounds__(KnnCfg<BM, BN, TM, TN>::NT, (TM * TN <= 32 ? 2
 #pragma unroll
       for (int j = 0; j < TN / 2; ++j) unpack_f32x2(acc2[i][j], acc[i][2 * j], acc[i][2 * j + 1]);
 
-    // epilogue: distances -> shared tile
+    // epilogue: distances -> shared tile (|y|^2 and the relative-position bias as 16-byte loads when M allows)
+    const bool vec4 = (M & 3) == 0;
+    float sy[TN];
+#pragma unroll
+    for (int g = 0; g < TN / 4; ++g) {
+      const int gj = j0 + g * 4 * TX + tx * 4;
+      if (vec4 && gj < M) {
+        const float4 v = *reinterpret_cast<const float4*>(sqy + (long long)b * M + gj);
+        sy[g * 4 + 0] = v.x; sy[g * 4 + 1] = v.y; sy[g * 4 + 2] = v.z; sy[g * 4 + 3] = v.w;
+      } else {
+#pragma unroll
+        for (int e = 0; e < 4; ++e) sy[g * 4 + e] = (gj + e < M) ? sqy[(long long)b * M + gj + e] : 0.f;
+      }
+    }
 #pragma unroll
     for (int i = 0; i < TM; ++i) {
       const int row = TM >= 4 ? (i / 4) * 4 * TY + ty * 4 + (i % 4) : ty * TM + i;
       const int gi = i0 + row;
       const float sx = (gi < N) ? sqx[(long long)b * N + gi] : 0.f;
+      const float* rprow = relpos ? relpos + (long long)gi * M : nullptr;
 #pragma unroll
       for (int g = 0; g < TN / 4; ++g) {
         const int col = g * 4 * TX + tx * 4;
+        const int gj0 = j0 + col;
+        float rp[4] = {0.f, 0.f, 0.f, 0.f};
+        if (rprow && gi < N) {
+          if (vec4 && gj0 < M) {
+            const float4 v = *reinterpret_cast<const float4*>(rprow + gj0);
+            rp[0] = v.x; rp[1] = v.y; rp[2] = v.z; rp[3] = v.w;
+          } else {
+#pragma unroll
+            for (int e = 0; e < 4; ++e)
+              if (gj0 + e < M) rp[e] = rprow[gj0 + e];
+          }
+        }
         float dv[4];
 #pragma unroll
         for (int e = 0; e < 4; ++e) {
-          const int gj = j0 + col + e;
           float d = __int_as_float(0x7f800000);
-          if (gi < N && gj < M) {
-            d = __fadd_rn(__fadd_rn(sx, __fmul_rn(-2.f, acc[i][g * 4 + e])), sqy[(long long)b * M + gj]);
-            if (relpos) d = __fadd_rn(d, relpos[(long long)gi * M + gj]);
+          if (gi < N && gj0 + e < M) {
+            d = __fadd_rn(__fadd_rn(sx, __fmul_rn(-2.f, acc[i][g * 4 + e])), sy[g * 4 + e]);
+            if (relpos) d = __fadd_rn(d, rp[e]);
           }
           dv[e] = d;
         }
@@ -388,14 +413,13 @@ __global__ void __launch_bounds__(KnnCfg<BM, BN, TM, TN>::NT, (TM * TN <= 32 ? 2
       float lst[LK];
 #pragma unroll
       for (int p = 0; p < LK; ++p) lst[p] = (p < LK - K) ? -INF : INF;
+      // sorted insert without a serial chain: slot p takes min(old[p], max(old[p - 1], v)) — every slot depends only on
+      // the OLD list, so the LK updates are independent (the bubble form v -> min / max -> next slot is LK deep)
       auto push = [&](float v) {
         if (v < lst[LK - 1]) {
 #pragma unroll
-          for (int p = 0; p < LK; ++p) {
-            const float t = fminf(lst[p], v);
-            v = fmaxf(lst[p], v);
-            lst[p] = t;
-          }
+          for (int p = LK - 1; p > 0; --p) lst[p] = fminf(lst[p], fmaxf(lst[p - 1], v));
+          lst[0] = fminf(lst[0], v);
         }
       };
       auto publish = [&](int slot) {

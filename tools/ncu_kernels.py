@@ -46,7 +46,7 @@ if "gemm" in which:
 if "knn" in which:
     ops.knn_graph(xs, 512, 168, relpos=rp, k=7)
 if "knn_pool" in which:      # Pool-GNN stage 3: 10 752 query tokens x 1 344 pooled candidates, 264 channels, k = 28
-    ops.knn_graph(torch.randn(10752, 264, device=dev), 1, 10752, y=torch.randn(1344, 264, device=dev), m=1344,
+    ops.knn_graph(torch.randn(10752, 264, device=dev), 1, 10752, y_tok=torch.randn(1344, 264, device=dev), m=1344,
                   relpos=torch.randn(1, 10752, 1344, device=dev) * 0.1, k=28)
 if "norm" in which:
     g = torch.ones(136, device=dev)
