@@ -428,7 +428,8 @@ extern "C" int nextou_conv3d_ndhwc_halo_fwd_affine(const void* x, long long ldx,
   int per_sm = (int)((220 * 1024) / smem);
   if (per_sm > 512 / p.tmem_cols) per_sm = 512 / p.tmem_cols;
   if (per_sm < 1) per_sm = 1;
-  long long ctas = ((long long)num_sms() * per_sm + n_tiles - 1) / n_tiles;
+  // one resident wave: rounding UP here put 150 CTAs of a 3-tile GEMM on 148 SMs, i.e. a second wave for 2 CTAs (2x kernel time)
+  long long ctas = ((long long)num_sms() * per_sm) / n_tiles;
   if (ctas > p.total_tiles) ctas = p.total_tiles;
   if (ctas < 1) ctas = 1;
   dim3 grid((unsigned)ctas, (unsigned)n_tiles);

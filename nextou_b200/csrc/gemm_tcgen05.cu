@@ -244,11 +244,14 @@ using namespace nextou;
 // (measured 8.7x off the HBM roofline).  Here a CTA keeps its [block_n x K] weight slice RESIDENT in shared memory
 // (loaded once), walks the row tiles m = blockIdx.x, blockIdx.x + gridDim.x, ..., streams only the activation tiles
 // through a TMA ring and double-buffers the accumulator in tensor memory so the epilogue of tile i overlaps tile i+1.
-// 192 threads: warp 0 TMA producer, warp 1 MMA issuer (warp-uniform, elected lane), warps 2-5 epilogue.
+// 320 threads: warp 0 TMA producer, warp 1 MMA issuer (warp-uniform, elected lane), warps 2-9 epilogue: the epilogue of a
+// 128 x block_n tile is a latency chain per warp (TMEM load -> convert -> store), so two warps share each TMEM lane quadrant
+// and take alternate 32-column chunks (ncu: 4 epilogue warps = 1 per scheduler ran the 86 016 x 132 -> 528 GEMM at 4 us per tile).
 // ======================================================================================================
 namespace nextou {
 
 constexpr int PG_MAX_STAGES = 8;
+constexpr int PG_THREADS = 320;   // warp 0 TMA producer, warp 1 MMA issuer, warps 2-9 epilogue (two per TMEM lane quadrant)
 
 struct PGemmParams {
   int M, N, K;
@@ -274,7 +277,7 @@ __device__ __forceinline__ void mbar_arrive_cta(uint64_t* bar) {
   asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
 
-__global__ void __launch_bounds__(GEMM_THREADS, 1)
+__global__ void __launch_bounds__(PG_THREADS, 1)
     gemm_pers_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                              const PGemmParams p) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
@@ -309,7 +312,7 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1)
     prefetch_tmap(&tmB);
     for (int s = 0; s < p.a_stages; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1); }
     mbar_init(bres_bar, 1);
-    for (int a = 0; a < 2; ++a) { mbar_init(&tmem_full[a], 1); mbar_init(&tmem_empty[a], 4); }
+    for (int a = 0; a < 2; ++a) { mbar_init(&tmem_full[a], 1); mbar_init(&tmem_empty[a], 8); }
     fence_barrier_init();
   }
   if (warp == 2) tmem_alloc(tmem_holder, (uint32_t)p.tmem_cols);
@@ -369,6 +372,8 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1)
     }
   } else {
     const int q = warp & 3;
+    const int part = (warp - 2) >> 2;     // which of the two warps of this lane quadrant
+    const bool plain = p.scale == nullptr && p.slope == 1.f;
     int it = 0;
     for (long long mt = blockIdx.x; mt < p.m_tiles; mt += gridDim.x, ++it) {
       const long long row = mt * GEMM_BM + q * 32 + lane;
@@ -389,15 +394,15 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1)
           const long long orow = ((b * (p.D * p.kd) + d * p.kd + a) * Ho + h * p.kh + i) * Wo + w * p.kw + j;
           __nv_bfloat16* dst = row < p.M ? reinterpret_cast<__nv_bfloat16*>(p.C) + orow * p.ldc : nullptr;
           epilogue_row_bf16(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * p.block_n + tl * p.cpb), p.cpb, sbias + tl * p.cpb,
-                            dst, p.cp_store, false, p.slope);
+                            dst, p.cp_store, false, p.slope, part, 2, plain);
         }
       } else if (p.out_dtype == NEXTOU_BF16) {
         __nv_bfloat16* dst = row < p.M ? reinterpret_cast<__nv_bfloat16*>(p.C) + row * p.ldc + n0 : nullptr;
         const long long left = p.ldc - n0;
         epilogue_row_bf16(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * p.block_n), p.block_n, sbias, dst,
-                          (int)(left < p.block_n ? left : p.block_n), p.row32 != 0, p.slope);
+                          (int)(left < p.block_n ? left : p.block_n), p.row32 != 0, p.slope, part, 2, plain);
       } else
-      for (int c = 0; c < p.block_n; c += 16) {
+      for (int c = part * 16; c < p.block_n; c += 32) {
         uint32_t raw[16];
         tmem_ld16(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * p.block_n + c), raw);
         tmem_ld_wait();
@@ -488,12 +493,13 @@ extern "C" int nextou_gemm_bf16_tn_affine(const void* A, long long lda, const vo
   int per_sm = (int)((220 * 1024) / smem);
   if (per_sm > 512 / p.tmem_cols) per_sm = 512 / p.tmem_cols;
   if (per_sm < 1) per_sm = 1;
-  long long ctas = ((long long)num_sms() * per_sm + n_tiles - 1) / n_tiles;
+  // one resident wave: rounding UP here put 150 CTAs of a 3-tile GEMM on 148 SMs, i.e. a second wave for 2 CTAs (2x kernel time)
+  long long ctas = ((long long)num_sms() * per_sm) / n_tiles;
   if (ctas > p.m_tiles) ctas = p.m_tiles;
   if (ctas < 1) ctas = 1;
   NEXTOU_REQUIRE(n_tiles <= 65535, "gemm_bf16_tn: grid too large");
   dim3 grid((unsigned)ctas, (unsigned)n_tiles);
-  gemm_pers_tcgen05_kernel<<<grid, GEMM_THREADS, smem, (cudaStream_t)stream>>>(tmA, tmB, p);
+  gemm_pers_tcgen05_kernel<<<grid, PG_THREADS, smem, (cudaStream_t)stream>>>(tmA, tmB, p);
   return check_launch("gemm_pers_tcgen05_kernel");
 }
 
@@ -573,11 +579,12 @@ extern "C" int nextou_convtranspose_scatter_fwd(const void* x, long long ldx, in
   int per_sm = (int)((220 * 1024) / smem);
   if (per_sm > 512 / p.tmem_cols) per_sm = 512 / p.tmem_cols;
   if (per_sm < 1) per_sm = 1;
-  long long ctas = ((long long)num_sms() * per_sm + n_tiles - 1) / n_tiles;
+  // one resident wave: rounding UP here put 150 CTAs of a 3-tile GEMM on 148 SMs, i.e. a second wave for 2 CTAs (2x kernel time)
+  long long ctas = ((long long)num_sms() * per_sm) / n_tiles;
   if (ctas > p.m_tiles) ctas = p.m_tiles;
   if (ctas < 1) ctas = 1;
   dim3 grid((unsigned)ctas, (unsigned)n_tiles);
-  gemm_pers_tcgen05_kernel<<<grid, GEMM_THREADS, smem, (cudaStream_t)stream>>>(tmA, tmB, p);
+  gemm_pers_tcgen05_kernel<<<grid, PG_THREADS, smem, (cudaStream_t)stream>>>(tmA, tmB, p);
   return check_launch("gemm_pers_tcgen05_kernel");
 }
 

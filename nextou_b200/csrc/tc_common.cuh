@@ -215,14 +215,23 @@ __device__ __forceinline__ float affine_act(uint32_t acc, float scale, float shi
 }
 template <int CHUNK>
 __device__ __forceinline__ void epilogue_store_chunk(const uint32_t* raw, const float* sb, __nv_bfloat16* dst, int c, int ncols,
-                                                     bool row32, float slope) {
+                                                     bool row32, float slope, bool plain = false) {
   uint32_t w[CHUNK / 2];
+  if (plain) {     // training forward / data gradient: "+ bias" only (warp-uniform branch)
 #pragma unroll
-  for (int g = 0; g < CHUNK / 4; ++g) {
-    const float4 b4 = *reinterpret_cast<const float4*>(sb + c + 4 * g);
-    const float4 s4 = *reinterpret_cast<const float4*>(sb + 256 + c + 4 * g);
-    w[2 * g] = pack_bf16x2(affine_act(raw[4 * g], s4.x, b4.x, slope), affine_act(raw[4 * g + 1], s4.y, b4.y, slope));
-    w[2 * g + 1] = pack_bf16x2(affine_act(raw[4 * g + 2], s4.z, b4.z, slope), affine_act(raw[4 * g + 3], s4.w, b4.w, slope));
+    for (int g = 0; g < CHUNK / 4; ++g) {
+      const float4 b4 = *reinterpret_cast<const float4*>(sb + c + 4 * g);
+      w[2 * g] = pack_bf16x2(__uint_as_float(raw[4 * g]) + b4.x, __uint_as_float(raw[4 * g + 1]) + b4.y);
+      w[2 * g + 1] = pack_bf16x2(__uint_as_float(raw[4 * g + 2]) + b4.z, __uint_as_float(raw[4 * g + 3]) + b4.w);
+    }
+  } else {
+#pragma unroll
+    for (int g = 0; g < CHUNK / 4; ++g) {
+      const float4 b4 = *reinterpret_cast<const float4*>(sb + c + 4 * g);
+      const float4 s4 = *reinterpret_cast<const float4*>(sb + 256 + c + 4 * g);
+      w[2 * g] = pack_bf16x2(affine_act(raw[4 * g], s4.x, b4.x, slope), affine_act(raw[4 * g + 1], s4.y, b4.y, slope));
+      w[2 * g + 1] = pack_bf16x2(affine_act(raw[4 * g + 2], s4.z, b4.z, slope), affine_act(raw[4 * g + 3], s4.w, b4.w, slope));
+    }
   }
   if (dst == nullptr) return;
   if (c + CHUNK <= ncols) {
@@ -245,20 +254,24 @@ __device__ __forceinline__ void epilogue_store_chunk(const uint32_t* raw, const 
   }
 }
 
+// `part` of `nparts` warps that share this TMEM lane quadrant: the 32-column chunks (and the 16-column tail) of the row are dealt
+// round-robin to them; plain = "+ bias" only (scale == 1, slope == 1)
 __device__ __forceinline__ void epilogue_row_bf16(uint32_t tmem_row, int block_n, const float* sbias, __nv_bfloat16* dst,
-                                                  int ncols, bool row32, float slope) {
-  int c = 0;
-  for (; c + 32 <= block_n; c += 32) {
+                                                  int ncols, bool row32, float slope, int part = 0, int nparts = 1,
+                                                  bool plain = false) {
+  int c = 0, ci = 0;
+  for (; c + 32 <= block_n; c += 32, ++ci) {
+    if (ci % nparts != part) continue;
     uint32_t raw[32];
     tmem_ld32(tmem_row + (uint32_t)c, raw);
     tmem_ld_wait();
-    epilogue_store_chunk<32>(raw, sbias, dst, c, ncols, row32, slope);
+    epilogue_store_chunk<32>(raw, sbias, dst, c, ncols, row32, slope, plain);
   }
-  if (c < block_n) {   // block_n is a multiple of 16
+  if (c < block_n && ci % nparts == part) {   // block_n is a multiple of 16
     uint32_t raw[16];
     tmem_ld16(tmem_row + (uint32_t)c, raw);
     tmem_ld_wait();
-    epilogue_store_chunk<16>(raw, sbias, dst, c, ncols, row32, slope);
+    epilogue_store_chunk<16>(raw, sbias, dst, c, ncols, row32, slope, plain);
   }
 }
 

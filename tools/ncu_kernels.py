@@ -48,6 +48,17 @@ if "knn" in which:
 if "knn_pool" in which:      # Pool-GNN stage 3: 10 752 query tokens x 1 344 pooled candidates, 264 channels, k = 28
     ops.knn_graph(torch.randn(10752, 264, device=dev), 1, 10752, y_tok=torch.randn(1344, 264, device=dev), m=1344,
                   relpos=torch.randn(1, 10752, 1344, device=dev) * 0.1, k=28)
+if "upconv" in which:        # last decoder up-sampling: ConvTranspose3d(66 -> 33, k = s = (1, 2, 2)) from 64x112x96 to 64x224x192
+    wt = torch.randn(66, 33, 1, 2, 2, device=dev) * 0.05
+    _, wb = ops.pack_weight_pair(wt, conv=True, flip_b=False)
+    cat = torch.empty(sp0[0] * sp0[1] * sp0[2], 80, device=dev, dtype=torch.bfloat16)
+    ops.convtranspose_fwd_bf16(x66, 1, sp1, 66, wb, 33, (1, 2, 2), torch.zeros(33, device=dev), out=cat, store_cols=40)
+if "seghead" in which:       # full-resolution segmentation head 33 -> 14 and its data gradient 14 -> 33
+    ws = torch.randn(14, 40, device=dev).bfloat16()[:, :33]
+    ops.gemm_bf16_tn(x33, ws, torch.zeros(14, device=dev))
+    dl = torch.randn(sp0[0] * sp0[1] * sp0[2], 16, device=dev).bfloat16()[:, :14]
+    wsT = torch.randn(33, 16, device=dev).bfloat16()[:, :14]
+    ops.gemm_bf16_tn(dl, wsT, None)
 if "norm" in which:
     g = torch.ones(136, device=dev)
     ops.norm_act_tokens(a132, g[:132], g[:132], None, None, 0.1, 1e-5, 0.01, 1)
