@@ -500,13 +500,16 @@ __global__ void __launch_bounds__(WH_THREADS, 1)
   uint32_t* tmem_holder = reinterpret_cast<uint32_t*>(tmem_full + 1);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  int t = blockIdx.y;
+  // grid = (tiles, ksplit): the tiles (kernel depth / row group / channel tiles) of one brick range are launched back to back and
+  // sweep the same dY / X bricks at the same time, so all but the first fetch hit L2 (with the tile index as the slow grid
+  // axis every depth tap re-read both tensors from DRAM: 3x the algorithmic traffic on the 3x3x3 layers)
+  int t = blockIdx.x;
   const int nt = t % p.n_ntiles; t /= p.n_ntiles;
   const int mt = t % p.n_mtiles; t /= p.n_mtiles;
   const int rg = t % p.n_rgroups; t /= p.n_rgroups;
   const int kd_ = t;
   const int m0 = mt * 128, n0 = nt * p.n_tile;
-  const int ks = blockIdx.x;
+  const int ks = blockIdx.y;
   const int r0 = rg * p.grp_rows;                          // first kernel row of this CTA
   const int nrows = min(p.grp_rows, p.kh - r0);
   const int inplane = nrows * p.kw;                        // in-plane taps of this CTA: rows r0 .. r0 + nrows - 1
@@ -695,7 +698,7 @@ extern "C" int nextou_conv3d_ndhwc_halo_wgrad(const void* dy, long long ldy, con
   int rc = ensure_smem(wgrad_halo_tcgen05_kernel, smem);
   if (rc) return rc;
   NEXTOU_REQUIRE(tiles <= 65535, "conv3d_ndhwc_halo_wgrad: too many tiles");
-  dim3 grid((unsigned)p.ksplit, (unsigned)tiles);
+  dim3 grid((unsigned)tiles, (unsigned)p.ksplit);
   wgrad_halo_tcgen05_kernel<<<grid, WH_THREADS, smem, (cudaStream_t)stream>>>(tmDY, tmX, p);
   return check_launch("wgrad_halo_tcgen05_kernel");
 }
@@ -739,9 +742,9 @@ __global__ void __launch_bounds__(WH_THREADS, 1)
   uint32_t* tmem_holder = reinterpret_cast<uint32_t*>(tmem_full + 1);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int mt = blockIdx.y % p.n_mtiles, kd_ = blockIdx.y / p.n_mtiles;
+  const int mt = blockIdx.x % p.n_mtiles, kd_ = blockIdx.x / p.n_mtiles;   // tiles fastest: see wgrad_halo_tcgen05_kernel
   const int m0 = mt * 128;
-  const int ks = blockIdx.x;
+  const int ks = blockIdx.y;
 
   if (warp == 0 && lane == 0) {
     prefetch_tmap(&tmDY);
@@ -902,7 +905,7 @@ extern "C" int nextou_conv3d_ndhwc_planes_wgrad(const void* dy, long long ldy, c
   int rc = ensure_smem(wgrad_planes_tcgen05_kernel, smem);
   if (rc) return rc;
   NEXTOU_REQUIRE(tiles <= 65535, "conv3d_ndhwc_planes_wgrad: too many tiles");
-  dim3 grid((unsigned)p.ksplit, (unsigned)tiles);
+  dim3 grid((unsigned)tiles, (unsigned)p.ksplit);
   wgrad_planes_tcgen05_kernel<<<grid, WH_THREADS, smem, (cudaStream_t)stream>>>(tmDY, tmX[0], tmX[1], tmX[2], tmX[3], p);
   return check_launch("wgrad_planes_tcgen05_kernel");
 }

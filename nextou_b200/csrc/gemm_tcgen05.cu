@@ -823,14 +823,14 @@ __global__ void __launch_bounds__(WG_THREADS, 1)
   uint32_t* tmem_base_holder = reinterpret_cast<uint32_t*>(tmem_full_bar + 1);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  int t = blockIdx.y;
+  int t = blockIdx.x;   // grid = (tiles, ksplit): the tap groups / channel tiles of one brick range run together and share L2
   const int nt = t % p.n_ntiles; t /= p.n_ntiles;
   const int mt = t % p.n_mtiles; t /= p.n_mtiles;
   const int grp = t;
   const int m0 = mt * 128, n0 = nt * p.n_tile;
   const int tap0 = grp * p.tap_group;
   const int ntaps = min(p.tap_group, p.taps - tap0);
-  const int ks = blockIdx.x;
+  const int ks = blockIdx.y;
 
   if (warp == 0 && lane == 0) {
     prefetch_tmap(&tmDY);
@@ -1001,7 +1001,7 @@ extern "C" int nextou_conv3d_ndhwc_strided_wgrad(const void* dy, long long ldy, 
   int rc = ensure_smem(wgrad_tcgen05_kernel, smem);
   if (rc) return rc;
   NEXTOU_REQUIRE(tiles <= 65535, "conv3d_ndhwc_wgrad: too many tiles");
-  dim3 grid((unsigned)p.ksplit, (unsigned)tiles);
+  dim3 grid((unsigned)tiles, (unsigned)p.ksplit);
   wgrad_tcgen05_kernel<<<grid, WG_THREADS, smem, (cudaStream_t)stream>>>(tmDY, tmX, p);
   return check_launch("wgrad_tcgen05_kernel");
 }
