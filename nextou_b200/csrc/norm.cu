@@ -416,7 +416,7 @@ static int plan_sweep(int C, long long rows, int instances, SweepPlan& p) {
   long long nblk = (4LL * num_sms() + instances - 1) / instances;   // one wave at 4 resident CTAs / SM (grid-stride sweeps)
   // small (L2-resident) tensors: fewer, fatter CTAs -> fewer partial rows for the latency-bound finalize (>= 16 sweeps each)
   const long long fat = (sweeps + 15) / 16;
-  const long long floor_blk = (2LL * num_sms() + instances - 1) / instances;
+  const long long floor_blk = ((long long)num_sms() + instances - 1) / instances;   // measured: 1 CTA / SM beats 2 for <= 6 MB tensors
   if (nblk > fat) nblk = fat > floor_blk ? fat : floor_blk;
   if (nblk > sweeps) nblk = sweeps;
   if (nblk < 1) nblk = 1;

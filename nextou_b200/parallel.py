@@ -49,6 +49,9 @@ class GradientAllReducer:
         self._pending = [0] * len(self.buckets)
         self._sizes = [len(g) for g in groups]
         self._handles = []
+        # NCCL averages inside the collective (ncclAvg); gloo has no AVG: sum, then one scaling pass over the buckets
+        self._avg = world_size > 1 and dist.is_initialized() and dist.get_backend() == "nccl"
+        self._op = dist.ReduceOp.AVG if self._avg else dist.ReduceOp.SUM
         self.attach()
         if self.overlap:
             for p in self.params:
@@ -71,7 +74,7 @@ class GradientAllReducer:
         b = self._bucket_of[p]
         self._pending[b] += 1
         if self._pending[b] == self._sizes[b]:
-            self._handles.append(dist.all_reduce(self.buckets[b], op=dist.ReduceOp.SUM, async_op=True))
+            self._handles.append(dist.all_reduce(self.buckets[b], op=self._op, async_op=True))
 
     def all_reduce(self):
         """Finish the step's gradient exchange: afterwards every param.grad holds the mean over ranks."""
@@ -83,12 +86,13 @@ class GradientAllReducer:
             done = {i for i in range(len(self.buckets)) if self.overlap and self._pending[i] == self._sizes[i]}
             for i, flat in enumerate(self.buckets):
                 if i not in done:
-                    self._handles.append(dist.all_reduce(flat, op=dist.ReduceOp.SUM, async_op=True))
+                    self._handles.append(dist.all_reduce(flat, op=self._op, async_op=True))
         for h in self._handles:
             h.wait()
         self._handles = []
         self._pending = [0] * len(self.buckets)
-        torch._foreach_mul_(self.buckets, 1.0 / self.world)
+        if not self._avg:
+            torch._foreach_mul_(self.buckets, 1.0 / self.world)
 
 
 class PeerExchange:
