@@ -72,6 +72,21 @@ def test_knn_full_size_sites_bit_exact(shape):
     assert np.array_equal(_gpu_knn(x, y, relpos, k, 1), want)
 
 
+@pytest.mark.parametrize("distinct", [1, 3, 40], ids=["all_equal", "3_distinct", "40_distinct"])
+@pytest.mark.parametrize("shape", [(4, 168, 0, 7, 1), (2, 168, 0, 9, 2), (1, 512, 1344, 28, 1)], ids=["swin_k7", "swin_k9_d2", "pool_k28"])
+def test_knn_massive_distance_ties_bit_exact(shape, distinct):
+    """Duplicated tokens (background of a CT volume): far more than KNN_CAP candidates tie with the K-th best distance, so the
+    kernel takes its warp-level slow path (and the running-list merge across candidate chunks); ties go to the lowest index."""
+    B, N, M, k, d = shape
+    g = torch.Generator().manual_seed(11)
+    C = 48
+    protos = torch.randn(distinct, C, generator=g)
+    x = protos[torch.randint(0, distinct, (B, N), generator=g)]
+    y = protos[torch.randint(0, distinct, (B, M), generator=g)] if M else None
+    want = c_oracle.knn_graph(x.numpy(), None if y is None else y.numpy(), None, k, d)
+    assert np.array_equal(_gpu_knn(x, y, None, k, d), want)
+
+
 def test_knn_bf16_input_unnormalized_and_row_map():
     from nextou_b200 import ops
     g = torch.Generator().manual_seed(3)
