@@ -156,3 +156,40 @@ class GraphedTrainStep:
         self._load(x, targets)
         self.graph.replay()
         return self.static_loss
+
+    # ---- input pipelining -----------------------------------------------------------------------------------------
+    # `step(x_host, t_host)` serialises the host -> device copy of a batch (25 MB for a 3d_fullres patch: ~0.45 ms over PCIe) in
+    # front of its replay.  prefetch() starts that copy for the NEXT batch on a copy stream, into a second set of device
+    # buffers, while the current replay is running; step_prefetched() then only moves it device-to-device (~10 us) into the
+    # graph's static inputs.  Call order per iteration: step_prefetched() -> prefetch(next batch) -> read the loss.
+    def prefetch(self, x: torch.Tensor, targets: Sequence[torch.Tensor]) -> None:
+        if not hasattr(self, "_copy_stream"):
+            dev = self.static_x.device
+            self._copy_stream = torch.cuda.Stream(dev)
+            self._stage_x = torch.empty_like(self.static_x)
+            self._stage_t = [torch.empty_like(t) for t in self.static_t]
+            self._staged = torch.cuda.Event()
+            self._consumed = torch.cuda.Event()
+            self._consumed.record(torch.cuda.current_stream(dev))
+        with torch.cuda.stream(self._copy_stream):
+            self._copy_stream.wait_event(self._consumed)        # the previous staged batch has been moved into the static inputs
+            self._stage_x.copy_(x, non_blocking=True)
+            for s, t in zip(self._stage_t, targets):
+                s.copy_(t, non_blocking=True)
+            self._staged.record(self._copy_stream)
+        self._has_staged = True
+
+    def step_prefetched(self) -> torch.Tensor:
+        """Replay on the batch handed to the last prefetch()."""
+        if not getattr(self, "_has_staged", False):
+            raise NextouError("step_prefetched() without a prefetch()")
+        self._has_staged = False
+        self._sync_hyper_parameters()
+        cur = torch.cuda.current_stream(self.static_x.device)
+        cur.wait_event(self._staged)
+        self.static_x.copy_(self._stage_x, non_blocking=True)
+        for s, t in zip(self.static_t, self._stage_t):
+            s.copy_(t, non_blocking=True)
+        self._consumed.record(cur)
+        self.graph.replay()
+        return self.static_loss

@@ -122,3 +122,45 @@ def test_graph_replay_follows_learning_rate_schedule():
     opt2.param_groups[0]["lr"] = 5e-3
     with pytest.raises(NextouError):
         step2(xd, td)
+
+
+def test_prefetched_steps_match_plain_replays():
+    """GraphedTrainStep.prefetch / step_prefetched (next batch staged on a copy stream during the current replay) must train
+    like step(x_host, t_host): the same losses for a sequence of DIFFERENT batches fed from pinned host memory."""
+    from nextou_b200.graphed import GraphedTrainStep
+    from nextou_b200._lib import NextouError
+    model, loss_fn, x, targets = _setup()
+    state0 = copy.deepcopy(model.state_dict())
+    g = torch.Generator().manual_seed(9)
+    batches = []
+    for _ in range(4):
+        xb = torch.randn(x.shape, generator=g).pin_memory()
+        tb = [torch.randint(0, 3, t.shape, generator=g).float().pin_memory() for t in targets]
+        batches.append((xb, tb))
+
+    def run(prefetched):
+        model.load_state_dict(state0)
+        params = [p for p in model.parameters() if p.requires_grad]
+        opt = torch.optim.SGD(params, lr=1e-2, momentum=0.9, fused=True)
+        step = GraphedTrainStep(model, loss_fn, opt, x.to(DEV), [t.to(DEV) for t in targets], clip_grad_norm=12, warmup=1)
+        model.load_state_dict(state0)           # the warm-up steps moved the weights
+        losses = []
+        if prefetched:
+            with pytest.raises(NextouError):
+                step.step_prefetched()
+            step.prefetch(*batches[0])
+            for i in range(len(batches)):
+                loss = step.step_prefetched()
+                if i + 1 < len(batches):
+                    step.prefetch(*batches[i + 1])
+                losses.append(loss.item())
+        else:
+            for xb, tb in batches:
+                losses.append(step(xb, tb).item())
+        del step
+        return losses
+
+    plain, pre = run(False), run(True)
+    assert max(plain) - min(plain) > 1e-2        # different batches, visibly different losses
+    # split-K weight gradients are reduced with floating-point atomics: two runs agree to rounding, not bit for bit
+    assert pre == pytest.approx(plain, rel=2e-3)
