@@ -170,7 +170,12 @@ def _dyn_graph_features(mod, q_tok, graphs, n, y_tok, m, relative_pos, q_row_map
     k, d = mod.k, mod.d
     knn_mod = mod.dilated_knn_graph
     cols = graph.draw_stochastic_columns(k, d, knn_mod.stochastic, knn_mod.epsilon, mod.training)
-    if cols is not None and d > 1:
+    forced = getattr(mod, "forced_nn_idx", None)
+    if forced is not None:
+        # diagnostics only (tools/dist_checks.py): neighbour lists recorded from another run of the same network, so that two
+        # runs whose statistics differ in the last bit do not diverge through a flipped near-tie (chaos note)
+        idx32 = forced
+    elif cols is not None and d > 1:
         _, idx32 = ops.knn_graph(q_tok, graphs, n, y_tok, m, relpos=relative_pos, k=k * d, dilation=1,
                                  x_row_map=q_row_map, y_row_map=q_row_map if y_tok is None else None)
         idx32 = idx32[:, :, cols.to(idx32.device)].contiguous()

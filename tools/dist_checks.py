@@ -108,7 +108,19 @@ def check_gradient_parity(rank, world, dev, log):
     cfg = MINI3D
     xs = [torch.randn(1, 1, *cfg["patch"], generator=torch.Generator().manual_seed(r)) for r in range(world)]
     base = build_nextou(cfg, seed=0)
+    # the single-process run: plain BatchNorm over the batch of `world` patches (every rank runs it: its neighbour lists are
+    # teacher-forced into the data-parallel run below)
+    ref = copy.deepcopy(base).to(dev).train()
+    outs = ref(torch.cat(xs).to(dev))
+    # mean over the batch of each output == mean over ranks of the per-patch means
+    sum(o.float().mean() for o in outs).backward()
     model = torch.nn.SyncBatchNorm.convert_sync_batchnorm(copy.deepcopy(base)).to(dev).train()
+    ref_graphs = [m for m in ref.modules() if hasattr(m, "last_nn_idx")]
+    own_graphs = [m for m in model.modules() if hasattr(m, "dilated_knn_graph")]
+    assert len(ref_graphs) == len(own_graphs) and ref_graphs
+    for mr, mo in zip(ref_graphs, own_graphs):
+        g = mr.last_nn_idx.shape[0] // world                  # graphs (patches or windows, batch-major) of one patch
+        mo.forced_nn_idx = mr.last_nn_idx[rank * g:(rank + 1) * g].contiguous()
     params = [p for p in model.parameters() if p.requires_grad]
     red = GradientAllReducer(params, world)
     red.zero_grad()
@@ -118,10 +130,6 @@ def check_gradient_parity(rank, world, dev, log):
     torch.cuda.synchronize()
     ok = True
     if rank == 0:
-        ref = copy.deepcopy(base).to(dev).train()               # plain BatchNorm over the batch of `world` patches
-        outs = ref(torch.cat(xs).to(dev))
-        # mean over the batch of each output == mean over ranks of the per-patch means
-        sum(o.float().mean() for o in outs).backward()
         num = den = 0.0
         worst = ("", 0.0)
         n_tensors = n_close = 0
@@ -140,11 +148,11 @@ def check_gradient_parity(rank, world, dev, log):
             if r > worst[1]:
                 worst = (n, r)
         total = (num / den) ** 0.5
-        # no teacher forcing here: the two runs sum their batch statistics in different orders, and a randomly initialised
-        # NexToU flips a few near-tied neighbours / max-pool positions on such 1e-7 differences.  Hence an
-        # overall bound plus a bound on the share of tensors that are off (the single-GPU test with replayed graphs has 5e-2
-        # for every tensor)
-        ok = total <= 2e-2 and n_close >= 0.85 * n_tensors and worst[1] <= 0.3
+        # the two runs sum their batch statistics in different orders; a randomly initialised NexToU flips near-tied
+        # neighbours on such 1e-7 differences and diverges, so the neighbour lists of the single-process run are
+        # teacher-forced into the data-parallel one.  What can still flip is the arg-max of a max-pool window: hence an overall
+        # bound plus a bound on the share of tensors that are off
+        ok = total <= 1e-2 and n_close >= 0.97 * n_tensors and worst[1] <= 0.1     # measured: 1.9e-3, 275 / 275, 9e-3
         log(f"gradient parity {world} ranks x 1 patch vs 1 process x batch {world}: overall relative L2 {total:.2e}, "
             f"{n_close}/{n_tensors} tensors within 5e-2, worst {worst[0]} {worst[1]:.2e}" + (" OK" if ok else " FAIL"))
     return ok
