@@ -40,6 +40,49 @@ def _fork_wgrad(ctx, tensor):
     return None
 
 
+class _PendingWgrads:
+    """Weight-gradient kernels of the running backward pass that the main stream has not waited for yet."""
+    keep = []          # tensors / closures the side-stream kernels still read or write
+    armed = False      # end-of-backward callback queued
+
+
+def _flush_pending(device):
+    torch.cuda.current_stream(device).wait_stream(ops.side_launch(device).side)
+    _PendingWgrads.keep.clear()        # only now may the caching allocator hand these blocks to main-stream tensors
+    _PendingWgrads.armed = False
+
+
+def _complete_wgrad(side, param, finish, keep):
+    """Finish a side-stream weight gradient: `finish()` turns the kernel's raw fp32 accumulator into the gradient tensor
+    (layout copy, gap / group slicing).
+
+    Default: join (the main stream waits for the side stream), then finish on the main stream.
+    Deferred (ops.DEFER_WGRAD_JOIN): when the parameter has no gradient yet and no post-accumulate hooks, autograd's
+    AccumulateGrad takes the returned tensor as param.grad without launching a kernel, so nothing on the main stream reads
+    it before the backward pass ends.  Then `finish` runs on the SIDE stream as well, the operands (`keep`) stay referenced,
+    and one join at the end of the backward pass (engine callback) orders everything before the optimizer.  The main stream
+    goes straight on to the previous layer's normalisation backward, which is HBM bound and co-resides with the
+    tensor-bound weight-gradient CTAs.  Gradient accumulation (param.grad already set), DistributedDataParallel /
+    GradientAllReducer buckets and hooks take the default path."""
+    hooks = getattr(param, "_post_accumulate_grad_hooks", None) if param is not None else None
+    if not (ops.DEFER_WGRAD_JOIN and param is not None and param.grad is None and not hooks and not torch.is_grad_enabled()):
+        side.join()
+        return finish()
+    with torch.cuda.stream(side.side):
+        # the layout copy into the parameter's own (contiguous) layout happens HERE, on the side stream: a strided view would
+        # be copied by AccumulateGrad on the main stream, before the kernel has written it
+        dw = finish().contiguous()
+    if dw.numel() != param.numel() or not param.is_contiguous():     # AccumulateGrad would copy it on the main stream: wait first
+        side.join()
+        return dw
+    _PendingWgrads.keep.append((keep, finish))
+    if not _PendingWgrads.armed:
+        _PendingWgrads.armed = True
+        device = dw.device
+        torch.autograd.Variable._execution_engine.queue_callback(lambda: _flush_pending(device))
+    return dw
+
+
 class _LinearTokens(torch.autograd.Function):
     """y[T, N] = x[T, K] @ w2d[N, K]^T + b  with w2d an fp32 / bf16 master weight."""
 
@@ -55,6 +98,7 @@ class _LinearTokens(torch.autograd.Function):
         y = ops.gemm_bf16_tn(xb, wp[:, :K], bias, n=N)[:, :N]
         ctx.save_for_backward(xb, w2d)
         ctx.wt = wt
+        ctx.owner = owner
         ctx.groups = groups
         ctx.has_bias = bias is not None
         ctx.bias_dtype = None if bias is None else bias.dtype
@@ -74,14 +118,15 @@ class _LinearTokens(torch.autograd.Function):
             dw = ops.conv_wgrad_bf16(dyb, xb, 1, (xb.shape[0],), K, N, (1,), side=side)
         if ctx.needs_input_grad[0]:
             dx = ops.gemm_bf16_tn(dyb, ctx.wt[:, :N], None, n=K)[:, :K]          # dX = dY W
-        if side is not None:
-            side.join()
-            dw = dw()
         if ctx.needs_input_grad[1]:
-            dw = dw.reshape(N, K)
-            if g > 1:   # diagonal blocks of the dense gradient -> (Cout, Cin / groups)
-                dw = dw.view(g, N // g, g, K // g).diagonal(dim1=0, dim2=2).permute(2, 0, 1).reshape(N, K // g)
-            dw = dw.to(w2d.dtype)
+            raw = dw
+
+            def finish():
+                d = (raw() if side is not None else raw).reshape(N, K)
+                if g > 1:   # diagonal blocks of the dense gradient -> (Cout, Cin / groups)
+                    d = d.view(g, N // g, g, K // g).diagonal(dim1=0, dim2=2).permute(2, 0, 1).reshape(N, K // g)
+                return d.to(w2d.dtype)
+            dw = _complete_wgrad(side, _unwrap(ctx.owner), finish, (dyb, xb)) if side is not None else finish()
         if ctx.has_bias and ctx.needs_input_grad[2]:
             db = ops.colsum_tokens(dyb).to(ctx.bias_dtype)
         return dx, dw, db, None, None
@@ -143,13 +188,15 @@ class _ConvTokens(torch.autograd.Function):
             if wt is None:     # small-Cin layer whose input wants a gradient (never the image itself): tensor-core data gradient
                 _, wt = ops.pack_weight_pair(weight, conv=True, flip_b=True, want_b=True, owner=_unwrap(ctx.owner))
             dx = ops.conv_ndhwc_bf16(dyb, batch, spatial, cout, wt, cin_p, ks, None)[:, :cin_p]
-        if side is not None:
-            side.join()
-            dw = dw()
         if ctx.needs_input_grad[1]:
-            if gap is not None and gap[1] > gap[0]:
-                dw = torch.cat([dw[:, :gap[0]], dw[:, gap[1]:]], 1)
-            dw = dw.to(weight.dtype)
+            raw = dw
+
+            def finish():
+                d = raw() if side is not None else raw
+                if gap is not None and gap[1] > gap[0]:
+                    d = torch.cat([d[:, :gap[0]], d[:, gap[1]:]], 1)
+                return d.to(weight.dtype)
+            dw = _complete_wgrad(side, _unwrap(ctx.owner), finish, (dyb, xb)) if side is not None else finish()
         if has_bias and ctx.needs_input_grad[2]:
             db = ops.colsum_tokens(dyb).to(bdt)
         return dx, dw, db, None, None, None, None
@@ -177,6 +224,7 @@ class _ConvStridedTokens(torch.autograd.Function):
         y, _ = ops.conv_strided_fwd_bf16(xb, batch, spatial, cin, wp, cout, ks, stride, padding, bias)
         ctx.save_for_backward(xb, weight)
         ctx.wt = wt
+        ctx.owner = owner
         ctx.meta = (batch, tuple(spatial), tuple(stride), tuple(padding), bias is not None, None if bias is None else bias.dtype)
         return y[:, :cout]
 
@@ -194,11 +242,12 @@ class _ConvStridedTokens(torch.autograd.Function):
             dw = ops.conv_strided_wgrad_bf16(dyb, xb, batch, osp, spatial, cin, cout, ks, stride, padding, side=side)
         if ctx.needs_input_grad[0]:
             dx = ops.conv_strided_dgrad_bf16(dyb, batch, osp, cout, ctx.wt, cin, ks, stride, padding, spatial)[:, :cin]
-        if side is not None:
-            side.join()
-            dw = dw()
         if ctx.needs_input_grad[1]:
-            dw = dw.permute(0, 2, 1).reshape(cout, cin, *ks).to(weight.dtype)
+            raw = dw
+
+            def finish():
+                return (raw() if side is not None else raw).permute(0, 2, 1).reshape(cout, cin, *ks).to(weight.dtype)
+            dw = _complete_wgrad(side, _unwrap(ctx.owner), finish, (dyb, xb)) if side is not None else finish()
         if has_bias and ctx.needs_input_grad[2]:
             db = ops.colsum_tokens(dyb).to(bdt)
         return dx, dw, db, None, None, None, None, None
@@ -283,6 +332,7 @@ class _UpCatTokens(torch.autograd.Function):
             buf[:, pa:pa + cb].copy_(skip)
         ctx.save_for_backward(xb, weight)
         ctx.wa = wa
+        ctx.owner = owner
         ctx.meta = (batch, tuple(spatial), osp, bias is not None, None if bias is None else bias.dtype, pa, cb, skip.dtype)
         return buf[:, :pa + cb]
 
@@ -301,11 +351,12 @@ class _UpCatTokens(torch.autograd.Function):
         if ctx.needs_input_grad[0]:
             dx, _ = ops.conv_strided_fwd_bf16(dyb, batch, osp, cout, ctx.wa, cin, ks, ks, zero, None)
             dx = dx[:, :cin]
-        if side is not None:
-            side.join()
-            dw = dw()
         if ctx.needs_input_grad[1]:
-            dw = dw.permute(0, 2, 1).reshape(cin, cout, *ks).to(weight.dtype)
+            raw = dw
+
+            def finish():
+                return (raw() if side is not None else raw).permute(0, 2, 1).reshape(cin, cout, *ks).to(weight.dtype)
+            dw = _complete_wgrad(side, _unwrap(ctx.owner), finish, (dyb, xb)) if side is not None else finish()
         if has_bias and ctx.needs_input_grad[2]:
             db = ops.colsum_tokens(dyb).to(bdt)
         if ctx.needs_input_grad[3]:

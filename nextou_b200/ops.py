@@ -866,6 +866,9 @@ def conv_strided_wgrad_bf16(dense_tok: torch.Tensor, strided_tok: torch.Tensor, 
 
 
 OVERLAP_WGRAD = True   # run a layer's weight-gradient kernel on a side stream, concurrently with its data-gradient kernel
+# ... and do not make the main stream wait for it at the end of the layer's backward when autograd will merely take the gradient
+# tensor as param.grad (no kernel reads it before the end of the backward pass): native._complete_wgrad
+DEFER_WGRAD_JOIN = os.environ.get("NEXTOU_DEFER_WGRAD_JOIN", "1") != "0"
 _SIDE_STREAMS = {}
 
 

@@ -4,6 +4,7 @@ A randomly initialised NexToU is chaotic in its neighbour lists, so whole-networ
 the product's own kNN results are recorded per site, VERIFIED against the oracle's fp64 distances (every chosen
 neighbour within 1e-4 of the true k-th distance) and replayed into the oracle forward.
 """
+import os
 import numpy as np
 import pytest
 import torch
@@ -415,3 +416,15 @@ def test_config3_global_knn_21952_tokens_matches_oracle():
     full18, _ = ops.knn_graph(tok.to(DEV), 1, 21952, k=18)
     part18, _ = ops.knn_graph(tok[9000:12000].to(DEV), 1, 3000, tok.to(DEV), 21952, k=18)
     assert torch.equal(full18[0, 9000:12000], part18[0])
+
+
+def test_deferred_wgrad_join_is_race_free_on_the_full_size_network():
+    """native._complete_wgrad leaves the weight-gradient kernels of a backward pass on the side stream until the pass ends.
+    tools/defer_check.py runs the 3d_fullres network (kernels long enough for a missing dependency to show): gradients with
+    the deferred join == gradients with a join per layer (up to the split-K atomics), and every deferred gradient becomes
+    param.grad without a main-stream copy."""
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    p = subprocess.run([sys.executable, os.path.join(root, "tools", "defer_check.py"), "3"], capture_output=True, text=True, timeout=600)
+    assert p.returncode == 0 and "DEFER CHECK PASSED" in p.stdout, (p.stdout[-2000:], p.stderr[-2000:])
