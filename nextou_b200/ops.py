@@ -843,12 +843,15 @@ def conv_strided_wgrad_bf16(dense_tok: torch.Tensor, strided_tok: torch.Tensor, 
         ssp = [1] + ssp
     taps = ks[0] * ks[1] * ks[2]
     cs = (c_strided + 3) // 4 * 4
-    dw = torch.zeros((c_dense, taps, cs), device=dense_tok.device, dtype=torch.float32)
+    # split-K accumulator: allocated on the current stream, zero-filled on the side stream when there is one
+    dw = (torch.empty if side is not None else torch.zeros)((c_dense, taps, cs), device=dense_tok.device, dtype=torch.float32)
     V = batch * dsp[0] * dsp[1] * dsp[2]
     L = _lib.lib()
     # down-sampling 3x3 convolutions with a small Cin: halo reuse over the four parity planes of the input (csrc/conv_tcgen05.cu)
     planes = bool(L.nextou_conv3d_ndhwc_planes_wgrad_supported(c_strided, *ks, *st, *pd)) and min(ssp[1], ssp[2]) >= 2
     with (side if side is not None else _null_ctx()):
+        if side is not None:
+            dw.zero_()
         with _lib.timed("wgrad_planes_tcgen05" if planes else "wgrad_tcgen05",
                         2 * V * c_dense + 2 * batch * ssp[0] * ssp[1] * ssp[2] * c_strided + 4 * c_dense * c_strided * taps,
                         2 * V * c_dense * c_strided * taps):
@@ -922,11 +925,14 @@ def conv_wgrad_bf16(dy_tok: torch.Tensor, x_tok: torch.Tensor, batch: int, spati
     D, H, W = sp
     taps = ks[0] * ks[1] * ks[2]
     cs = (cin + 3) // 4 * 4                                     # 16-byte rows: the split-K reduction uses vector reds
-    dw = torch.zeros((cout, taps, cs), device=x_tok.device, dtype=torch.float32)
+    # split-K accumulator: allocated on the current stream, zero-filled on the side stream when there is one
+    dw = (torch.empty if side is not None else torch.zeros)((cout, taps, cs), device=x_tok.device, dtype=torch.float32)
     use_halo = (CONV_HALO if halo is None else halo) and ks[1] in (1, 3) and ks[2] in (1, 3) and taps > 1
     fn = _lib.lib().nextou_conv3d_ndhwc_halo_wgrad if use_halo else _lib.lib().nextou_conv3d_ndhwc_wgrad
     V = batch * D * H * W
     with (side if side is not None else _null_ctx()):
+        if side is not None:
+            dw.zero_()
         with _lib.timed("wgrad_halo_tcgen05" if use_halo else "wgrad_tcgen05", 2 * V * (cin + cout) + 4 * cin * cout * taps,
                         2 * V * cin * cout * taps):
             check(fn(ptr(dy_tok), ll(dy_tok.stride(0)), ptr(x_tok), ll(x_tok.stride(0)), batch, D, H, W, cin, cout, ks[0], ks[1],
