@@ -118,7 +118,7 @@ struct KnnCfg {
   static constexpr int DS = BN + 4;  // distance tile row stride (floats)
   // the operand ring is dead while a chunk's top-K runs: the candidate arrays (+ thresholds, counters) live in it
   static constexpr size_t ring_floats = (size_t)KNN_STAGES * KNN_KC * (BM + BN);
-  static constexpr size_t cand_floats = 2 * ((size_t)BM * KNN_CAP + BM);
+  static constexpr size_t cand_floats = 2 * (size_t)BM * KNN_CAP + 3 * (size_t)BM;
   static constexpr size_t smem_bytes =
       sizeof(float) * ((ring_floats > cand_floats ? ring_floats : cand_floats) + (size_t)BM * DS + 2 * (size_t)BM * 32);
 };
@@ -189,7 +189,7 @@ __device__ __forceinline__ void warp_row_topk(const float* __restrict__ Ds, int 
   }
 }
 
-// LK = 8 / 16 / 32: register list length of the per-row threshold search (>= k * dilation)
+// LK = 8 / 16 / 24 / 32: register list length of the per-row threshold search (>= k * dilation)
 template <int BM, int BN, int TM, int TN, int LK>
 __global__ void __launch_bounds__(KnnCfg<BM, BN, TM, TN>::NT, (TM * TN <= 32 ? 2 : 1))
     knn_topk_kernel(const float* __restrict__ xn, const float* __restrict__ sqx, int ldn,
@@ -211,6 +211,7 @@ __global__ void __launch_bounds__(KnnCfg<BM, BN, TM, TN>::NT, (TM * TN <= 32 ? 2
   int* Ci = reinterpret_cast<int*>(Cd + BM * KNN_CAP);  //                                   index
   float* Thr = reinterpret_cast<float*>(Ci + BM * KNN_CAP);   // [BM] row threshold = K-th smallest distance so far
   int* Cnt = reinterpret_cast<int*>(Thr + BM);                // [BM] candidates <= threshold
+  int* New = Cnt + BM;                                        // [BM] ... of which from this chunk (0: the running list stands)
 
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int tx = tid % TX, ty = tid / TX;
@@ -403,6 +404,23 @@ __global__ void __launch_bounds__(KnnCfg<BM, BN, TM, TN>::NT, (TM * TN <= 32 ? 2
     //     A thread walks its segment rotated by (row / 8) % 4 columns: DS = 172 maps 8 consecutive rows to banks 4 apart.
     const bool first = (j0 == jbeg);
     const float INF = __int_as_float(0x7f800000);
+    constexpr int NFULL = NT / 32;
+    // a CTA that walks MANY chunks (one global graph of 21 952 tokens = 172 chunks): after the first few almost no row changes
+    // any more, and the warp-per-row path (one ballot per 32 candidates, nothing else when none beats the K-th best) is cheaper
+    // than the block-wide steps below
+    const bool warp_path = (j0 - jbeg) >= 8 * BN;
+    if (warp_path) {
+      if (warp < NFULL) {
+        for (int row = warp; row < BM; row += NFULL) {
+          if (i0 + row >= N) continue;
+          float td = Ld[row * 32 + lane];
+          int ti = Li[row * 32 + lane];
+          warp_row_topk<BN, DS>(Ds, row, j0, M, K, lane, td, ti);
+          Ld[row * 32 + lane] = td;
+          Li[row * 32 + lane] = ti;
+        }
+      }
+    } else {
     {
       constexpr int TPR = (NT / BM >= 4) ? 4 : (NT / BM >= 2 ? 2 : 1);
       constexpr int SEG = (BN + TPR - 1) / TPR;
@@ -434,8 +452,17 @@ __global__ void __launch_bounds__(KnnCfg<BM, BN, TM, TN>::NT, (TM * TN <= 32 ? 2
         }
       };
       if (active) {
-        if (!first && part == 0)
-          for (int q = 0; q < K; ++q) push(Ld[row * 32 + q]);
+        // later chunks: the running list (sorted, K entries) seeds thread 0's list directly; the other threads of the row only
+        // look at values below the running K-th best `cap` (a value >= cap cannot lower the K-th smallest value, and ties with
+        // it are collected by step (2) from the distance tile itself)
+        float cap = INF;
+        if (!first) {
+          cap = Ld[row * 32 + K - 1];
+          if (part == 0) {
+#pragma unroll
+            for (int p = 0; p < LK; ++p) lst[p] = (p >= LK - K) ? Ld[row * 32 + p - (LK - K)] : -INF;
+          }
+        }
         const int c0 = part * SEG;
         const int len = min(SEG, BN - c0);
         const int skew = (row >> 3) & 3;
@@ -444,7 +471,8 @@ __global__ void __launch_bounds__(KnnCfg<BM, BN, TM, TN>::NT, (TM * TN <= 32 ? 2
         for (int c = 0; c < len; ++c) {
           int col = c + skew;
           col -= (col >= len) ? len : 0;
-          push(drow[col]);
+          const float v = drow[col];
+          if (v < cap) push(v);
         }
       }
       if constexpr (TPR == 4) {
@@ -461,6 +489,7 @@ __global__ void __launch_bounds__(KnnCfg<BM, BN, TM, TN>::NT, (TM * TN <= 32 ? 2
       if (active && part == 0) {
         Thr[row] = lst[LK - 1];
         Cnt[row] = 0;
+        New[row] = 0;
       }
     }
     __syncthreads();
@@ -469,6 +498,7 @@ __global__ void __launch_bounds__(KnnCfg<BM, BN, TM, TN>::NT, (TM * TN <= 32 ? 2
       const int row = e / BN, col = e - row * BN;
       const float d = Ds[row * DS + col];
       if (d <= Thr[row] && j0 + col < M && i0 + row < N) {
+        New[row] = 1;
         const int pos = atomicAdd(&Cnt[row], 1);
         if (pos < KNN_CAP) {
           Cd[row * KNN_CAP + pos] = d;
@@ -477,8 +507,10 @@ __global__ void __launch_bounds__(KnnCfg<BM, BN, TM, TN>::NT, (TM * TN <= 32 ? 2
       }
     }
     if (!first) {
+      __syncthreads();                       // New[] is complete
       for (int e = tid; e < BM * 32; e += NT) {
         const int row = e >> 5;
+        if (New[row] == 0) continue;         // nothing in this chunk reaches the row's list
         const float d = Ld[e];
         const int ci = Li[e];
         if ((e & 31) < K && ci != INT_MAX && d <= Thr[row]) {
@@ -495,7 +527,7 @@ __global__ void __launch_bounds__(KnnCfg<BM, BN, TM, TN>::NT, (TM * TN <= 32 ? 2
     for (int e = tid; e < BM * 32; e += NT) {
       const int row = e >> 5;
       const int cnt = Cnt[row];
-      if (cnt > KNN_CAP) continue;                 // slow path below
+      if (cnt > KNN_CAP || New[row] == 0) continue;   // slow path below / list unchanged
       const float* cd = Cd + row * KNN_CAP;
       const int* cx = Ci + row * KNN_CAP;
       for (int a = e & 31; a < cnt; a += 32) {
@@ -510,10 +542,9 @@ __global__ void __launch_bounds__(KnnCfg<BM, BN, TM, TN>::NT, (TM * TN <= 32 ? 2
       }
     }
     // rows with more than KNN_CAP candidates at or below the threshold (massive distance ties): one full warp per row
-    constexpr int NFULL = NT / 32;
     if (warp < NFULL) {
       for (int row = warp; row < BM; row += NFULL) {
-        if (Cnt[row] <= KNN_CAP) continue;
+        if (Cnt[row] <= KNN_CAP || New[row] == 0) continue;
         float td = first ? INF : Ld[row * 32 + lane];
         int ti = first ? INT_MAX : Li[row * 32 + lane];
         warp_row_topk<BN, DS>(Ds, row, j0, M, K, lane, td, ti);
@@ -521,6 +552,7 @@ __global__ void __launch_bounds__(KnnCfg<BM, BN, TM, TN>::NT, (TM * TN <= 32 ? 2
         Li[row * 32 + lane] = ti;
       }
     }
+    }   // !warp_path
     __syncthreads();
     if (j0 + BN >= jend) {
       for (int e = tid; e < BM * 32; e += NT) {
@@ -574,7 +606,7 @@ static int launch_topk(const float* xn, const float* sqx, int ldn, const float* 
   using Cfg = KnnCfg<BM, BN, TM, TN>;
   const int K = k * dilation;
   auto kern = K <= 8 ? knn_topk_kernel<BM, BN, TM, TN, 8> : K <= 16 ? knn_topk_kernel<BM, BN, TM, TN, 16>
-                                                                      : knn_topk_kernel<BM, BN, TM, TN, 32>;
+              : K <= 24 ? knn_topk_kernel<BM, BN, TM, TN, 24> : knn_topk_kernel<BM, BN, TM, TN, 32>;
   int rc = ensure_smem(kern, Cfg::smem_bytes);
   if (rc) return rc;
   dim3 grid((N + BM - 1) / BM, B, msplit);
