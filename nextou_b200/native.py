@@ -62,9 +62,11 @@ def _complete_wgrad(side, param, finish, keep):
     it before the backward pass ends.  Then `finish` runs on the SIDE stream as well, the operands (`keep`) stay referenced,
     and one join at the end of the backward pass (engine callback) orders everything before the optimizer.  The main stream
     goes straight on to the previous layer's normalisation backward, which is HBM bound and co-resides with the
-    tensor-bound weight-gradient CTAs.  Gradient accumulation (param.grad already set), DistributedDataParallel /
-    GradientAllReducer buckets and hooks take the default path."""
+    tensor-bound weight-gradient CTAs.  Gradient accumulation (param.grad already set), DistributedDataParallel and foreign
+    hooks take the default path; parallel.GradientAllReducer's hook is stream-safe (it copies behind the side stream)."""
     hooks = getattr(param, "_post_accumulate_grad_hooks", None) if param is not None else None
+    if hooks and all(getattr(h, "_nextou_stream_safe", False) for h in hooks.values()):
+        hooks = None       # e.g. parallel.GradientAllReducer: bookkeeping on the host, its copies run behind the side stream
     if not (ops.DEFER_WGRAD_JOIN and param is not None and param.grad is None and not hooks and not torch.is_grad_enabled()):
         side.join()
         return finish()

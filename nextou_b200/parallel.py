@@ -17,6 +17,16 @@ import torch.distributed as dist
 
 
 class GradientAllReducer:
+    """Flat fp32 gradient buckets + one asynchronous all-reduce per bucket, overlapped with the backward pass.
+
+    During the backward pass param.grad is whatever autograd produces (so nextou_b200's weight-gradient kernels can stay on
+    their side stream, native._complete_wgrad).  As soon as every parameter of a bucket has its gradient, ONE multi-tensor
+    copy moves them into the bucket and the bucket's all-reduce starts — both enqueued on the side stream, i.e. behind the
+    weight-gradient kernels that write those gradients and behind everything the main stream had enqueued.  all_reduce()
+    finishes the exchange and re-binds every param.grad to its (averaged) slice of the buckets, so the optimizer reads the same
+    addresses every step (CUDA-graph friendly).  zero_grad() drops the gradients; accumulation over several backward passes
+    is not supported (nnU-Net does not use it)."""
+
     def __init__(self, params: Iterable[torch.nn.Parameter], world_size: int, bucket_mb: float = 32.0,
                  overlap: bool = True):
         self.world = world_size
@@ -27,6 +37,7 @@ class GradientAllReducer:
         self.buckets: List[torch.Tensor] = []
         self._bucket_of = {}
         self._slices = {}
+        self._views = {}
         cur, cur_n = [], 0
         groups = []
         for p in order:
@@ -44,10 +55,13 @@ class GradientAllReducer:
             for p in grp:
                 self._bucket_of[p] = b
                 self._slices[p] = (off, off + p.numel())
+                self._views[p] = flat[off:off + p.numel()].view_as(p)
                 off += p.numel()
             self.buckets.append(flat)
+        self._groups = groups
         self._pending = [0] * len(self.buckets)
         self._sizes = [len(g) for g in groups]
+        self._launched = set()
         self._handles = []
         # NCCL averages inside the collective (ncclAvg); gloo has no AVG: sum, then one scaling pass over the buckets
         self._avg = world_size > 1 and dist.is_initialized() and dist.get_backend() == "nccl"
@@ -60,39 +74,58 @@ class GradientAllReducer:
     def attach(self):
         """(Re)bind every param.grad to its slice of the flat buckets."""
         for p in self.params:
-            a, b = self._slices[p]
-            p.grad = self.buckets[self._bucket_of[p]][a:b].view_as(p)
+            p.grad = self._views[p]
 
     def zero_grad(self):
-        for flat in self.buckets:
-            flat.zero_()
-        self.attach()
+        for p in self.params:
+            p.grad = None
         self._pending = [0] * len(self.buckets)
+        self._launched = set()
         self._handles = []
 
     def _on_grad_ready(self, p):
+        # host-side bookkeeping only: nothing here reads the gradient on the current stream (see native._complete_wgrad)
         b = self._bucket_of[p]
         self._pending[b] += 1
         if self._pending[b] == self._sizes[b]:
-            self._handles.append(dist.all_reduce(self.buckets[b], op=self._op, async_op=True))
+            self._launch(b)
+    _on_grad_ready._nextou_stream_safe = True
+
+    def _launch(self, b: int):
+        """Gradients of bucket b -> the flat bucket (one multi-tensor copy; parameters without a gradient get zeros), then its
+        asynchronous all-reduce."""
+        flat = self.buckets[b]
+        have = [p for p in self._groups[b] if p.grad is not None]
+        missing = [p for p in self._groups[b] if p.grad is None]
+
+        def body():
+            if have:
+                torch._foreach_copy_([self._views[p] for p in have], [p.grad.to(torch.float32) for p in have])
+            for p in missing:
+                self._views[p].zero_()
+            if self.world > 1:
+                self._handles.append(dist.all_reduce(flat, op=self._op, async_op=True))
+        if flat.is_cuda:
+            from . import ops
+            with ops.side_launch(flat.device):   # the side stream first waits for the current one, then runs copy + collective
+                body()
+        else:
+            body()
+        self._launched.add(b)
 
     def all_reduce(self):
-        """Finish the step's gradient exchange: afterwards every param.grad holds the mean over ranks."""
-        if self.world <= 1:
-            return
-        launched = len(self._handles)
-        if not self.overlap or launched != len(self.buckets):
-            # parameters without a gradient this step (or overlap disabled): reduce what has not been launched
-            done = {i for i in range(len(self.buckets)) if self.overlap and self._pending[i] == self._sizes[i]}
-            for i, flat in enumerate(self.buckets):
-                if i not in done:
-                    self._handles.append(dist.all_reduce(flat, op=self._op, async_op=True))
+        """Finish the step's gradient exchange: afterwards every param.grad is its slice of the buckets and holds the mean
+        over ranks."""
+        for b in range(len(self.buckets)):
+            if b not in self._launched:      # overlap disabled, or parameters that received no gradient this step
+                self._launch(b)
         for h in self._handles:
             h.wait()
         self._handles = []
         self._pending = [0] * len(self.buckets)
-        if not self._avg:
+        if self.world > 1 and not self._avg:
             torch._foreach_mul_(self.buckets, 1.0 / self.world)
+        self.attach()
 
 
 class PeerExchange:
