@@ -158,6 +158,44 @@ def check_gradient_parity(rank, world, dev, log):
     return ok
 
 
+def check_deferred_join_ddp(rank, world, dev, log):
+    """bf16 data-parallel step of the full-size network: gradients with the weight-gradient join deferred to the end of the
+    backward pass (native._complete_wgrad + GradientAllReducer's side-stream bucket copies) == gradients with a join per layer."""
+    import bench
+    from nextou_b200 import ops
+    from nextou_b200.factory import build_nextou
+    from nextou_b200.parallel import GradientAllReducer
+    model = torch.nn.SyncBatchNorm.convert_sync_batchnorm(build_nextou(bench.CFG, seed=0)).to(dev).train()
+    x, _ = bench.synthetic_batch(rank)
+    x = x.to(dev)
+    params = [p for p in model.parameters() if p.requires_grad]
+    names = [n for n, p in model.named_parameters() if p.requires_grad]
+    red = GradientAllReducer(params, world)
+
+    def grads(defer):
+        ops.DEFER_WGRAD_JOIN = defer
+        red.zero_grad()
+        with torch.autocast("cuda", dtype=torch.bfloat16):
+            outs = model(x)
+        sum(o.float().square().mean() for o in outs).backward()
+        red.all_reduce()
+        torch.cuda.synchronize()
+        return [p.grad.detach().clone() for p in params]
+
+    def worst(a, b):
+        return max((float((u - v).norm() / v.norm().clamp_min(1e-20)), n) for n, u, v in zip(names, a, b))
+    base = grads(False)
+    noise = worst(grads(False), base)[0]
+    ok = True
+    for r in range(2):
+        e, n = worst(grads(True), base)
+        good = e <= max(20 * noise, 1e-4)
+        ok = ok and good
+        log(f"deferred join, {world} ranks, bf16, run {r}: worst {n} {e:.2e} (joined vs joined {noise:.2e}) " + ("OK" if good else "FAIL"))
+    ops.DEFER_WGRAD_JOIN = True
+    return ok
+
+
 def main():
     rank, world, local = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"]), int(os.environ["LOCAL_RANK"])
     torch.cuda.set_device(local)
@@ -167,7 +205,7 @@ def main():
     def log(msg):
         if rank == 0:
             print(msg, flush=True)
-    which = sys.argv[1:] or ["syncbn", "dice", "grads"]
+    which = sys.argv[1:] or ["syncbn", "dice", "grads", "defer"]
     ok = True
     if "syncbn" in which:
         ok = check_syncbn(rank, world, dev, log) and ok
@@ -175,6 +213,8 @@ def main():
         ok = check_batch_dice(rank, world, dev, log) and ok
     if "grads" in which:
         ok = check_gradient_parity(rank, world, dev, log) and ok
+    if "defer" in which:
+        ok = check_deferred_join_ddp(rank, world, dev, log) and ok
     t = torch.tensor([1.0 if ok else 0.0], device=dev)
     dist.all_reduce(t, op=dist.ReduceOp.MIN)
     log("ALL CHECKS PASSED" if float(t) == 1.0 else "SOME CHECK FAILED")
