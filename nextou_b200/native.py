@@ -52,6 +52,11 @@ def _flush_pending(device):
     _PendingWgrads.armed = False
 
 
+def _data_parallel() -> bool:
+    import torch.distributed as dist
+    return dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1
+
+
 def _complete_wgrad(side, param, finish, keep):
     """Finish a side-stream weight gradient: `finish()` turns the kernel's raw fp32 accumulator into the gradient tensor
     (layout copy, gap / group slicing).
@@ -65,8 +70,13 @@ def _complete_wgrad(side, param, finish, keep):
     tensor-bound weight-gradient CTAs.  Gradient accumulation (param.grad already set), DistributedDataParallel and foreign
     hooks take the default path; parallel.GradientAllReducer's hook is stream-safe (it copies behind the side stream)."""
     hooks = getattr(param, "_post_accumulate_grad_hooks", None) if param is not None else None
-    if hooks and all(getattr(h, "_nextou_stream_safe", False) for h in hooks.values()):
-        hooks = None       # e.g. parallel.GradientAllReducer: bookkeeping on the host, its copies run behind the side stream
+    ours = bool(hooks) and all(getattr(h, "_nextou_stream_safe", False) for h in hooks.values())
+    if ours:
+        hooks = None       # parallel.GradientAllReducer: bookkeeping on the host, its copies run behind the side stream
+    elif _data_parallel():
+        # a process group without our reducer on this parameter: torch's DistributedDataParallel hooks the AccumulateGrad NODE
+        # (invisible from here) and copies the gradient into its bucket on the main stream right away -> join per layer
+        hooks = True
     if not (ops.DEFER_WGRAD_JOIN and param is not None and param.grad is None and not hooks and not torch.is_grad_enabled()):
         side.join()
         return finish()
