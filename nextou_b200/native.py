@@ -43,13 +43,13 @@ def _fork_wgrad(ctx, tensor):
 class _PendingWgrads:
     """Weight-gradient kernels of the running backward pass that the main stream has not waited for yet."""
     keep = []          # tensors / closures the side-stream kernels still read or write
-    armed = False      # end-of-backward callback queued
+    task = None        # autograd graph task whose end-of-backward callback is queued
 
 
 def _flush_pending(device):
     torch.cuda.current_stream(device).wait_stream(ops.side_launch(device).side)
     _PendingWgrads.keep.clear()        # only now may the caching allocator hand these blocks to main-stream tensors
-    _PendingWgrads.armed = False
+    _PendingWgrads.task = None
 
 
 def _data_parallel() -> bool:
@@ -87,11 +87,14 @@ def _complete_wgrad(side, param, finish, keep):
     if dw.numel() != param.numel() or not param.is_contiguous():     # AccumulateGrad would copy it on the main stream: wait first
         side.join()
         return dw
-    _PendingWgrads.keep.append((keep, finish))
-    if not _PendingWgrads.armed:
-        _PendingWgrads.armed = True
-        device = dw.device
+    device = dw.device
+    task = torch._C._current_graph_task_id()
+    if _PendingWgrads.task != task:
+        if _PendingWgrads.keep:            # a backward pass that raised before its callback ran: settle it now
+            _flush_pending(device)
+        _PendingWgrads.task = task
         torch.autograd.Variable._execution_engine.queue_callback(lambda: _flush_pending(device))
+    _PendingWgrads.keep.append((keep, finish))
     return dw
 
 
